@@ -1,0 +1,132 @@
+/* oprl_b200 -- C ABI of the B200-native off-policy update engine.
+ *
+ * The reference (schatty/oprl) has no FFI: its hot path is three duck-typed Python
+ * protocols.  This header is the boundary a maintainer would bind (ctypes / cffi)
+ * to replace that path; each entry point cites the reference interface it stands
+ * in for (paths relative to the reference root).
+ *
+ *   ReplayBufferProtocol.sample      src/oprl/buffers/protocols.py:19-21,
+ *                                    src/oprl/buffers/episodic_buffer.py:114-133
+ *   AlgorithmProtocol.update         src/oprl/algos/protocols.py:31-38,
+ *                                    src/oprl/algos/{ddpg.py:61-107,td3.py:71-146,
+ *                                    sac.py:75-155,tqc.py:116-189}
+ *   AlgorithmProtocol.create         src/oprl/algos/protocols.py:27 (parameter/optimizer state)
+ *   soft_update                      src/oprl/algos/nn_functions.py:5-10
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success
+ * and a negative code on failure with a message in oprl_last_error() (thread
+ * local).  Device memory for parameters, optimizer state, replay storage and the
+ * sampled batch is owned by the caller (e.g. torch tensors) and only borrowed;
+ * the engine owns its activation workspace.  All work is enqueued on the
+ * engine's stream; oprl_sync() or a scalar read-back waits for it.
+ */
+#ifndef OPRL_B200_H_
+#define OPRL_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct oprl_engine oprl_engine;
+
+enum { OPRL_ALGO_DDPG = 0, OPRL_ALGO_TD3 = 1, OPRL_ALGO_SAC = 2, OPRL_ALGO_TQC = 3 };
+/* GEMM arithmetic: 3xTF32 on tcgen05 is fp32-accurate (parity mode); single-pass TF32
+ * is the labelled fast mode; SIMT is the FFMA cross-check of the same data path. */
+enum { OPRL_GEMM_TC_3XTF32 = 0, OPRL_GEMM_TC_TF32 = 1, OPRL_GEMM_SIMT = 2 };
+enum { OPRL_NET_ACTOR = 0, OPRL_NET_CRITIC = 1 };
+/* oprl_update flags */
+enum { OPRL_UPDATE_ACTOR = 1 /* also run the actor step + Polyak updates */ };
+/* oprl_update segments (multi-GPU learners all-reduce the gradient arena between them) */
+enum {
+  OPRL_SEG_ALL = -1,
+  OPRL_SEG_CRITIC_GRAD = 0, /* target-Q, critic forward/backward -> critic gradient arena */
+  OPRL_SEG_CRITIC_STEP_ACTOR_GRAD = 1, /* critic Adam(+Polyak), actor forward/backward */
+  OPRL_SEG_ACTOR_STEP = 2 /* actor Adam (+Polyak), temperature step */
+};
+
+typedef struct oprl_cfg {
+  int algo;          /* OPRL_ALGO_* */
+  int state_dim;     /* ddpg.py:19 */
+  int action_dim;    /* ddpg.py:20 */
+  int actor_hidden;  /* 256: ddpg.py:43 */
+  int actor_layers;  /* 2 hidden layers */
+  int critic_hidden; /* 256: nn_models.py:31 ; TQC 512: tqc.py:49 */
+  int critic_layers; /* 2 ; TQC 3 */
+  int n_critics;     /* DDPG 1, TD3/SAC 2, TQC n_nets (tqc.py:73) */
+  int n_quantiles;   /* TQC 25 (tqc.py:72), else 1 */
+  int top_quantiles_to_drop; /* tqc.py:71 */
+  int policy_freq;   /* td3.py:24 (host decides OPRL_UPDATE_ACTOR; informational) */
+  int tune_alpha;    /* sac.py:22 */
+  int gemm_mode;     /* OPRL_GEMM_* */
+  int device;        /* CUDA ordinal */
+  float gamma, tau, lr_actor, lr_critic, lr_alpha;
+  float policy_noise, noise_clip, max_action; /* td3.py:21-28 */
+  float alpha_init, target_entropy;           /* sac.py:27,70 */
+  unsigned long long seed;
+} oprl_cfg;
+
+typedef struct oprl_state { /* optimizer / RNG counters for checkpoint + tests */
+  unsigned long long tick;
+  int step_actor, step_critic, step_alpha, pad;
+  double log_alpha, m_alpha, v_alpha;
+} oprl_state;
+
+const char* oprl_last_error(void);
+int oprl_abi_version(void);
+
+int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out);
+void oprl_engine_destroy(oprl_engine* e);
+
+/* Number of fp32 elements of a network group's flat parameter arena, laid out
+ * exactly as torch's parameters() of the reference module: per net, per layer,
+ * weight [out,in] then bias [out] (nn_models.py:98-104). */
+long long oprl_engine_arena_floats(const oprl_engine* e, int net);
+/* Borrow the caller's flat device arrays (each `arena_floats` long).  theta_target
+ * may be NULL for groups without a target network (SAC/TQC actor). */
+int oprl_engine_bind_arena(oprl_engine* e, int net, float* theta, float* grad, float* m,
+                           float* v, float* theta_target);
+/* Re-derive the engine's tiled tf32 operand copies after the caller edited theta /
+ * theta_target (load_state_dict, initial weights). */
+int oprl_engine_sync_params(oprl_engine* e);
+
+/* Replay storage (device pointers), shapes as episodic_buffer.py:29-55:
+ * states [E, L+1, S], actions [E, L, A], rewards [E, L, 1], dones [E, L, 1]. */
+int oprl_buffer_bind(oprl_engine* e, const float* states, const float* actions,
+                     const float* rewards, const float* dones, int E, int L);
+/* Host prefix sums of episode lengths (n_eps + 1 ints) for on-device index sampling. */
+int oprl_buffer_set_prefix(oprl_engine* e, const int* prefix_host, int n_eps);
+/* Row-major batch arrays the gather writes (what sample() returns): device pointers
+ * s [cap,S], a [cap,A], r [cap], d [cap], s2 [cap,S]. */
+int oprl_batch_bind(oprl_engine* e, float* s, float* a, float* r, float* d, float* s2, int cap);
+
+/* sample(): gather B transitions.  ep_step_host = B (episode, step) int pairs chosen
+ * by the host (reference RNG parity), or NULL to draw uniformly on the device. */
+int oprl_sample(oprl_engine* e, const int* ep_step_host, int B);
+/* Generic path: load a caller-provided dense device batch instead of gathering. */
+int oprl_load_batch(oprl_engine* e, const float* s, const float* a, const float* r,
+                    const float* d, const float* s2, int B);
+/* Inject the standard-normal draws of the next update (parity tests).  which = 0:
+ * first draw of the update (TD3 smoothing noise / SAC-TQC next-action noise),
+ * 1: second draw (SAC-TQC actor-step noise).  noise: device pointer [B, A]. */
+int oprl_set_noise(oprl_engine* e, int which, const float* noise_dev, int n);
+
+/* update(): one gradient update on the batch last sampled / loaded. */
+int oprl_update(oprl_engine* e, int flags, int segment);
+/* Fused device-resident learner step: on-device sampling + update in one graph. */
+int oprl_step(oprl_engine* e, int B, int flags);
+
+/* Logging scalars (synchronises the stream):
+ * 0 critic_loss 1 actor_loss 2 alpha_loss 3 mean q 4 mean q_target 5 mean logpi
+ * 6 mean (q - q_target) 7 alpha */
+int oprl_get_scalars(oprl_engine* e, float* out_host, int n);
+int oprl_get_state(oprl_engine* e, oprl_state* out);
+int oprl_set_state(oprl_engine* e, const oprl_state* in);
+int oprl_sync(oprl_engine* e);
+void* oprl_stream(oprl_engine* e); /* cudaStream_t */
+/* number of kernel launches one oprl_update(flags, OPRL_SEG_ALL) enqueues */
+int oprl_update_launches(oprl_engine* e, int flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPRL_B200_H_ */

@@ -1,0 +1,354 @@
+// SIMT kernels around the GEMM chain: replay-buffer gather (K0 in SURVEY.md §2b),
+// TD target + MSE seed gradient (K3/K4), fused Adam + Polyak + tf32 re-tiling
+// (K6/K9/K10), per-update prologue (counters + noise).  All HBM/latency bound.
+#pragma once
+#include <curand_kernel.h>
+#include "gemm.cuh"
+
+namespace oprl {
+
+struct TM {  // CT32 tiled matrix, tf32 hi/lo halves
+  float* hi;
+  float* lo;
+  int rows;  // padded
+  int cols;  // padded
+};
+
+// Engine scalars that live on the device so a captured CUDA graph can replay.
+struct DevState {
+  unsigned long long tick;  // number of updates started (noise stream offset)
+  int step[4];              // Adam step counts: 0 actor, 1 critic, 2 alpha
+  int use_ext_noise;        // 1: caller supplied noise for this update, skip generation
+  int pad0;
+  double log_alpha, m_alpha, v_alpha;  // SAC/TQC temperature, float64 like the reference
+  float alpha;                         // exp(log_alpha) rounded to fp32
+  float pad1;
+  float scalars[32];  // 0 critic_loss, 1 actor_loss, 2 alpha_loss, 3 mean q, 4 mean q_target, 5 mean logpi
+};
+
+enum Scalar : int {
+  SC_CRITIC_LOSS = 0,
+  SC_ACTOR_LOSS = 1,
+  SC_ALPHA_LOSS = 2,
+  SC_Q_MEAN = 3,
+  SC_QT_MEAN = 4,
+  SC_LOGPI_MEAN = 5,
+  SC_Q_ERR_MEAN = 6,
+};
+
+__device__ __forceinline__ void store_tiled(const TM& t, int r, int c, float x) {
+  float hi, lo;
+  ptx::split_tf32(x, hi, lo);
+  const size_t off = ct_index(t.rows, r, c);
+  t.hi[off] = hi;
+  t.lo[off] = lo;
+}
+
+// ------------------------------------------------------------------ prologue
+// One block.  Bumps the update tick and Adam step counters (so that every later
+// kernel of the same graph replay reads the new values) and draws the standard
+// normal noise of this update with Philox unless the caller injected its own.
+struct NoiseSpec {
+  float* dst;   // [n]
+  int n;
+  float scale;  // TD3: policy_noise ; SAC/TQC: 1
+  float clip;   // TD3: noise_clip ; <= 0: no clip
+};
+__global__ void prologue_kernel(DevState* st, int bump_actor, int bump_critic, int bump_alpha,
+                                NoiseSpec n0, NoiseSpec n1, unsigned long long seed) {
+  const unsigned long long tick = st->tick;
+  const int ext = st->use_ext_noise;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st->tick = tick + 1;
+    st->step[0] += bump_actor;
+    st->step[1] += bump_critic;
+    st->step[2] += bump_alpha;
+    st->use_ext_noise = 0;
+  }
+  if (ext) return;
+  const int total = n0.n + n1.n;
+  for (int base = threadIdx.x * 4; base < total; base += blockDim.x * 4) {
+    curandStatePhilox4_32_10_t rng;
+    curand_init(seed, static_cast<unsigned long long>(base >> 2), tick * 8ull, &rng);
+    const float4 z = curand_normal4(&rng);
+    const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = base + k;
+      if (i >= total) break;
+      const NoiseSpec& s = (i < n0.n) ? n0 : n1;
+      const int j = (i < n0.n) ? i : i - n0.n;
+      float v = zz[k] * s.scale;
+      if (s.clip > 0.f) v = fminf(fmaxf(v, -s.clip), s.clip);
+      s.dst[j] = v;
+    }
+  }
+}
+
+// -------------------------------------------------------------------- gather
+// Reference: EpisodicReplayBuffer.sample, episodic_buffer.py:123-133 -- five
+// advanced-index gathers; next_state = states[ep, step + 1] is the adjacent row.
+struct GatherArgs {
+  // sources: replay storage (gathered) or dense user batch (dense = 1)
+  const float* states;   // [E, L+1, S]   | dense: [B, S]
+  const float* actions;  // [E, L, A]     | dense: [B, A]
+  const float* rewards;  // [E, L, 1]     | dense: [B]
+  const float* dones;    // [E, L, 1]     | dense: [B]
+  const float* next_states;  // dense only: [B, S]
+  const int* ep_step;        // [B][2] (episode, step) pairs, or nullptr -> device sampling
+  const int* prefix;         // [n_eps + 1] transition prefix sums (device sampling)
+  int n_eps, n_trans;
+  int L, S, A, A4, B;
+  int dense;
+  unsigned long long seed;
+  // outputs
+  float *bs, *ba, *br, *bd, *bs2;  // row-major batch arena (nullable when dense)
+  int* out_ep_step;                 // [B][2] what was sampled (device sampling), nullable
+  TM X, XT, Xn, Xp;
+};
+
+__global__ void gather_kernel(GatherArgs g, const DevState* st) {
+  const int b = blockIdx.x;
+  __shared__ int s_ep, s_step;
+  if (threadIdx.x == 0) {
+    int ep = 0, step = 0;
+    if (!g.dense) {
+      if (g.ep_step) {
+        ep = g.ep_step[2 * b];
+        step = g.ep_step[2 * b + 1];
+      } else {
+        curandStatePhilox4_32_10_t rng;
+        curand_init(g.seed ^ 0x9E3779B97F4A7C15ull, static_cast<unsigned long long>(b), st->tick * 4ull, &rng);
+        const unsigned int u = curand(&rng);
+        int t = static_cast<int>((static_cast<unsigned long long>(u) * g.n_trans) >> 32);
+        int lo = 0, hi = g.n_eps;  // find ep with prefix[ep] <= t < prefix[ep+1]
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (g.prefix[mid] <= t) lo = mid; else hi = mid;
+        }
+        ep = lo;
+        step = t - g.prefix[lo];
+        if (g.out_ep_step) {
+          g.out_ep_step[2 * b] = ep;
+          g.out_ep_step[2 * b + 1] = step;
+        }
+      }
+    }
+    s_ep = ep;
+    s_step = step;
+  }
+  __syncthreads();
+  const int ep = s_ep, step = s_step;
+  const float* src_a;
+  const float* src_s;
+  const float* src_s2;
+  float r, d;
+  if (g.dense) {
+    src_a = g.actions + static_cast<size_t>(b) * g.A;
+    src_s = g.states + static_cast<size_t>(b) * g.S;
+    src_s2 = g.next_states + static_cast<size_t>(b) * g.S;
+    r = g.rewards[b];
+    d = g.dones[b];
+  } else {
+    const size_t row = static_cast<size_t>(ep) * g.L + step;
+    const size_t srow = static_cast<size_t>(ep) * (g.L + 1) + step;
+    src_a = g.actions + row * g.A;
+    src_s = g.states + srow * g.S;
+    src_s2 = src_s + g.S;
+    r = g.rewards[row];
+    d = g.dones[row];
+  }
+  const int W = g.A + 2 * g.S;
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    if (c < g.A) {
+      const float v = src_a[c];
+      if (g.ba) g.ba[static_cast<size_t>(b) * g.A + c] = v;
+      store_tiled(g.X, b, c, v);
+      store_tiled(g.XT, c, b, v);
+    } else if (c < g.A + g.S) {
+      const int j = c - g.A;
+      const float v = src_s[j];
+      if (g.bs) g.bs[static_cast<size_t>(b) * g.S + j] = v;
+      store_tiled(g.X, b, g.A4 + j, v);
+      store_tiled(g.XT, g.A4 + j, b, v);
+      store_tiled(g.Xp, b, g.A4 + j, v);
+    } else {
+      const int j = c - g.A - g.S;
+      const float v = src_s2[j];
+      if (g.bs2) g.bs2[static_cast<size_t>(b) * g.S + j] = v;
+      store_tiled(g.Xn, b, g.A4 + j, v);
+    }
+  }
+  if (threadIdx.x == 0) {
+    g.br[b] = r;
+    g.bd[b] = d;
+  }
+}
+
+// ---------------------------------------------------------------- block reduce
+template <int kThreads>
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  // fixed-shape tree -> bit-reproducible
+  sh[threadIdx.x] = v;
+  __syncthreads();
+#pragma unroll
+  for (int s = kThreads / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  const float r = sh[0];
+  __syncthreads();
+  return r;
+}
+
+// ------------------------------------------------------- TD target (DDPG / TD3)
+// Reference: ddpg.py:94-98, td3.py:95-112.
+//   y = r + ((1 - d) * gamma) * min_i q'_i ;  L = sum_i mean((q_i - y)^2)
+//   dL/dq_i = (1/B) * (2 * (q_i - y))
+// Writes the seed gradient as tiled [Bp x 32] matrices (column 0) + transposes,
+// the last-layer bias gradients, and the logging scalars.  One block.
+struct TdArgs {
+  const float* qn;  // [Bp x nq] target-critic outputs
+  const float* q;   // [Bp x nq] online critic outputs
+  const float* r;
+  const float* d;
+  const float* logpi_next;  // SAC: [Bp] log pi(a'|s') (nullable)
+  float gamma;
+  int B, nq;
+  TM D3[2];
+  TM D3T[2];
+  float* db3[2];  // gradient slot of each critic's output bias
+  float* y_out;   // [Bp] (nullable)
+};
+constexpr int kTdThreads = 256;
+__global__ void __launch_bounds__(kTdThreads) td_kernel(TdArgs a, DevState* st) {
+  __shared__ float sh[kTdThreads];
+  const float invB = 1.0f / static_cast<float>(a.B);
+  float loss[2] = {0.f, 0.f}, dsum[2] = {0.f, 0.f}, qsum = 0.f, ysum = 0.f, esum = 0.f;
+  const float alpha = st->alpha;
+  for (int m = threadIdx.x; m < a.B; m += kTdThreads) {
+    float qn = a.qn[static_cast<size_t>(m) * a.nq];
+    if (a.nq == 2) qn = fminf(qn, a.qn[static_cast<size_t>(m) * 2 + 1]);
+    if (a.logpi_next) qn = qn - alpha * a.logpi_next[m];
+    const float y = a.r[m] + ((1.0f - a.d[m]) * a.gamma) * qn;
+    if (a.y_out) a.y_out[m] = y;
+    ysum += y;
+    for (int i = 0; i < a.nq; ++i) {
+      const float q = a.q[static_cast<size_t>(m) * a.nq + i];
+      const float diff = q - y;
+      loss[i] += diff * diff;
+      const float dq = invB * (2.0f * diff);
+      dsum[i] += dq;
+      store_tiled(a.D3[i], m, 0, dq);
+      store_tiled(a.D3T[i], 0, m, dq);
+      if (i == 0) { qsum += q; esum += diff; }
+    }
+  }
+  float total = 0.f;
+  for (int i = 0; i < a.nq; ++i) {
+    const float l = block_sum<kTdThreads>(loss[i], sh);
+    const float ds = block_sum<kTdThreads>(dsum[i], sh);
+    total += l * invB;
+    if (threadIdx.x == 0) a.db3[i][0] = ds;
+  }
+  const float qs = block_sum<kTdThreads>(qsum, sh);
+  const float ys = block_sum<kTdThreads>(ysum, sh);
+  const float es = block_sum<kTdThreads>(esum, sh);
+  if (threadIdx.x == 0) {
+    st->scalars[SC_CRITIC_LOSS] = total;
+    st->scalars[SC_Q_MEAN] = qs * invB;
+    st->scalars[SC_QT_MEAN] = ys * invB;
+    st->scalars[SC_Q_ERR_MEAN] = es * invB;
+  }
+}
+
+// ------------------------------------------------ Adam + Polyak + tf32 re-tiling
+// Reference: torch.optim.Adam single-tensor path (ddpg.py:51,56,101,107) and the
+// Polyak loops (ddpg.py:72-84, nn_functions.py:5-10).  One pass over
+// [theta, g, m, v, theta_target]; also refreshes the CT32 hi/lo operand copies
+// (W and W^T, target W) that the GEMM kernel consumes.
+struct AdamSeg {
+  float* theta;
+  const float* grad;
+  float* m;
+  float* v;
+  float* target;  // nullable
+  float *w_hi, *w_lo;    // tiled [rows_pad x cols_pad] (nullable for biases)
+  float *wt_hi, *wt_lo;  // tiled transposed (nullable)
+  float *tw_hi, *tw_lo;  // tiled target weights (nullable)
+  int w_rows, wt_rows;   // padded row counts of the tiled copies
+  int n, rows, cols;     // row-major [rows x cols]
+  int split, off_lo, off_hi;  // tiled col = j < split ? j + off_lo : j - split + off_hi
+  int opt;                    // 0 actor, 1 critic
+};
+struct AdamHyper {
+  float lr[2];
+  float beta1, beta2, eps, tau;
+};
+constexpr int kAdamThreads = 256;
+// mode: bit0 = Adam step, bit1 = Polyak, bit2 = (re)tile online weights, bit3 = tile targets
+__global__ void __launch_bounds__(kAdamThreads)
+    adam_kernel(const AdamSeg* segs, AdamHyper hp, const DevState* st, int mode) {
+  const AdamSeg sg = segs[blockIdx.y];
+  __shared__ float s_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0 && (mode & 1)) {
+    const int t = st->step[sg.opt];
+    const double bc1 = 1.0 - pow(static_cast<double>(hp.beta1), static_cast<double>(t));
+    const double bc2 = 1.0 - pow(static_cast<double>(hp.beta2), static_cast<double>(t));
+    s_step_size = static_cast<float>(static_cast<double>(hp.lr[sg.opt]) / bc1);
+    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
+  }
+  __syncthreads();
+  const float w1 = 1.0f - hp.beta1;
+  const float w2 = 1.0f - hp.beta2;
+  for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.n; i += gridDim.x * kAdamThreads) {
+    float p = sg.theta[i];
+    if (mode & 1) {
+      const float g = sg.grad[i];
+      float m = sg.m[i];
+      float v = sg.v[i];
+      m = fmaf(w1, g - m, m);                              // exp_avg.lerp_(grad, 1 - beta1)
+      v = __fadd_rn(__fmul_rn(v, hp.beta2), __fmul_rn(__fmul_rn(w2, g), g));  // mul_().addcmul_()
+      const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s_bc2_sqrt), hp.eps);
+      p = __fadd_rn(p, __fmul_rn(-s_step_size, __fdiv_rn(m, denom)));       // addcdiv_
+      sg.m[i] = m;
+      sg.v[i] = v;
+      sg.theta[i] = p;
+    }
+    float tp = 0.f;
+    if (sg.target) {
+      tp = sg.target[i];
+      if (mode & 2) {
+        tp = __fadd_rn(__fmul_rn(hp.tau, p), __fmul_rn(1.0f - hp.tau, tp));
+        sg.target[i] = tp;
+      }
+    }
+    if (sg.w_hi) {
+      const int r = i / sg.cols;
+      const int j = i - r * sg.cols;
+      const int c = j < sg.split ? j + sg.off_lo : j - sg.split + sg.off_hi;
+      if (mode & 4) {
+        float hi, lo;
+        ptx::split_tf32(p, hi, lo);
+        const size_t o1 = ct_index(sg.w_rows, r, c);
+        sg.w_hi[o1] = hi;
+        sg.w_lo[o1] = lo;
+        if (sg.wt_hi) {
+          const size_t o2 = ct_index(sg.wt_rows, c, r);
+          sg.wt_hi[o2] = hi;
+          sg.wt_lo[o2] = lo;
+        }
+      }
+      if (sg.tw_hi && (mode & 8)) {
+        float hi, lo;
+        ptx::split_tf32(tp, hi, lo);
+        const size_t o1 = ct_index(sg.w_rows, r, c);
+        sg.tw_hi[o1] = hi;
+        sg.tw_lo[o1] = lo;
+      }
+    }
+  }
+}
+
+}  // namespace oprl

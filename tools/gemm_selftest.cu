@@ -1,0 +1,267 @@
+// Standalone GPU self-test for the tcgen05 3xTF32 GEMM (oprl_b200/csrc/gemm.cuh).
+// Checks the tensor-core and FFMA variants against an fp64 host reference
+// (row-major, tiled, transposed-tiled and column-sum outputs), prints an
+// in-kernel phase breakdown, and times stream / CUDA-graph launch chains.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo tools/gemm_selftest.cu -o build/gemm_selftest
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include "../oprl_b200/csrc/gemm.cuh"
+
+using namespace oprl;
+
+#define CK(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess) {                                                          \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+      exit(2);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+static float tf32_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+struct HostMat {  // logical [rows x cols] row-major + tiled device copies
+  int rows, cols;
+  std::vector<float> v;
+  float *d_hi = nullptr, *d_lo = nullptr;
+  void upload() {
+    std::vector<float> hi((size_t)rows * cols), lo((size_t)rows * cols);
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) {
+        float x = v[(size_t)r * cols + c];
+        float h = tf32_host(x);
+        float l = tf32_host(x - h);
+        hi[ct_index(rows, r, c)] = h;
+        lo[ct_index(rows, r, c)] = l;
+      }
+    CK(cudaMalloc(&d_hi, hi.size() * 4));
+    CK(cudaMalloc(&d_lo, lo.size() * 4));
+    CK(cudaMemcpy(d_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+  }
+};
+
+static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
+
+template <bool kSimt>
+static void launch(const GemmLaunch& L, cudaStream_t st = 0) {
+  int tiles = 0;
+  for (int i = 0; i < L.n_ops; ++i) tiles += gemm_tiles(L.op[i]);
+  gemm_kernel<kSimt><<<tiles, kGemmThreads, kGemmSmemBytes, st>>>(L);
+}
+
+static double run_case(int M, int N, int K, bool simt, int passes) {
+  HostMat A, B;
+  A.rows = M; A.cols = K; B.rows = N; B.cols = K;
+  A.v.resize((size_t)M * K);
+  B.v.resize((size_t)N * K);
+  for (auto& x : A.v) x = frand();
+  for (auto& x : B.v) x = frand();
+  A.upload();
+  B.upload();
+  std::vector<float> bias(N);
+  for (auto& x : bias) x = frand();
+  float *d_bias, *d_rm, *d_thi, *d_tlo, *d_tthi, *d_ttlo, *d_cs;
+  CK(cudaMalloc(&d_bias, N * 4));
+  CK(cudaMemcpy(d_bias, bias.data(), N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&d_rm, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_thi, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_tlo, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_tthi, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_ttlo, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_cs, (size_t)(M / 128) * N * 4));
+  CK(cudaMemset(d_rm, 0xff, (size_t)M * N * 4));
+
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_ops = 1;
+  GemmOp& o = L.op[0];
+  o.a_hi = A.d_hi; o.a_lo = A.d_lo; o.a_rows = M;
+  o.b_hi = B.d_hi; o.b_lo = B.d_lo; o.b_rows = N;
+  o.M = M; o.N = N; o.K = K;
+  o.bias = d_bias; o.bias_n = N; o.act = ACT_RELU;
+  o.t_hi = d_thi; o.t_lo = d_tlo; o.t_rows = M; o.t_c0 = 0; o.t_n = N;
+  o.tt_hi = d_tthi; o.tt_lo = d_ttlo; o.tt_rows = N;
+  o.rm = d_rm; o.rm_ld = N; o.rm_m = M; o.rm_n = N;
+  o.colsum = d_cs; o.colsum_ld = N;
+  o.passes = passes; o.alpha = 1.f;
+  if (simt) launch<true>(L); else launch<false>(L);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    printf("  kernel failed: %s\n", cudaGetErrorString(e));
+    exit(3);
+  }
+  size_t mn = (size_t)M * N;
+  std::vector<float> out(mn), thi(mn), tlo(mn), tthi(mn), ttlo(mn), cs((size_t)(M / 128) * N);
+  CK(cudaMemcpy(out.data(), d_rm, mn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(thi.data(), d_thi, mn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(tlo.data(), d_tlo, mn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(tthi.data(), d_tthi, mn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ttlo.data(), d_ttlo, mn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(cs.data(), d_cs, cs.size() * 4, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_terr = 0, max_tterr = 0, max_cerr = 0;
+  std::vector<double> colref((size_t)(M / 128) * N, 0.0);
+  for (int m = 0; m < M; ++m)
+    for (int n = 0; n < N; ++n) {
+      double acc = 0, mag = 0;
+      for (int k = 0; k < K; ++k) {
+        double a = A.v[(size_t)m * K + k];
+        double b = B.v[(size_t)n * K + k];
+        acc += a * b;
+        mag += fabs(a * b);
+      }
+      acc += bias[n];
+      if (acc < 0) acc = 0;
+      double got = out[(size_t)m * N + n];
+      double err = fabs(got - acc) / (mag + 1.0);
+      if (!(err <= max_err)) max_err = err;  // NaN-propagating
+      double tgot = (double)thi[ct_index(M, m, n)] + (double)tlo[ct_index(M, m, n)];
+      double terr = fabs(tgot - got) / (fabs(got) + 1e-3);
+      if (!(terr <= max_terr)) max_terr = terr;
+      double ttgot = (double)tthi[ct_index(N, n, m)] + (double)ttlo[ct_index(N, n, m)];
+      double tterr = fabs(ttgot - got) / (fabs(got) + 1e-3);
+      if (!(tterr <= max_tterr)) max_tterr = tterr;
+      colref[(size_t)(m / 128) * N + n] += got;
+    }
+  for (size_t i = 0; i < cs.size(); ++i) {
+    double ce = fabs(cs[i] - colref[i]) / (fabs(colref[i]) + 1.0);
+    if (!(ce <= max_cerr)) max_cerr = ce;
+  }
+  printf("  M=%d N=%d K=%d %s passes=%d: rel_err=%.3e tiled=%.3e ttiled=%.3e colsum=%.3e\n", M, N, K,
+         simt ? "SIMT" : "TC  ", passes, max_err, max_terr, max_tterr, max_cerr);
+  cudaFree(A.d_hi); cudaFree(A.d_lo); cudaFree(B.d_hi); cudaFree(B.d_lo);
+  cudaFree(d_bias); cudaFree(d_rm); cudaFree(d_thi); cudaFree(d_tlo); cudaFree(d_tthi);
+  cudaFree(d_ttlo); cudaFree(d_cs);
+  double worst = max_err;
+  if (!(max_terr < 1e-6)) worst = 1;
+  if (!(max_tterr < 1e-6)) worst = 1;
+  if (!(max_cerr < 1e-5)) worst = 1;
+  return worst;
+}
+
+static GemmLaunch make_bench(int nops, int M, int N, int K, int passes, bool tt) {
+  GemmLaunch L;
+  memset(&L, 0, sizeof(L));
+  L.n_ops = nops;
+  for (int i = 0; i < nops; ++i) {
+    float *a_hi, *a_lo, *b_hi, *b_lo, *t_hi, *t_lo, *tt_hi, *tt_lo;
+    CK(cudaMalloc(&a_hi, (size_t)M * K * 4)); CK(cudaMalloc(&a_lo, (size_t)M * K * 4));
+    CK(cudaMalloc(&b_hi, (size_t)N * K * 4)); CK(cudaMalloc(&b_lo, (size_t)N * K * 4));
+    CK(cudaMalloc(&t_hi, (size_t)M * N * 4)); CK(cudaMalloc(&t_lo, (size_t)M * N * 4));
+    CK(cudaMalloc(&tt_hi, (size_t)M * N * 4)); CK(cudaMalloc(&tt_lo, (size_t)M * N * 4));
+    CK(cudaMemset(a_hi, 0, (size_t)M * K * 4)); CK(cudaMemset(a_lo, 0, (size_t)M * K * 4));
+    CK(cudaMemset(b_hi, 0, (size_t)N * K * 4)); CK(cudaMemset(b_lo, 0, (size_t)N * K * 4));
+    GemmOp& o = L.op[i];
+    o.a_hi = a_hi; o.a_lo = a_lo; o.a_rows = M; o.b_hi = b_hi; o.b_lo = b_lo; o.b_rows = N;
+    o.M = M; o.N = N; o.K = K; o.act = ACT_RELU;
+    o.t_hi = t_hi; o.t_lo = t_lo; o.t_rows = M; o.t_n = N; o.passes = passes; o.alpha = 1.f;
+    if (tt) { o.tt_hi = tt_hi; o.tt_lo = tt_lo; o.tt_rows = N; }
+  }
+  return L;
+}
+
+static void spin_warm(const GemmLaunch& L, double ms_target) {
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0));
+  float ms = 0;
+  while (ms < ms_target) {
+    for (int i = 0; i < 200; ++i) launch<false>(L);
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+  }
+}
+
+static void bench(int nops, int M, int N, int K, int passes, bool simt, bool tt) {
+  GemmLaunch L = make_bench(nops, M, N, K, passes, tt);
+  if (!simt) spin_warm(L, 300.0);
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  const int iters = 2000;
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < iters; ++i) { if (simt) launch<true>(L); else launch<false>(L); }
+  CK(cudaEventRecord(e1));
+  CK(cudaEventSynchronize(e1));
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  double us = ms * 1e3 / iters;
+  double flop = 2.0 * M * N * K * nops;
+  printf("bench stream %s ops=%d M=%d N=%d K=%d passes=%d tt=%d: %.2f us/launch  %.2f TFLOP/s (algorithmic fp32)\n",
+         simt ? "SIMT" : "TC  ", nops, M, N, K, passes, (int)tt, us, flop / us * 1e-6);
+  if (simt) return;
+  // the same launch as a 20-node dependent chain inside a CUDA graph
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  cudaGraph_t g;
+  cudaGraphExec_t ge;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
+  for (int i = 0; i < 20; ++i) launch<false>(L, st);
+  CK(cudaStreamEndCapture(st, &g));
+  CK(cudaGraphInstantiate(&ge, g, 0));
+  for (int i = 0; i < 20; ++i) CK(cudaGraphLaunch(ge, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < 200; ++i) CK(cudaGraphLaunch(ge, st));
+  CK(cudaEventRecord(e1, st));
+  CK(cudaEventSynchronize(e1));
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  printf("bench graph  TC   (20-node chain): %.2f us/node\n", ms * 1e3 / (200 * 20));
+  // phase profile of CTA 0
+  long long* d_prof;
+  CK(cudaMalloc(&d_prof, 16 * 8));
+  CK(cudaMemset(d_prof, 0, 16 * 8));
+  GemmLaunch P = L;
+  P.prof = d_prof;
+  for (int i = 0; i < 3; ++i) launch<false>(P);
+  CK(cudaDeviceSynchronize());
+  long long h[16];
+  CK(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
+  double ns = (double)(h[10] - h[9]);
+  printf("  prof cycles: setup=%lld issue_all=%lld first_full=%lld last_commit=%lld accum=%lld tmem_ld=%lld epi_end=%lld exit=%lld | %.0f ns => %.0f MHz\n",
+         h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0],
+         h[8] - h[0], ns, (h[8] - h[0]) / ns * 1e3);
+}
+
+int main(int argc, char** argv) {
+  CK(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  CK(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  cudaDeviceProp p;
+  CK(cudaGetDeviceProperties(&p, 0));
+  printf("device %s sm_%d%d SMs=%d\n", p.name, p.major, p.minor, p.multiProcessorCount);
+
+  int fails = 0;
+  printf("== SIMT cross-check path (validates layout / copies / epilogue)\n");
+  if (!(run_case(256, 256, 256, true, 3) < 2e-6)) ++fails;
+  if (!(run_case(128, 32, 32, true, 3) < 2e-6)) ++fails;
+  printf("== tcgen05 path\n");
+  if (!(run_case(256, 256, 256, false, 3) < 2e-6)) ++fails;
+  if (!(run_case(256, 256, 256, false, 1) < 1e-3)) ++fails;
+  if (!(run_case(128, 32, 32, false, 3) < 2e-6)) ++fails;
+  if (!(run_case(256, 32, 256, false, 3) < 2e-6)) ++fails;
+  if (!(run_case(1024, 512, 96, false, 3) < 2e-6)) ++fails;
+  if (!(run_case(256, 512, 512, false, 3) < 2e-6)) ++fails;
+  printf("fails=%d\n", fails);
+
+  if (argc > 1 && atoi(argv[1]) == 0) return fails ? 1 : 0;
+  bench(1, 256, 256, 256, 3, false, false);
+  bench(3, 256, 256, 256, 3, false, false);
+  bench(3, 256, 256, 256, 3, false, true);
+  bench(3, 256, 256, 256, 1, false, false);
+  bench(3, 256, 256, 32, 3, false, false);
+  bench(5, 256, 512, 512, 3, false, false);
+  bench(8, 1024, 256, 256, 3, false, false);
+  bench(3, 256, 256, 256, 3, true, false);
+  printf("SELFTEST %s\n", fails == 0 ? "PASS" : "FAIL");
+  return fails ? 1 : 0;
+}
