@@ -35,13 +35,13 @@ enum { OPRL_ALGO_DDPG = 0, OPRL_ALGO_TD3 = 1, OPRL_ALGO_SAC = 2, OPRL_ALGO_TQC =
 enum { OPRL_GEMM_TC_3XTF32 = 0, OPRL_GEMM_TC_TF32 = 1, OPRL_GEMM_SIMT = 2 };
 enum { OPRL_NET_ACTOR = 0, OPRL_NET_CRITIC = 1 };
 /* oprl_update flags */
-enum { OPRL_UPDATE_ACTOR = 1 /* also run the actor step + Polyak updates */ };
+enum { OPRL_UPDATE_ACTOR = 1 /* also run the actor step (+ Polyak updates tied to it) */ };
 /* oprl_update segments (multi-GPU learners all-reduce the gradient arena between them) */
 enum {
   OPRL_SEG_ALL = -1,
-  OPRL_SEG_CRITIC_GRAD = 0, /* target-Q, critic forward/backward -> critic gradient arena */
-  OPRL_SEG_CRITIC_STEP_ACTOR_GRAD = 1, /* critic Adam(+Polyak), actor forward/backward */
-  OPRL_SEG_ACTOR_STEP = 2 /* actor Adam (+Polyak), temperature step */
+  OPRL_SEG_CRITIC_GRAD = 0,           /* target-Q, critic forward/backward -> critic gradient arena */
+  OPRL_SEG_CRITIC_STEP_ACTOR_GRAD = 1, /* critic Adam(+Polyak), actor forward/backward -> actor gradient arena */
+  OPRL_SEG_ACTOR_STEP = 2              /* actor Adam (+Polyak), temperature step */
 };
 
 typedef struct oprl_cfg {
@@ -49,20 +49,21 @@ typedef struct oprl_cfg {
   int state_dim;     /* ddpg.py:19 */
   int action_dim;    /* ddpg.py:20 */
   int actor_hidden;  /* 256: ddpg.py:43 */
-  int actor_layers;  /* 2 hidden layers */
+  int actor_layers;  /* hidden layers: 2 */
   int critic_hidden; /* 256: nn_models.py:31 ; TQC 512: tqc.py:49 */
-  int critic_layers; /* 2 ; TQC 3 */
+  int critic_layers; /* hidden layers: 2 ; TQC 3 */
   int n_critics;     /* DDPG 1, TD3/SAC 2, TQC n_nets (tqc.py:73) */
   int n_quantiles;   /* TQC 25 (tqc.py:72), else 1 */
   int top_quantiles_to_drop; /* tqc.py:71 */
-  int policy_freq;   /* td3.py:24 (host decides OPRL_UPDATE_ACTOR; informational) */
-  int tune_alpha;    /* sac.py:22 */
+  int tune_alpha;    /* sac.py:22 ; TQC always 1 */
   int gemm_mode;     /* OPRL_GEMM_* */
   int device;        /* CUDA ordinal */
-  float gamma, tau, lr_actor, lr_critic, lr_alpha;
-  float policy_noise, noise_clip, max_action; /* td3.py:21-28 */
-  float alpha_init, target_entropy;           /* sac.py:27,70 */
-  unsigned long long seed;
+  int world_size;    /* data-parallel learners sharing the minibatch (losses are means over world_size * B rows) */
+  /* python floats of the reference dataclasses, as doubles (rounded to fp32 where torch would) */
+  double gamma, tau, lr_actor, lr_critic, lr_alpha;
+  double policy_noise, noise_clip, max_action; /* td3.py:21-28 */
+  double alpha_init, target_entropy;           /* sac.py:27,70 */
+  unsigned long long seed;                     /* device-side sampling / noise streams */
 } oprl_cfg;
 
 typedef struct oprl_state { /* optimizer / RNG counters for checkpoint + tests */
@@ -122,9 +123,26 @@ int oprl_get_scalars(oprl_engine* e, float* out_host, int n);
 int oprl_get_state(oprl_engine* e, oprl_state* out);
 int oprl_set_state(oprl_engine* e, const oprl_state* in);
 int oprl_sync(oprl_engine* e);
-void* oprl_stream(oprl_engine* e); /* cudaStream_t */
-/* number of kernel launches one oprl_update(flags, OPRL_SEG_ALL) enqueues */
-int oprl_update_launches(oprl_engine* e, int flags);
+void* oprl_stream(oprl_engine* e); /* cudaStream_t the engine currently launches into */
+/* Redirect the engine's launches to the caller's stream (e.g. torch's current stream) so that
+ * ordinary stream ordering holds between the caller's tensors and the engine; NULL = engine-owned. */
+int oprl_engine_set_stream(oprl_engine* e, void* stream);
+
+/* Engine-less sample(): plain row-major gather of B host-chosen (episode, step) pairs out of
+ * replay storage shaped as in oprl_buffer_bind (episodic_buffer.py:127-133); next_state is the
+ * adjacent row states[ep, step + 1].  ep_step_dev: device scratch of 2*B ints. */
+int oprl_gather_rows(const float* states, const float* actions, const float* rewards,
+                     const float* dones, int E, int L, int S, int A, const int* ep_step_host,
+                     int* ep_step_dev, int B, float* s, float* a, float* r, float* d, float* s2,
+                     void* stream);
+/* number of kernel launches one oprl_update(flags, OPRL_SEG_ALL) enqueues at batch B */
+int oprl_update_launches(oprl_engine* e, int B, int flags);
+
+/* Measurement hook for bench.py's roofline: what = 0 replays only the tcgen05 GEMM launches of
+ * one update `iters` times, what = 1 the gather (device index draw); total milliseconds by CUDA
+ * events on the launch stream.  Leaves activations / batch in an unspecified state. */
+int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* ms_total,
+                 int* launches_per_iter);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,89 @@
+"""Shared host logic of the four algorithms: arena adoption, batch hand-off, lazy metrics.
+
+Reference surface: OffPolicyAlgorithm (base_algorithm.py:7-15) + the dataclass fields /
+``create()`` / ``update()`` of ddpg.py, td3.py, sac.py, tqc.py.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import torch as t
+import torch.nn as nn
+
+from ..engine import EngineSpec, UpdateEngine
+from .nn_functions import disable_gradient
+from .nn_models import adopt_parameters
+
+
+class EngineAdam:
+    """Read-only view of the engine's fused Adam state (stands where the reference keeps a
+    ``torch.optim.Adam``: ddpg.py:51,56)."""
+
+    def __init__(self, engine: UpdateEngine, group: str, lr: float, step_field: str):
+        self._engine, self._group, self.lr, self._step_field = engine, group, lr, step_field
+
+    @property
+    def exp_avg(self) -> t.Tensor:
+        return self._engine.arena[self._group]["m"]
+
+    @property
+    def exp_avg_sq(self) -> t.Tensor:
+        return self._engine.arena[self._group]["v"]
+
+    @property
+    def step_count(self) -> int:
+        return int(getattr(self._engine.state(), self._step_field))
+
+    def state_dict(self) -> dict:
+        return {"exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "step": self.step_count, "lr": self.lr}
+
+
+class OffPolicyAlgorithm:
+    _created: bool = False
+    engine: UpdateEngine
+
+    def check_created(self) -> None:
+        if not self._created:
+            raise RuntimeError(f"Algorithm {type(self).__name__} has not been created with `create()`.")
+
+    def get_policy_state_dict(self) -> dict[str, Any]:
+        return self.actor.state_dict()
+
+    # ------------------------------------------------------------------ engine glue
+    def _critic_nets(self) -> list[nn.Module]:
+        raise NotImplementedError
+
+    def _start_engine(self, spec: EngineSpec) -> None:
+        self.engine = UpdateEngine(spec, self.device)
+        ar = self.engine.arena
+        adopt_parameters(ar["actor"]["theta"], [self.actor])
+        adopt_parameters(ar["critic"]["theta"], [self.critic])
+        adopt_parameters(ar["critic"]["target"], [self.critic_target])
+        disable_gradient(self.critic_target)
+        if ar["actor"]["target"] is not None:
+            adopt_parameters(ar["actor"]["target"], [self.actor_target])
+            disable_gradient(self.actor_target)
+        for mod in (self.actor, self.critic, self.critic_target, getattr(self, "actor_target", None)):
+            if mod is not None:
+                mod.register_load_state_dict_post_hook(lambda *_: self.engine.mark_params_dirty())
+        self.engine.mark_params_dirty()
+
+    def _hand_batch(self, state, action, reward, done, next_state) -> None:
+        """update() accepts any five tensors (int64 ``done`` and aliased state / next_state
+        included: tests/functional/test_rl_algos.py:25-31); tensors that are the engine's own
+        sampled batch (``attach_buffer`` + ``sample``) are used in place."""
+        token = getattr(state, "_oprl_batch_token", None)
+        if token is not None and token == getattr(self.engine, "last_batch_token", None):
+            return
+        self.engine.last_batch_token = None
+        self.engine.load_batch(state, action, reward, done, next_state)
+
+    def attach_buffer(self, buffer) -> None:
+        """Fuse ``buffer.sample()`` with this algorithm's engine: the gather kernel then writes
+        the GEMM operand layout directly and ``update(*batch)`` skips the copy-in."""
+        buffer.attach_engine(self.engine)
+
+    def log_scalars_now(self) -> dict:
+        """Device-side metrics of the last update (synchronises; only call on logging steps)."""
+        return self.engine.scalars()

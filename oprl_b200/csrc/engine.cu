@@ -1,0 +1,1081 @@
+// oprl_b200 engine: builds, per (batch size, update flags), the launch program of one
+// off-policy gradient update -- gather -> target-Q -> critic backward -> Adam/Polyak ->
+// actor forward/backward -> Adam/Polyak -- out of grouped tcgen05 GEMM launches
+// (gemm.cuh) and a few SIMT kernels (kernels.cuh), captures it in a CUDA graph and
+// exposes it through the C ABI of include/oprl_b200.h.
+//
+// Reference semantics followed (paths relative to the reference root):
+//   DDPG  src/oprl/algos/ddpg.py:61-107      TD3  src/oprl/algos/td3.py:71-146
+//   SAC   src/oprl/algos/sac.py:75-155       TQC  src/oprl/algos/tqc.py:116-189
+//   nets  src/oprl/algos/nn_models.py:27-214 sample src/oprl/buffers/episodic_buffer.py:114-133
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/oprl_b200.h"
+#include "kernels.cuh"
+#include "policy.cuh"
+
+namespace oprl {
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+struct CudaError {
+  cudaError_t e;
+  const char* what;
+  int line;
+};
+#define CU(x)                                         \
+  do {                                                \
+    cudaError_t e_ = (x);                             \
+    if (e_ != cudaSuccess) throw CudaError{e_, #x, __LINE__}; \
+  } while (0)
+
+static inline int pad4(int x) { return (x + 3) & ~3; }
+
+// ------------------------------------------------------------------- network specs
+struct Layer {
+  int in, out;     // reference dims
+  int Kp, Np;      // padded tiled dims (multiples of 32)
+  size_t w_off, b_off;  // float offsets inside the group's flat arena
+  int split, off_lo, off_hi;  // reference input column j -> tiled column (layer 0 only)
+  TM W, WT, TW;    // tiled operand copies: W [Np x Kp], WT [Kp x Np], target W [Np x Kp]
+};
+struct Net {
+  std::vector<Layer> L;
+};
+struct Group {  // actor (1 net) or critic (n_critics nets) -- one flat arena, one Adam
+  std::vector<Net> nets;
+  size_t floats = 0;
+  float *theta = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr, *target = nullptr;
+  bool want_target = false;
+  AdamSeg* d_segs = nullptr;
+  int n_segs = 0;
+  size_t max_seg = 0;
+};
+
+// one forward pass of one net: saved activations
+struct Pass {
+  std::vector<TM> h;   // post-ReLU hidden outputs [Bp x Hp]
+  std::vector<TM> hT;  // transposes [Hp x Bp] (training passes only)
+};
+
+struct Stage {
+  std::vector<GemmOp> ops;
+  std::function<void(cudaStream_t)> simt;
+  int segment = 0;
+  int launches() const { return (ops.empty() ? 0 : 1) + (simt ? 1 : 0); }
+};
+
+struct Program {
+  int B = 0, Bp = 0;
+  int flags = 0;
+  std::vector<Stage> stages;
+  cudaGraphExec_t graph[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] segments, [3] all, [4] GEMM launches only (profiling)
+  int n_gemm_launches = 0;
+  int n_launches = 0;
+};
+
+}  // namespace oprl
+
+using namespace oprl;
+
+struct oprl_engine {
+  oprl_cfg cfg;
+  cudaStream_t stream = nullptr;      // launch stream (caller may redirect it, e.g. torch's current stream)
+  cudaStream_t own_stream = nullptr;  // engine-owned: setup work and graph capture
+  int A4 = 0, Kin = 0;  // padded action columns / padded input width of layer 0
+  Group grp[2];
+  DevState* d_state = nullptr;
+  DevState* h_state = nullptr;  // pinned mirror for reads
+  // bump allocator over zero-initialised workspaces
+  std::vector<void*> blocks;
+  // replay + batch bindings
+  const float *rb_states = nullptr, *rb_actions = nullptr, *rb_rewards = nullptr, *rb_dones = nullptr;
+  int rb_E = 0, rb_L = 0;
+  int* d_prefix = nullptr;
+  int prefix_cap = 0, n_eps = 0, n_trans = 0;
+  float *bs = nullptr, *ba = nullptr, *br = nullptr, *bd = nullptr, *bs2 = nullptr;
+  int batch_cap = 0;
+  std::vector<float*> own_batch;  // engine-owned batch arena when the caller bound none
+  // per-batch-size working set
+  struct Work;
+  std::map<int, std::unique_ptr<Work>> work;
+  int* h_idx = nullptr;  // pinned staging for host-chosen (episode, step) pairs
+  int h_idx_cap = 0;
+  int* h_flag = nullptr;  // pinned: ext_noise mask staging
+  int ext_mask = 0;
+  int cur_B = 0;
+
+  float* alloc_floats(size_t n) {
+    void* p = nullptr;
+    const size_t bytes = ((n * 4 + 1023) / 1024) * 1024;
+    CU(cudaMalloc(&p, bytes));
+    CU(cudaMemsetAsync(p, 0, bytes, stream));
+    blocks.push_back(p);
+    return static_cast<float*>(p);
+  }
+  TM alloc_tm(int rows, int cols) {
+    TM t;
+    t.rows = rows;
+    t.cols = cols;
+    const size_t n = static_cast<size_t>(rows) * cols;
+    float* p = alloc_floats(2 * n);
+    t.hi = p;
+    t.lo = p + n;
+    return t;
+  }
+};
+
+struct oprl_engine::Work {
+  int B, Bp;
+  TM X, XT, Xn, Xp;
+  int* d_idx = nullptr;      // [B][2]
+  float* noise_raw[2] = {nullptr, nullptr};
+  float* noise_out[2] = {nullptr, nullptr};
+  std::map<int, std::unique_ptr<Program>> prog;  // by flags
+  GatherArgs gather;  // template (sources patched per call)
+};
+
+namespace oprl {
+
+// ------------------------------------------------------------------ layout of nets
+static void build_group(oprl_engine* e, Group& g, int n_nets, const std::vector<int>& dims,
+                        bool is_critic, bool want_target) {
+  const int S = e->cfg.state_dim, A4 = e->A4;
+  g.want_target = want_target;
+  size_t off = 0;
+  g.nets.resize(n_nets);
+  for (int n = 0; n < n_nets; ++n) {
+    Net& net = g.nets[n];
+    net.L.resize(dims.size() - 1);
+    for (size_t l = 0; l + 1 < dims.size(); ++l) {
+      Layer& ly = net.L[l];
+      ly.in = dims[l];
+      ly.out = dims[l + 1];
+      ly.Np = pad32(ly.out);
+      if (l == 0) {
+        // layer-0 inputs live in the X matrices as [action | pad4 | state]
+        ly.Kp = e->Kin;
+        ly.split = S;
+        ly.off_lo = A4;
+        ly.off_hi = 0;  // critic: reference column S + j -> tiled column j
+      } else {
+        ly.Kp = pad32(ly.in);
+        ly.split = ly.in;
+        ly.off_lo = 0;
+        ly.off_hi = 0;
+      }
+      ly.w_off = off;
+      off += static_cast<size_t>(ly.out) * ly.in;
+      ly.b_off = off;
+      off += ly.out;
+      ly.W = e->alloc_tm(ly.Np, ly.Kp);
+      ly.WT = e->alloc_tm(ly.Kp, ly.Np);
+      if (want_target) ly.TW = e->alloc_tm(ly.Np, ly.Kp);
+      else ly.TW = TM{nullptr, nullptr, 0, 0};
+    }
+  }
+  (void)is_critic;
+  g.floats = off;
+}
+
+static void upload_segs(oprl_engine* e, Group& g, int opt) {
+  std::vector<AdamSeg> segs;
+  g.max_seg = 0;
+  for (auto& net : g.nets)
+    for (auto& ly : net.L) {
+      AdamSeg w;
+      memset(&w, 0, sizeof(w));
+      w.theta = g.theta + ly.w_off;
+      w.grad = g.grad + ly.w_off;
+      w.m = g.m + ly.w_off;
+      w.v = g.v + ly.w_off;
+      w.target = g.target ? g.target + ly.w_off : nullptr;
+      w.w_hi = ly.W.hi; w.w_lo = ly.W.lo;
+      w.wt_hi = ly.WT.hi; w.wt_lo = ly.WT.lo;
+      w.tw_hi = g.target ? ly.TW.hi : nullptr;
+      w.tw_lo = g.target ? ly.TW.lo : nullptr;
+      w.w_rows = ly.Np;
+      w.wt_rows = ly.Kp;
+      w.n = ly.out * ly.in;
+      w.rows = ly.out;
+      w.cols = ly.in;
+      w.split = ly.split; w.off_lo = ly.off_lo; w.off_hi = ly.off_hi;
+      w.opt = opt;
+      segs.push_back(w);
+      AdamSeg b;
+      memset(&b, 0, sizeof(b));
+      b.theta = g.theta + ly.b_off;
+      b.grad = g.grad + ly.b_off;
+      b.m = g.m + ly.b_off;
+      b.v = g.v + ly.b_off;
+      b.target = g.target ? g.target + ly.b_off : nullptr;
+      b.n = ly.out;
+      b.rows = 1;
+      b.cols = ly.out;
+      b.opt = opt;
+      segs.push_back(b);
+      g.max_seg = std::max(g.max_seg, static_cast<size_t>(w.n));
+    }
+  if (!g.d_segs) {
+    void* p;
+    CU(cudaMalloc(&p, segs.size() * sizeof(AdamSeg)));
+    e->blocks.push_back(p);
+    g.d_segs = static_cast<AdamSeg*>(p);
+  }
+  g.n_segs = static_cast<int>(segs.size());
+  CU(cudaMemcpyAsync(g.d_segs, segs.data(), segs.size() * sizeof(AdamSeg), cudaMemcpyHostToDevice,
+                     e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+}
+
+static AdamHyper make_hyper(const oprl_cfg& c) {
+  AdamHyper hp;
+  hp.lr[0] = c.lr_actor;
+  hp.lr[1] = c.lr_critic;
+  hp.beta1 = 0.9;
+  hp.beta2 = 0.999;
+  hp.w1 = static_cast<float>(1.0 - hp.beta1);
+  hp.w2 = static_cast<float>(1.0 - hp.beta2);
+  hp.beta2f = static_cast<float>(hp.beta2);
+  hp.eps = 1e-8f;
+  hp.tau = static_cast<float>(c.tau);
+  hp.one_minus_tau = static_cast<float>(1.0 - c.tau);
+  return hp;
+}
+
+static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st) {
+  const int bx = static_cast<int>(std::min<size_t>((g.max_seg + kAdamThreads * 2 - 1) / (kAdamThreads * 2), 64));
+  dim3 grid(std::max(bx, 1), g.n_segs);
+  adam_kernel<<<grid, kAdamThreads, 0, st>>>(g.d_segs, make_hyper(e->cfg), e->d_state, mode);
+}
+
+// --------------------------------------------------------------- program builder
+struct Builder {
+  oprl_engine* e;
+  oprl_engine::Work* w;
+  Program* p;
+  int passes;
+  int seg = 0;
+
+  Stage& stage(int i) {
+    while (static_cast<int>(p->stages.size()) <= i) {
+      p->stages.emplace_back();
+      p->stages.back().segment = seg;
+    }
+    return p->stages[i];
+  }
+  GemmOp base_op(const TM& a, const TM& b, int M, int N, int K) {
+    GemmOp o;
+    memset(&o, 0, sizeof(o));
+    o.a_hi = a.hi; o.a_lo = a.lo; o.a_rows = a.rows;
+    o.b_hi = b.hi; o.b_lo = b.lo; o.b_rows = b.rows;
+    o.M = M; o.N = N; o.K = K;
+    o.passes = passes;
+    o.alpha = 1.f;
+    return o;
+  }
+  float* counters(int n) { return e->alloc_floats(n); }
+
+  // ---- forward of one net over input X (tiled [Bp x Kin]).  Hidden layers: bias+ReLU,
+  // outputs kept tiled (and transposed when `train`).  The last layer is returned
+  // half-configured (bias set) for the caller to attach its epilogue; it goes in
+  // stage s0 + n_layers - 1.  Returns the stage after the last layer.
+  int forward(int s0, const Net& net, const float* theta, bool use_target, const TM& X,
+              Pass& pass, bool train, GemmOp* last) {
+    const int Bp = w->Bp;
+    const int nl = static_cast<int>(net.L.size());
+    pass.h.resize(nl - 1);
+    pass.hT.resize(nl - 1);
+    TM in = X;
+    for (int l = 0; l < nl; ++l) {
+      const Layer& ly = net.L[l];
+      GemmOp o = base_op(in, use_target ? ly.TW : ly.W, Bp, ly.Np, ly.Kp);
+      o.bias = theta + ly.b_off;
+      o.bias_n = ly.out;
+      if (l < nl - 1) {
+        o.act = ACT_RELU;
+        if (!pass.h[l].hi) pass.h[l] = e->alloc_tm(Bp, ly.Np);
+        o.t_hi = pass.h[l].hi; o.t_lo = pass.h[l].lo;
+        o.t_rows = Bp; o.t_c0 = 0; o.t_n = ly.Np;
+        if (train) {
+          if (!pass.hT[l].hi) pass.hT[l] = e->alloc_tm(ly.Np, Bp);
+          o.tt_hi = pass.hT[l].hi; o.tt_lo = pass.hT[l].lo;
+          o.tt_rows = ly.Np;
+        }
+        stage(s0 + l).ops.push_back(o);
+        in = pass.h[l];
+      } else {
+        *last = o;
+      }
+    }
+    return s0 + nl;
+  }
+
+  // ---- backward of one net.  dz = dL/d(pre-activation of the last layer), tiled
+  // [Bp x Np_last] (+ transpose dzT [pad128(out) x Bp]).  Emits, starting at stage s0:
+  //   for l = last..0:  dW_l = dzT_l . hT_{l-1}  (-> grad arena),  db_l (colsum, produced
+  //   with dz_l), dz_{l-1} = (dz_l . W_l) * relu'(h_{l-1}).
+  // want_dw = false: only the dX chain (critic inside the actor step).  If dx_last is
+  // set, the layer-0 input gradient GEMM is emitted with that (half-configured) epilogue.
+  // Returns the stage after the last emitted op.
+  int backward(int s0, const Net& net, float* grad, const Pass& pass, TM dz, TM dzT,
+               const TM& XT, bool want_dw, bool is_actor, GemmOp* dx_epilogue) {
+    const int Bp = w->Bp;
+    const int nl = static_cast<int>(net.L.size());
+    const int S = e->cfg.state_dim, A = e->cfg.action_dim, A4 = e->A4;
+    int s = s0;
+    for (int l = nl - 1; l >= 0; --l, ++s) {
+      const Layer& ly = net.L[l];
+      if (want_dw) {
+        // dW_l [out x in] = sum_b dzT(o, b) * hprevT(i, b)
+        const TM& hprevT = (l == 0) ? XT : pass.hT[l - 1];
+        GemmOp o = base_op(dzT, hprevT, pad128(ly.out), ly.Kp, Bp);
+        o.rm = grad + ly.w_off;
+        o.rm_ld = ly.in;
+        o.rm_m = ly.out;
+        o.rm_n = ly.Kp;
+        if (l == 0) {
+          // tiled input columns [action | pad4 | state] -> reference columns [state | action]
+          o.map_a = is_actor ? 0 : A;
+          o.map_a4 = A4;
+          o.map_s = S;
+        } else {
+          o.rm_n = ly.in;
+        }
+        stage(s).ops.push_back(o);
+      }
+      if (l == 0) {
+        if (dx_epilogue) {
+          // dX (first N tile = the action columns) = dz_0 . W_0
+          GemmOp o = *dx_epilogue;
+          o.a_hi = dz.hi; o.a_lo = dz.lo; o.a_rows = dz.rows;
+          o.b_hi = ly.WT.hi; o.b_lo = ly.WT.lo; o.b_rows = ly.WT.rows;
+          o.M = Bp; o.N = 32; o.K = ly.Np;
+          o.passes = passes;
+          stage(s).ops.push_back(o);
+        }
+        break;
+      }
+      // dz_{l-1} = (dz_l . W_l) (.) relu'(h_{l-1});  db_{l-1} = column sums
+      const Layer& lp = net.L[l - 1];
+      GemmOp o = base_op(dz, ly.WT, Bp, ly.Kp, ly.Np);
+      o.mask_hi = pass.h[l - 1].hi;
+      o.mask_rows = Bp;
+      TM ndz = e->alloc_tm(Bp, lp.Np);
+      o.t_hi = ndz.hi; o.t_lo = ndz.lo; o.t_rows = Bp; o.t_c0 = 0; o.t_n = lp.Np;
+      TM ndzT = TM{nullptr, nullptr, 0, 0};
+      if (want_dw) {
+        ndzT = e->alloc_tm(pad128(lp.out), Bp);
+        o.tt_hi = ndzT.hi; o.tt_lo = ndzT.lo; o.tt_rows = pad128(lp.out);
+        o.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * lp.Np);
+        o.colsum_ld = lp.Np;
+        o.colsum_n = lp.out;
+        o.colsum_out = grad + lp.b_off;
+        o.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(lp.Np / kBN));
+      }
+      stage(s).ops.push_back(o);
+      dz = ndz;
+      dzT = ndzT;
+    }
+    return s + 1;
+  }
+};
+
+}  // namespace oprl
+
+// ================================================================== DDPG / TD3 program
+namespace oprl {
+
+static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
+  const oprl_cfg& c = e->cfg;
+  const bool td3 = c.algo == OPRL_ALGO_TD3;
+  const bool do_actor = (p->flags & OPRL_UPDATE_ACTOR) != 0;
+  const int B = w->B, Bp = w->Bp, A = c.action_dim, nq = c.n_critics;
+  Builder b{e, w, p, c.gemm_mode == OPRL_GEMM_TC_TF32 ? 1 : 3};
+  Group& ga = e->grp[OPRL_NET_ACTOR];
+  Group& gc = e->grp[OPRL_NET_CRITIC];
+  const float inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
+
+  // S0: gather / dense load + noise (launched by oprl_sample / oprl_load_batch, not here)
+  int s = 0;
+  // ---- critic step ---------------------------------------------------------
+  float* q = e->alloc_floats(static_cast<size_t>(Bp) * nq);
+  float* qn = e->alloc_floats(static_cast<size_t>(Bp) * nq);
+  Pass p_at, p_ct[2], p_c[2];
+  // actor_target(s') -> a' into Xn[:, :A]        (ddpg.py:94, td3.py:102-103)
+  {
+    GemmOp last;
+    const int s_end = b.forward(s, ga.nets[0], ga.target, true, w->Xn, p_at, false, &last);
+    last.act = ACT_TANH;
+    if (td3) {
+      last.addm = w->noise_out[0];
+      last.addm_ld = A;
+      last.addm_n = A;
+      last.clamp = static_cast<float>(c.max_action);
+    }
+    last.t_hi = w->Xn.hi; last.t_lo = w->Xn.lo; last.t_rows = Bp; last.t_c0 = 0; last.t_n = A;
+    b.stage(s_end - 1).ops.push_back(last);
+    // critic(s, a) -> q                          (ddpg.py:96, td3.py:95)
+    for (int i = 0; i < nq; ++i) {
+      GemmOp lq;
+      b.forward(s, gc.nets[i], gc.theta, false, w->X, p_c[i], true, &lq);
+      lq.rm = q + i; lq.rm_ld = nq; lq.rm_m = Bp; lq.rm_n = 1;
+      b.stage(s_end - 1).ops.push_back(lq);
+    }
+    s = s_end;
+  }
+  // critic_target(s', a') -> qn
+  {
+    int s_end = s;
+    for (int i = 0; i < nq; ++i) {
+      GemmOp lq;
+      s_end = b.forward(s, gc.nets[i], gc.target, true, w->Xn, p_ct[i], false, &lq);
+      lq.rm = qn + i; lq.rm_ld = nq; lq.rm_m = Bp; lq.rm_n = 1;
+      b.stage(s_end - 1).ops.push_back(lq);
+    }
+    s = s_end;
+  }
+  // TD target + MSE seeds                        (ddpg.py:95-98, td3.py:105-112)
+  TdArgs td;
+  memset(&td, 0, sizeof(td));
+  td.qn = qn; td.q = q; td.r = e->br; td.d = e->bd;
+  td.gamma = static_cast<float>(c.gamma);
+  td.inv_count = inv_count;
+  td.B = B; td.nq = nq;
+  td.bump_actor = do_actor ? 1 : 0;
+  for (int i = 0; i < nq; ++i) {
+    td.D3[i] = e->alloc_tm(Bp, 32);
+    td.D3T[i] = e->alloc_tm(128, Bp);
+    td.db3[i] = gc.grad + gc.nets[i].L.back().b_off;
+  }
+  {
+    DevState* st = e->d_state;
+    b.stage(s).simt = [td, st](cudaStream_t sm) { td_kernel<<<1, kTdThreads, 0, sm>>>(td, st); };
+    ++s;
+  }
+  // critic backward
+  {
+    int s_end = s;
+    for (int i = 0; i < nq; ++i)
+      s_end = b.backward(s, gc.nets[i], gc.grad, p_c[i], td.D3[i], td.D3T[i], w->XT, true, false, nullptr);
+    s = s_end;
+  }
+  b.seg = 1;
+  // critic Adam (+ Polyak when the reference does it in this update) + re-tiling
+  {
+    const bool polyak = td3 ? do_actor : true;  // td3.py:81-84 ; ddpg.py:72-77
+    const int mode = 1 | 4 | (polyak ? (2 | 8) : 0);
+    b.stage(s).simt = [e, &gc, mode](cudaStream_t sm) { launch_adam(e, gc, mode, sm); };
+    ++s;
+  }
+  if (do_actor) {
+    // ---- actor step ----------------------------------------------------------
+    Pass p_a, p_cq;
+    float* a_rm = e->alloc_floats(static_cast<size_t>(Bp) * A);
+    GemmOp last;
+    int s_end = b.forward(s, ga.nets[0], ga.theta, false, w->Xp, p_a, true, &last);
+    last.act = ACT_TANH;
+    last.t_hi = w->Xp.hi; last.t_lo = w->Xp.lo; last.t_rows = Bp; last.t_c0 = 0; last.t_n = A;
+    last.rm = a_rm; last.rm_ld = A; last.rm_m = Bp; last.rm_n = A;
+    b.stage(s_end - 1).ops.push_back(last);
+    s = s_end;
+    // critic.Q1(s, pi(s)) with the just-updated critic   (ddpg.py:104, td3.py:135-137)
+    GemmOp lq;
+    s_end = b.forward(s, gc.nets[0], gc.theta, false, w->Xp, p_cq, false, &lq);
+    // actor_loss = -mean(q): alpha = -1/count, rows >= B dropped, column sum -> scalar
+    lq.alpha = -inv_count;
+    lq.m_valid = B;
+    lq.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * 32);
+    lq.colsum_ld = 32;
+    lq.colsum_n = 1;
+    lq.colsum_out = &e->d_state->scalars[SC_ACTOR_LOSS];
+    lq.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+    b.stage(s_end - 1).ops.push_back(lq);
+    s = s_end - 1;  // the dX chain starts beside the q head
+    // seed: dL/dq = -1/count on valid rows (constant)
+    TM Dm = e->alloc_tm(Bp, 32);
+    {
+      std::vector<float> hi(static_cast<size_t>(Bp) * 32, 0.f), lo(hi.size(), 0.f);
+      for (int m = 0; m < B; ++m) {
+        const float x = -inv_count;
+        uint32_t u;
+        memcpy(&u, &x, 4);
+        u = (u + 0x1000u) & 0xFFFFE000u;
+        float h;
+        memcpy(&h, &u, 4);
+        hi[ct_index(Bp, m, 0)] = h;
+        const float l = x - h;
+        memcpy(&u, &l, 4);
+        u = (u + 0x1000u) & 0xFFFFE000u;
+        float l2;
+        memcpy(&l2, &u, 4);
+        lo[ct_index(Bp, m, 0)] = l2;
+      }
+      CU(cudaMemcpyAsync(Dm.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, e->stream));
+      CU(cudaMemcpyAsync(Dm.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, e->stream));
+      CU(cudaStreamSynchronize(e->stream));
+    }
+    // critic dX chain down to the action columns, then tanh'
+    TM dza = e->alloc_tm(Bp, 32);
+    TM dzaT = e->alloc_tm(128, Bp);
+    const Layer& a_last = ga.nets[0].L.back();
+    GemmOp dx;
+    memset(&dx, 0, sizeof(dx));
+    dx.alpha = 1.f;
+    dx.rs = a_rm; dx.rs_ld = A; dx.rs_n = A;
+    dx.t_hi = dza.hi; dx.t_lo = dza.lo; dx.t_rows = Bp; dx.t_c0 = 0; dx.t_n = A;
+    dx.tt_hi = dzaT.hi; dx.tt_lo = dzaT.lo; dx.tt_rows = 128;
+    dx.n_valid = A;  // columns >= A of this tile are pad / state gradients: drop them
+    dx.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * 32);
+    dx.colsum_ld = 32;
+    dx.colsum_n = a_last.out;
+    dx.colsum_out = ga.grad + a_last.b_off;
+    dx.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+    s = b.backward(s, gc.nets[0], nullptr, p_cq, Dm, TM{nullptr, nullptr, 0, 0}, w->XT, false, false, &dx);
+    // actor backward
+    s = b.backward(s, ga.nets[0], ga.grad, p_a, dza, dzaT, w->XT, true, true, nullptr);
+    // actor Adam + Polyak + re-tiling   (ddpg.py:107,79-84 ; td3.py:141,83-84)
+    b.seg = 2;
+    b.stage(s).simt = [e, &ga](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm); };
+    ++s;
+  }
+}
+
+}  // namespace oprl
+
+// ================================================================== program execution
+namespace oprl {
+
+static void launch_gemm_ops(oprl_engine* e, const std::vector<GemmOp>& ops, cudaStream_t st) {
+  for (size_t i0 = 0; i0 < ops.size(); i0 += kMaxOps) {
+    GemmLaunch L;
+    memset(&L, 0, sizeof(L));
+    int tiles = 0;
+    L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, ops.size() - i0));
+    for (int i = 0; i < L.n_ops; ++i) {
+      L.op[i] = ops[i0 + i];
+      tiles += gemm_tiles(L.op[i]);
+    }
+    if (e->cfg.gemm_mode == OPRL_GEMM_SIMT)
+      gemm_kernel<true><<<tiles, kGemmThreads, kGemmSmemBytes, st>>>(L);
+    else
+      gemm_kernel<false><<<tiles, kGemmThreads, kGemmSmemBytes, st>>>(L);
+  }
+}
+
+static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, bool gemm_only = false) {
+  int n = 0;
+  for (auto& sg : p->stages) {
+    if (segment >= 0 && sg.segment != segment) continue;
+    if (!sg.ops.empty()) {
+      launch_gemm_ops(e, sg.ops, st);
+      n += static_cast<int>((sg.ops.size() + kMaxOps - 1) / kMaxOps);
+    }
+    if (sg.simt && !gemm_only) {
+      sg.simt(st);
+      ++n;
+    }
+  }
+  return n;
+}
+
+static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p);
+
+static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
+  auto it = w->prog.find(flags);
+  if (it != w->prog.end()) return it->second.get();
+  std::unique_ptr<Program> p(new Program);
+  p->B = w->B;
+  p->Bp = w->Bp;
+  p->flags = flags;
+  if (e->cfg.algo == OPRL_ALGO_DDPG || e->cfg.algo == OPRL_ALGO_TD3) build_ddpg_td3(e, w, p.get());
+  else build_sac_tqc(e, w, p.get());
+  CU(cudaStreamSynchronize(e->stream));  // workspace memsets / constant uploads done
+  // capture: one graph per segment + one for the whole update
+  for (int k = 0; k < 5; ++k) {
+    const int segment = (k >= 3) ? -1 : k;
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
+    int n = 0;
+    try {
+      n = run_stages(e, p.get(), segment, e->own_stream, k == 4);
+    } catch (...) {
+      cudaStreamEndCapture(e->own_stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CU(cudaStreamEndCapture(e->own_stream, &g));
+    if (k == 3) p->n_launches = n;
+    if (k == 4) p->n_gemm_launches = n;
+    if (n > 0) {
+      CU(cudaGraphInstantiate(&p->graph[k], g, 0));
+    }
+    CU(cudaGraphDestroy(g));
+  }
+  Program* raw = p.get();
+  w->prog[flags] = std::move(p);
+  return raw;
+}
+
+static oprl_engine::Work* get_work(oprl_engine* e, int B) {
+  auto it = e->work.find(B);
+  if (it != e->work.end()) return it->second.get();
+  const oprl_cfg& c = e->cfg;
+  std::unique_ptr<oprl_engine::Work> w(new oprl_engine::Work);
+  w->B = B;
+  w->Bp = pad128(B);
+  const int Bp = w->Bp;
+  w->X = e->alloc_tm(Bp, e->Kin);
+  w->Xn = e->alloc_tm(Bp, e->Kin);
+  w->Xp = e->alloc_tm(Bp, e->Kin);
+  w->XT = e->alloc_tm(e->Kin, Bp);
+  w->d_idx = reinterpret_cast<int*>(e->alloc_floats(static_cast<size_t>(Bp) * 2));
+  const size_t nz = static_cast<size_t>(Bp) * c.action_dim;
+  for (int k = 0; k < 2; ++k) {
+    w->noise_raw[k] = e->alloc_floats(nz);
+    w->noise_out[k] = (c.algo == OPRL_ALGO_TD3 && k == 0) ? e->alloc_floats(nz) : nullptr;
+  }
+  if (!e->bs || e->batch_cap < B) {
+    // caller bound no (or a too small) batch arena: own one
+    e->bs = e->alloc_floats(static_cast<size_t>(Bp) * c.state_dim);
+    e->ba = e->alloc_floats(static_cast<size_t>(Bp) * c.action_dim);
+    e->br = e->alloc_floats(Bp);
+    e->bd = e->alloc_floats(Bp);
+    e->bs2 = e->alloc_floats(static_cast<size_t>(Bp) * c.state_dim);
+    e->batch_cap = Bp;
+    for (auto& kv : e->work) kv.second->prog.clear();  // programs bake br / bd pointers
+  }
+  GatherArgs& g = w->gather;
+  memset(&g, 0, sizeof(g));
+  g.L = e->rb_L;
+  g.S = c.state_dim;
+  g.A = c.action_dim;
+  g.A4 = e->A4;
+  g.B = B;
+  g.seed = c.seed;
+  g.X = w->X; g.XT = w->XT; g.Xn = w->Xn; g.Xp = w->Xp;
+  const int n_draws = (c.algo == OPRL_ALGO_TD3) ? 1 : (c.algo == OPRL_ALGO_DDPG ? 0 : 2);
+  for (int k = 0; k < 2; ++k) {
+    g.noise[k].raw = w->noise_raw[k];
+    g.noise[k].out = w->noise_out[k];
+    g.noise[k].n = (k < n_draws) ? B * c.action_dim : 0;
+    g.noise[k].scale = (c.algo == OPRL_ALGO_TD3) ? static_cast<float>(c.policy_noise) : 1.f;
+    g.noise[k].clip = (c.algo == OPRL_ALGO_TD3) ? static_cast<float>(c.noise_clip) : 0.f;
+  }
+  oprl_engine::Work* raw = w.get();
+  e->work[B] = std::move(w);
+  return raw;
+}
+
+static void launch_gather(oprl_engine* e, oprl_engine::Work* w, GatherArgs g) {
+  g.bs = e->bs; g.ba = e->ba; g.br = e->br; g.bd = e->bd; g.bs2 = e->bs2;
+  const int total = g.noise[0].n + g.noise[1].n;
+  const int nblocks = total ? std::min((total + kGatherThreads * 4 - 1) / (kGatherThreads * 4), 64) : 0;
+  gather_kernel<<<g.B + nblocks, kGatherThreads, 0, e->stream>>>(g, e->d_state);
+  CU(cudaGetLastError());
+}
+
+}  // namespace oprl
+
+// ============================================================================ C ABI
+#define API_BEGIN try {
+#define API_END                                                                             \
+  }                                                                                         \
+  catch (const CudaError& ce) {                                                             \
+    return fail(-2, "CUDA error %s (%s) at engine.cu:%d", cudaGetErrorString(ce.e), ce.what, \
+                ce.line);                                                                   \
+  }                                                                                         \
+  catch (const std::exception& ex) {                                                        \
+    return fail(-3, "%s", ex.what());                                                       \
+  }
+
+extern "C" {
+
+const char* oprl_last_error(void) { return g_err.c_str(); }
+int oprl_abi_version(void) { return 1; }
+
+int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
+  if (!cfg || !out) return fail(-1, "null argument");
+  *out = nullptr;
+  if (cfg->algo < 0 || cfg->algo > 3) return fail(-1, "unknown algo %d", cfg->algo);
+  if (cfg->state_dim <= 0 || cfg->action_dim <= 0) return fail(-1, "bad dims");
+  if (cfg->n_critics < 1 || cfg->n_critics > 8) return fail(-1, "n_critics out of range");
+  if ((cfg->algo == OPRL_ALGO_DDPG && cfg->n_critics != 1) ||
+      ((cfg->algo == OPRL_ALGO_TD3 || cfg->algo == OPRL_ALGO_SAC) && cfg->n_critics != 2))
+    return fail(-1, "n_critics does not match algo");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(-4, "no CUDA device: oprl_b200 has no CPU fallback");
+  oprl_engine* e = nullptr;
+  API_BEGIN
+  CU(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail(-4, "device sm_%d%d is not Blackwell sm_100", prop.major, prop.minor);
+  e = new oprl_engine;
+  e->cfg = *cfg;
+  if (e->cfg.world_size < 1) e->cfg.world_size = 1;
+  CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
+  CU(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  CU(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  e->A4 = pad4(cfg->action_dim);
+  e->Kin = pad32(e->A4 + cfg->state_dim);
+  const bool stochastic = cfg->algo == OPRL_ALGO_SAC || cfg->algo == OPRL_ALGO_TQC;
+  std::vector<int> ad{cfg->state_dim}, cd{cfg->state_dim + cfg->action_dim};
+  for (int i = 0; i < cfg->actor_layers; ++i) ad.push_back(cfg->actor_hidden);
+  ad.push_back(stochastic ? 2 * cfg->action_dim : cfg->action_dim);
+  for (int i = 0; i < cfg->critic_layers; ++i) cd.push_back(cfg->critic_hidden);
+  cd.push_back(cfg->algo == OPRL_ALGO_TQC ? cfg->n_quantiles : 1);
+  build_group(e, e->grp[OPRL_NET_ACTOR], 1, ad, false, !stochastic);
+  build_group(e, e->grp[OPRL_NET_CRITIC], cfg->n_critics, cd, true, true);
+  void* p;
+  CU(cudaMalloc(&p, sizeof(DevState)));
+  e->blocks.push_back(p);
+  e->d_state = static_cast<DevState*>(p);
+  CU(cudaMallocHost(&p, sizeof(DevState)));
+  e->h_state = static_cast<DevState*>(p);
+  memset(e->h_state, 0, sizeof(DevState));
+  e->h_state->log_alpha = std::log(cfg->alpha_init > 0 ? cfg->alpha_init : 1.0);
+  e->h_state->alpha = static_cast<float>(cfg->alpha_init);
+  CU(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(DevState), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMallocHost(&p, 64));
+  e->h_flag = static_cast<int*>(p);
+  CU(cudaStreamSynchronize(e->stream));
+  *out = e;
+  return 0;
+  API_END
+}
+
+void oprl_engine_destroy(oprl_engine* e) {
+  if (!e) return;
+  cudaStreamSynchronize(e->stream);
+  for (auto& kv : e->work)
+    for (auto& pv : kv.second->prog)
+      for (int k = 0; k < 5; ++k)
+        if (pv.second->graph[k]) cudaGraphExecDestroy(pv.second->graph[k]);
+  for (void* p : e->blocks) cudaFree(p);
+  if (e->h_state) cudaFreeHost(e->h_state);
+  if (e->h_flag) cudaFreeHost(e->h_flag);
+  if (e->d_prefix) cudaFree(e->d_prefix);
+  cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+long long oprl_engine_arena_floats(const oprl_engine* e, int net) {
+  if (!e || net < 0 || net > 1) return -1;
+  return static_cast<long long>(e->grp[net].floats);
+}
+
+int oprl_engine_bind_arena(oprl_engine* e, int net, float* theta, float* grad, float* m, float* v,
+                           float* theta_target) {
+  if (!e || net < 0 || net > 1) return fail(-1, "bad engine / net");
+  if (!theta || !grad || !m || !v) return fail(-1, "null arena pointer");
+  Group& g = e->grp[net];
+  if (g.want_target && !theta_target) return fail(-1, "this group needs a target arena");
+  API_BEGIN
+  g.theta = theta; g.grad = grad; g.m = m; g.v = v;
+  g.target = g.want_target ? theta_target : nullptr;
+  upload_segs(e, g, net);
+  for (auto& kv : e->work) kv.second->prog.clear();
+  return 0;
+  API_END
+}
+
+int oprl_engine_sync_params(oprl_engine* e) {
+  if (!e) return fail(-1, "null engine");
+  API_BEGIN
+  for (int k = 0; k < 2; ++k) {
+    if (!e->grp[k].theta) return fail(-1, "arena %d not bound", k);
+    launch_adam(e, e->grp[k], 4 | 8, e->stream);
+  }
+  CU(cudaGetLastError());
+  return 0;
+  API_END
+}
+
+int oprl_buffer_bind(oprl_engine* e, const float* states, const float* actions, const float* rewards,
+                     const float* dones, int E, int L) {
+  if (!e || !states || !actions || !rewards || !dones || E <= 0 || L <= 0) return fail(-1, "bad buffer");
+  e->rb_states = states; e->rb_actions = actions; e->rb_rewards = rewards; e->rb_dones = dones;
+  e->rb_E = E; e->rb_L = L;
+  for (auto& kv : e->work) kv.second->gather.L = L;
+  return 0;
+}
+
+int oprl_buffer_set_prefix(oprl_engine* e, const int* prefix_host, int n_eps) {
+  if (!e || !prefix_host || n_eps <= 0) return fail(-1, "bad prefix");
+  API_BEGIN
+  if (n_eps + 1 > e->prefix_cap) {
+    if (e->d_prefix) {
+      CU(cudaStreamSynchronize(e->stream));
+      CU(cudaFree(e->d_prefix));
+    }
+    e->prefix_cap = std::max(1024, 2 * (n_eps + 1));
+    void* p;
+    CU(cudaMalloc(&p, sizeof(int) * e->prefix_cap));
+    e->d_prefix = static_cast<int*>(p);
+  }
+  CU(cudaMemcpyAsync(e->d_prefix, prefix_host, sizeof(int) * (n_eps + 1), cudaMemcpyHostToDevice, e->stream));
+  e->n_eps = n_eps;
+  e->n_trans = prefix_host[n_eps];
+  return 0;
+  API_END
+}
+
+int oprl_batch_bind(oprl_engine* e, float* s, float* a, float* r, float* d, float* s2, int cap) {
+  if (!e || !s || !a || !r || !d || !s2 || cap <= 0) return fail(-1, "bad batch arena");
+  e->bs = s; e->ba = a; e->br = r; e->bd = d; e->bs2 = s2;
+  e->batch_cap = cap;
+  for (auto& kv : e->work) kv.second->prog.clear();
+  return 0;
+}
+
+static int push_ext_mask(oprl_engine* e) {
+  API_BEGIN
+  if (e->ext_mask) {
+    *e->h_flag = e->ext_mask;
+    CU(cudaMemcpyAsync(&e->d_state->ext_noise, e->h_flag, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    e->ext_mask = 0;
+  }
+  return 0;
+  API_END
+}
+
+int oprl_sample(oprl_engine* e, const int* ep_step_host, int B) {
+  if (!e || B <= 0) return fail(-1, "bad sample call");
+  if (!e->rb_states) return fail(-1, "no replay storage bound");
+  if (e->batch_cap && B > e->batch_cap) return fail(-1, "B=%d exceeds the bound batch arena (%d)", B, e->batch_cap);
+  API_BEGIN
+  oprl_engine::Work* w = get_work(e, B);
+  if (int rc = push_ext_mask(e)) return rc;
+  GatherArgs g = w->gather;
+  g.states = e->rb_states; g.actions = e->rb_actions; g.rewards = e->rb_rewards; g.dones = e->rb_dones;
+  g.L = e->rb_L;
+  g.dense = 0;
+  if (ep_step_host) {
+    for (int i = 0; i < B; ++i) {
+      const int ep = ep_step_host[2 * i], st = ep_step_host[2 * i + 1];
+      if (ep < 0 || ep >= e->rb_E || st < 0 || st >= e->rb_L)
+        return fail(-1, "index %d out of range: episode %d step %d", i, ep, st);
+    }
+    CU(cudaMemcpyAsync(w->d_idx, ep_step_host, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, e->stream));
+    g.ep_step = w->d_idx;
+  } else {
+    if (!e->d_prefix || e->n_trans <= 0) return fail(-1, "device sampling needs oprl_buffer_set_prefix");
+    g.ep_step = nullptr;
+    g.prefix = e->d_prefix;
+    g.n_eps = e->n_eps;
+    g.n_trans = e->n_trans;
+    g.out_ep_step = w->d_idx;
+  }
+  launch_gather(e, w, g);
+  e->cur_B = B;
+  return 0;
+  API_END
+}
+
+int oprl_load_batch(oprl_engine* e, const float* s, const float* a, const float* r, const float* d,
+                    const float* s2, int B) {
+  if (!e || !s || !a || !r || !d || !s2 || B <= 0) return fail(-1, "bad batch");
+  API_BEGIN
+  oprl_engine::Work* w = get_work(e, B);
+  if (B > e->batch_cap) return fail(-1, "B=%d exceeds the bound batch arena (%d)", B, e->batch_cap);
+  if (int rc = push_ext_mask(e)) return rc;
+  GatherArgs g = w->gather;
+  g.states = s; g.actions = a; g.rewards = r; g.dones = d; g.next_states = s2;
+  g.dense = 1;
+  launch_gather(e, w, g);
+  e->cur_B = B;
+  return 0;
+  API_END
+}
+
+int oprl_set_noise(oprl_engine* e, int which, const float* noise_dev, int n) {
+  if (!e || which < 0 || which > 1 || !noise_dev) return fail(-1, "bad noise call");
+  const int A = e->cfg.action_dim;
+  if (n <= 0 || n % A) return fail(-1, "noise length %d is not a multiple of action_dim", n);
+  API_BEGIN
+  oprl_engine::Work* w = get_work(e, n / A);
+  CU(cudaMemcpyAsync(w->noise_raw[which], noise_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, e->stream));
+  e->ext_mask |= 1 << which;
+  return 0;
+  API_END
+}
+
+int oprl_update(oprl_engine* e, int flags, int segment) {
+  if (!e) return fail(-1, "null engine");
+  if (!e->cur_B) return fail(-1, "update before sample / load_batch");
+  if (segment < -1 || segment > 2) return fail(-1, "bad segment");
+  for (int k = 0; k < 2; ++k)
+    if (!e->grp[k].theta) return fail(-1, "arena %d not bound", k);
+  API_BEGIN
+  oprl_engine::Work* w = get_work(e, e->cur_B);
+  Program* p = get_program(e, w, flags);
+  cudaGraphExec_t g = p->graph[segment < 0 ? 3 : segment];
+  if (g) CU(cudaGraphLaunch(g, e->stream));
+  return 0;
+  API_END
+}
+
+int oprl_step(oprl_engine* e, int B, int flags) {
+  if (int rc = oprl_sample(e, nullptr, B)) return rc;
+  return oprl_update(e, flags, OPRL_SEG_ALL);
+}
+
+static int read_state(oprl_engine* e) {
+  API_BEGIN
+  CU(cudaMemcpyAsync(e->h_state, e->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+  API_END
+}
+
+int oprl_get_scalars(oprl_engine* e, float* out_host, int n) {
+  if (!e || !out_host || n < 0 || n > 32) return fail(-1, "bad scalars call");
+  if (int rc = read_state(e)) return rc;
+  e->h_state->scalars[SC_ALPHA] = e->h_state->alpha;
+  memcpy(out_host, e->h_state->scalars, sizeof(float) * n);
+  return 0;
+}
+
+int oprl_get_state(oprl_engine* e, oprl_state* out) {
+  if (!e || !out) return fail(-1, "null argument");
+  if (int rc = read_state(e)) return rc;
+  const DevState& s = *e->h_state;
+  out->tick = s.tick;
+  out->step_actor = s.step[0];
+  out->step_critic = s.step[1];
+  out->step_alpha = s.step[2];
+  out->pad = 0;
+  out->log_alpha = s.log_alpha;
+  out->m_alpha = s.m_alpha;
+  out->v_alpha = s.v_alpha;
+  return 0;
+}
+
+int oprl_set_state(oprl_engine* e, const oprl_state* in) {
+  if (!e || !in) return fail(-1, "null argument");
+  if (int rc = read_state(e)) return rc;
+  API_BEGIN
+  DevState& s = *e->h_state;
+  s.tick = in->tick;
+  s.step[0] = in->step_actor;
+  s.step[1] = in->step_critic;
+  s.step[2] = in->step_alpha;
+  s.log_alpha = in->log_alpha;
+  s.m_alpha = in->m_alpha;
+  s.v_alpha = in->v_alpha;
+  s.alpha = static_cast<float>(std::exp(in->log_alpha));
+  CU(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(DevState), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+  API_END
+}
+
+int oprl_sync(oprl_engine* e) {
+  if (!e) return fail(-1, "null engine");
+  API_BEGIN
+  CU(cudaStreamSynchronize(e->stream));
+  return 0;
+  API_END
+}
+
+void* oprl_stream(oprl_engine* e) { return e ? static_cast<void*>(e->stream) : nullptr; }
+
+int oprl_engine_set_stream(oprl_engine* e, void* stream) {
+  if (!e) return fail(-1, "null engine");
+  e->stream = stream ? static_cast<cudaStream_t>(stream) : e->own_stream;
+  return 0;
+}
+
+int oprl_gather_rows(const float* states, const float* actions, const float* rewards,
+                     const float* dones, int E, int L, int S, int A, const int* ep_step_host,
+                     int* ep_step_dev, int B, float* s, float* a, float* r, float* d, float* s2,
+                     void* stream) {
+  if (!states || !actions || !rewards || !dones || !ep_step_host || !ep_step_dev || !s || !a || !r ||
+      !d || !s2 || B <= 0 || E <= 0 || L <= 0)
+    return fail(-1, "bad gather_rows call");
+  for (int i = 0; i < B; ++i) {
+    const int ep = ep_step_host[2 * i], st = ep_step_host[2 * i + 1];
+    if (ep < 0 || ep >= E || st < 0 || st >= L)
+      return fail(-1, "index %d out of range: episode %d step %d", i, ep, st);
+  }
+  API_BEGIN
+  cudaStream_t sm = static_cast<cudaStream_t>(stream);
+  CU(cudaMemcpyAsync(ep_step_dev, ep_step_host, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, sm));
+  RowGatherArgs g{states, actions, rewards, dones, ep_step_dev, L, S, A, B, s, a, r, d, s2};
+  gather_rows_kernel<<<B, kGatherThreads, 0, sm>>>(g);
+  CU(cudaGetLastError());
+  return 0;
+  API_END
+}
+
+int oprl_update_launches(oprl_engine* e, int B, int flags) {
+  if (!e || B <= 0) return fail(-1, "bad argument");
+  API_BEGIN
+  oprl_engine::Work* w = get_work(e, B);
+  return get_program(e, w, flags)->n_launches;
+  API_END
+}
+
+/* what = 0: replay only the GEMM launches of one update `iters` times; what = 1: the gather
+ * (device-side index draw) `iters` times.  Timed with CUDA events on the launch stream. */
+int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* ms_total, int* launches_per_iter) {
+  if (!e || B <= 0 || iters <= 0 || !ms_total) return fail(-1, "bad argument");
+  API_BEGIN
+  oprl_engine::Work* w = get_work(e, B);
+  Program* p = get_program(e, w, flags);
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  auto body = [&]() -> int {
+    if (what == 0) {
+      if (p->graph[4]) CU(cudaGraphLaunch(p->graph[4], e->stream));
+      return 0;
+    }
+    return oprl_sample(e, nullptr, B);
+  };
+  for (int i = 0; i < 5; ++i)
+    if (int rc = body()) return rc;
+  CU(cudaEventRecord(e0, e->stream));
+  for (int i = 0; i < iters; ++i)
+    if (int rc = body()) return rc;
+  CU(cudaEventRecord(e1, e->stream));
+  CU(cudaEventSynchronize(e1));
+  CU(cudaEventElapsedTime(ms_total, e0, e1));
+  CU(cudaEventDestroy(e0));
+  CU(cudaEventDestroy(e1));
+  if (launches_per_iter) *launches_per_iter = what == 0 ? p->n_gemm_launches : 1;
+  return 0;
+  API_END
+}
+
+}  // extern "C"
+
+namespace oprl {
+static void build_sac_tqc(oprl_engine*, oprl_engine::Work*, Program*) {
+  throw std::runtime_error("SAC / TQC programs are not built yet");
+}
+}  // namespace oprl

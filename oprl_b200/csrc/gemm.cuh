@@ -48,7 +48,7 @@ constexpr int kStageFloats = 2 * kAFloats + 2 * kBFloats;
 constexpr int kStageBytes = kStageFloats * 4;  // 40 KB
 constexpr int kGemmThreads = 192;
 constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024;
-constexpr int kMaxOps = 8;
+constexpr int kMaxOps = 12;
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
@@ -80,6 +80,7 @@ struct GemmOp {
   int rs_ld, rs_n;
   int addm_ld, addm_n;
   int m_valid;  // rows m >= m_valid are forced to 0 before any output (0 = no limit)
+  int n_valid;  // columns n >= n_valid are forced to 0 before any output (0 = no limit)
   int t_rows, t_c0, t_n;
   int tt_rows;
   int rm_ld, rm_trans, rm_m, rm_n;
@@ -313,6 +314,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (o.m_valid > 0 && m >= o.m_valid) {
 #pragma unroll
       for (int j = 0; j < kBN; ++j) v[j] = 0.f;
+    }
+    if (o.n_valid > 0) {
+#pragma unroll
+      for (int j = 0; j < kBN; ++j)
+        if (n0 + j >= o.n_valid) v[j] = 0.f;
     }
     // ---- outputs
     if (o.t_hi) {

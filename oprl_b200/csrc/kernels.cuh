@@ -1,6 +1,6 @@
 // SIMT kernels around the GEMM chain: replay-buffer gather (K0 in SURVEY.md §2b),
 // TD target + MSE seed gradient (K3/K4), fused Adam + Polyak + tf32 re-tiling
-// (K6/K9/K10), per-update prologue (counters + noise).  All HBM/latency bound.
+// (K6/K9/K10), counters + noise draws.  All HBM/latency bound.
 #pragma once
 #include <curand_kernel.h>
 #include "gemm.cuh"
@@ -16,14 +16,14 @@ struct TM {  // CT32 tiled matrix, tf32 hi/lo halves
 
 // Engine scalars that live on the device so a captured CUDA graph can replay.
 struct DevState {
-  unsigned long long tick;  // number of updates started (noise stream offset)
+  unsigned long long tick;  // number of updates completed (noise / sampling stream offset)
   int step[4];              // Adam step counts: 0 actor, 1 critic, 2 alpha
-  int use_ext_noise;        // 1: caller supplied noise for this update, skip generation
+  int ext_noise;            // bit w: the caller injected the w-th normal draw of the next update
   int pad0;
   double log_alpha, m_alpha, v_alpha;  // SAC/TQC temperature, float64 like the reference
   float alpha;                         // exp(log_alpha) rounded to fp32
   float pad1;
-  float scalars[32];  // 0 critic_loss, 1 actor_loss, 2 alpha_loss, 3 mean q, 4 mean q_target, 5 mean logpi
+  float scalars[32];  // see enum Scalar
 };
 
 enum Scalar : int {
@@ -34,6 +34,7 @@ enum Scalar : int {
   SC_QT_MEAN = 4,
   SC_LOGPI_MEAN = 5,
   SC_Q_ERR_MEAN = 6,
+  SC_ALPHA = 7,
 };
 
 __device__ __forceinline__ void store_tiled(const TM& t, int r, int c, float x) {
@@ -44,47 +45,16 @@ __device__ __forceinline__ void store_tiled(const TM& t, int r, int c, float x) 
   t.lo[off] = lo;
 }
 
-// ------------------------------------------------------------------ prologue
-// One block.  Bumps the update tick and Adam step counters (so that every later
-// kernel of the same graph replay reads the new values) and draws the standard
-// normal noise of this update with Philox unless the caller injected its own.
+// Standard-normal draws of one update.  raw[i] is either injected by the caller
+// (parity tests: the reference's torch.randn stream) or drawn here with Philox;
+// out[i] = clip(raw[i] * scale, +-clip)  (TD3 target-policy smoothing, td3.py:98-100).
 struct NoiseSpec {
-  float* dst;   // [n]
+  float* raw;   // [n]
+  float* out;   // [n] (may alias raw when scale == 1 and clip <= 0), nullable
   int n;
-  float scale;  // TD3: policy_noise ; SAC/TQC: 1
-  float clip;   // TD3: noise_clip ; <= 0: no clip
+  float scale;
+  float clip;  // <= 0: no clip
 };
-__global__ void prologue_kernel(DevState* st, int bump_actor, int bump_critic, int bump_alpha,
-                                NoiseSpec n0, NoiseSpec n1, unsigned long long seed) {
-  const unsigned long long tick = st->tick;
-  const int ext = st->use_ext_noise;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    st->tick = tick + 1;
-    st->step[0] += bump_actor;
-    st->step[1] += bump_critic;
-    st->step[2] += bump_alpha;
-    st->use_ext_noise = 0;
-  }
-  if (ext) return;
-  const int total = n0.n + n1.n;
-  for (int base = threadIdx.x * 4; base < total; base += blockDim.x * 4) {
-    curandStatePhilox4_32_10_t rng;
-    curand_init(seed, static_cast<unsigned long long>(base >> 2), tick * 8ull, &rng);
-    const float4 z = curand_normal4(&rng);
-    const float zz[4] = {z.x, z.y, z.z, z.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = base + k;
-      if (i >= total) break;
-      const NoiseSpec& s = (i < n0.n) ? n0 : n1;
-      const int j = (i < n0.n) ? i : i - n0.n;
-      float v = zz[k] * s.scale;
-      if (s.clip > 0.f) v = fminf(fmaxf(v, -s.clip), s.clip);
-      s.dst[j] = v;
-    }
-  }
-}
 
 // -------------------------------------------------------------------- gather
 // Reference: EpisodicReplayBuffer.sample, episodic_buffer.py:123-133 -- five
@@ -106,10 +76,43 @@ struct GatherArgs {
   float *bs, *ba, *br, *bd, *bs2;  // row-major batch arena (nullable when dense)
   int* out_ep_step;                 // [B][2] what was sampled (device sampling), nullable
   TM X, XT, Xn, Xp;
+  NoiseSpec noise[2];  // blocks >= B draw the update's normals (n == 0: none)
 };
 
-__global__ void gather_kernel(GatherArgs g, const DevState* st) {
+constexpr int kGatherThreads = 64;
+__global__ void __launch_bounds__(kGatherThreads)
+    gather_kernel(const __grid_constant__ GatherArgs g, const DevState* st) {
   const int b = blockIdx.x;
+  if (b >= g.B) {
+    // ---- noise blocks: 4 normals per thread, one Philox subsequence per quad
+    const int total = g.noise[0].n + g.noise[1].n;
+    const unsigned long long tick = st->tick;
+    const int ext = st->ext_noise;
+    for (int base = ((b - g.B) * kGatherThreads + threadIdx.x) * 4; base < total;
+         base += (gridDim.x - g.B) * kGatherThreads * 4) {
+      curandStatePhilox4_32_10_t rng;
+      curand_init(g.seed, static_cast<unsigned long long>(base >> 2), tick * 8ull, &rng);
+      const float4 z = curand_normal4(&rng);
+      const float zz[4] = {z.x, z.y, z.z, z.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = base + k;
+        if (i >= total) break;
+        const int w = (i < g.noise[0].n) ? 0 : 1;
+        const NoiseSpec& sp = g.noise[w];
+        const int j = w ? i - g.noise[0].n : i;
+        float v;
+        if (ext & (1 << w)) v = sp.raw[j];
+        else { v = zz[k]; sp.raw[j] = v; }
+        if (sp.out) {
+          v *= sp.scale;
+          if (sp.clip > 0.f) v = fminf(fmaxf(v, -sp.clip), sp.clip);
+          sp.out[j] = v;
+        }
+      }
+    }
+    return;
+  }
   __shared__ int s_ep, s_step;
   if (threadIdx.x == 0) {
     int ep = 0, step = 0;
@@ -186,6 +189,31 @@ __global__ void gather_kernel(GatherArgs g, const DevState* st) {
   }
 }
 
+// Plain row-major gather (EpisodicReplayBuffer.sample without an attached engine,
+// episodic_buffer.py:127-133): one block per sampled transition.
+struct RowGatherArgs {
+  const float *states, *actions, *rewards, *dones;
+  const int* ep_step;
+  int L, S, A, B;
+  float *s, *a, *r, *d, *s2;
+};
+__global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(RowGatherArgs g) {
+  const int b = blockIdx.x;
+  const int ep = g.ep_step[2 * b], step = g.ep_step[2 * b + 1];
+  const size_t row = static_cast<size_t>(ep) * g.L + step;
+  const float* src_s = g.states + (static_cast<size_t>(ep) * (g.L + 1) + step) * g.S;
+  const float* src_a = g.actions + row * g.A;
+  for (int c = threadIdx.x; c < 2 * g.S + g.A; c += blockDim.x) {
+    if (c < g.S) g.s[static_cast<size_t>(b) * g.S + c] = src_s[c];
+    else if (c < 2 * g.S) g.s2[static_cast<size_t>(b) * g.S + c - g.S] = src_s[c];  // adjacent row
+    else g.a[static_cast<size_t>(b) * g.A + c - 2 * g.S] = src_a[c - 2 * g.S];
+  }
+  if (threadIdx.x == 0) {
+    g.r[b] = g.rewards[row];
+    g.d[b] = g.dones[row];
+  }
+}
+
 // ---------------------------------------------------------------- block reduce
 template <int kThreads>
 __device__ __forceinline__ float block_sum(float v, float* sh) {
@@ -215,7 +243,9 @@ struct TdArgs {
   const float* d;
   const float* logpi_next;  // SAC: [Bp] log pi(a'|s') (nullable)
   float gamma;
+  float inv_count;  // 1 / (global batch rows): the losses are means over all learners' rows
   int B, nq;
+  int bump_actor;   // this update also steps the actor (Adam step counter)
   TM D3[2];
   TM D3T[2];
   float* db3[2];  // gradient slot of each critic's output bias
@@ -224,7 +254,7 @@ struct TdArgs {
 constexpr int kTdThreads = 256;
 __global__ void __launch_bounds__(kTdThreads) td_kernel(TdArgs a, DevState* st) {
   __shared__ float sh[kTdThreads];
-  const float invB = 1.0f / static_cast<float>(a.B);
+  const float invB = a.inv_count;
   float loss[2] = {0.f, 0.f}, dsum[2] = {0.f, 0.f}, qsum = 0.f, ysum = 0.f, esum = 0.f;
   const float alpha = st->alpha;
   for (int m = threadIdx.x; m < a.B; m += kTdThreads) {
@@ -260,6 +290,12 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(TdArgs a, DevState* st) 
     st->scalars[SC_Q_MEAN] = qs * invB;
     st->scalars[SC_QT_MEAN] = ys * invB;
     st->scalars[SC_Q_ERR_MEAN] = es * invB;
+    // Everything that consumed the old tick (sampling, noise) ran in earlier launches;
+    // everything that needs the new Adam step counts runs in later ones.
+    st->tick += 1;
+    st->step[1] += 1;
+    st->step[0] += a.bump_actor;
+    st->ext_noise = 0;
   }
 }
 
@@ -282,9 +318,12 @@ struct AdamSeg {
   int split, off_lo, off_hi;  // tiled col = j < split ? j + off_lo : j - split + off_hi
   int opt;                    // 0 actor, 1 critic
 };
-struct AdamHyper {
-  float lr[2];
-  float beta1, beta2, eps, tau;
+struct AdamHyper {  // python doubles of torch.optim.Adam, rounded to fp32 where torch does
+  double lr[2];
+  double beta1, beta2;
+  float w1, w2;  // (float)(1 - beta1), (float)(1 - beta2)
+  float beta2f, eps;
+  float tau, one_minus_tau;  // (float)tau, (float)(1 - tau)
 };
 constexpr int kAdamThreads = 256;
 // mode: bit0 = Adam step, bit1 = Polyak, bit2 = (re)tile online weights, bit3 = tile targets
@@ -294,14 +333,14 @@ __global__ void __launch_bounds__(kAdamThreads)
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0 && (mode & 1)) {
     const int t = st->step[sg.opt];
-    const double bc1 = 1.0 - pow(static_cast<double>(hp.beta1), static_cast<double>(t));
-    const double bc2 = 1.0 - pow(static_cast<double>(hp.beta2), static_cast<double>(t));
-    s_step_size = static_cast<float>(static_cast<double>(hp.lr[sg.opt]) / bc1);
+    const double bc1 = 1.0 - pow(hp.beta1, static_cast<double>(t));
+    const double bc2 = 1.0 - pow(hp.beta2, static_cast<double>(t));
+    s_step_size = static_cast<float>(hp.lr[sg.opt] / bc1);
     s_bc2_sqrt = static_cast<float>(sqrt(bc2));
   }
   __syncthreads();
-  const float w1 = 1.0f - hp.beta1;
-  const float w2 = 1.0f - hp.beta2;
+  const float w1 = hp.w1;
+  const float w2 = hp.w2;
   for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.n; i += gridDim.x * kAdamThreads) {
     float p = sg.theta[i];
     if (mode & 1) {
@@ -309,9 +348,9 @@ __global__ void __launch_bounds__(kAdamThreads)
       float m = sg.m[i];
       float v = sg.v[i];
       m = fmaf(w1, g - m, m);                              // exp_avg.lerp_(grad, 1 - beta1)
-      v = __fadd_rn(__fmul_rn(v, hp.beta2), __fmul_rn(__fmul_rn(w2, g), g));  // mul_().addcmul_()
+      v = __fadd_rn(__fmul_rn(v, hp.beta2f), __fmul_rn(__fmul_rn(w2, g), g));  // mul_().addcmul_()
       const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s_bc2_sqrt), hp.eps);
-      p = __fadd_rn(p, __fmul_rn(-s_step_size, __fdiv_rn(m, denom)));       // addcdiv_
+      p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-s_step_size, m), denom));  // addcdiv_: p + (value*m)/denom
       sg.m[i] = m;
       sg.v[i] = v;
       sg.theta[i] = p;
@@ -320,7 +359,7 @@ __global__ void __launch_bounds__(kAdamThreads)
     if (sg.target) {
       tp = sg.target[i];
       if (mode & 2) {
-        tp = __fadd_rn(__fmul_rn(hp.tau, p), __fmul_rn(1.0f - hp.tau, tp));
+        tp = __fadd_rn(__fmul_rn(hp.tau, p), __fmul_rn(hp.one_minus_tau, tp));
         sg.target[i] = tp;
       }
     }

@@ -1,0 +1,93 @@
+"""GPU parity: the CUDA engine (through the C ABI / python shim) against the fixtures produced
+by the reference itself, and against the CPU oracle on fresh seeded inputs.
+
+Bars (BASELINE.json north_star): |loss - loss_ref| <= 1e-4 and ||theta - theta_ref||_2 <= 1e-5
+over the concatenation of all networks after one update, fixed seeds + fixed minibatch."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import (fixture_batch, fixture_noise, load_case, oracle_from_fixture,
+                        run_fixture_updates, spec_from_fixture)
+
+pytestmark = pytest.mark.gpu
+
+LOSS_TOL = 1e-4
+PARAM_L2_TOL = 1e-5
+
+
+def make_algo(fx, **kw):
+    from oprl_b200.algos.ddpg import DDPG
+    from oprl_b200.algos.td3 import TD3
+
+    spec = spec_from_fixture(fx)
+
+    class NullLogger:
+        log_dir = "/tmp"
+
+        def log_scalar(self, *a, **k):
+            pass
+
+        def log_scalars(self, *a, **k):
+            pass
+
+    cls = dict(ddpg=DDPG, td3=TD3)[spec.algo]
+    algo = cls(logger=NullLogger(), state_dim=spec.state_dim, action_dim=spec.action_dim, **kw).create()
+    return algo
+
+
+def load_initial(algo, orc):
+    ar = algo.engine.arena
+    for name in ("actor", "critic"):
+        flat = torch.from_numpy(orc.flat(name)).cuda()
+        ar[name]["theta"].copy_(flat)
+        if ar[name]["target"] is not None:
+            ar[name]["target"].copy_(flat)
+    algo.engine.mark_params_dirty()
+
+
+def engine_flat(algo, which):
+    ar = algo.engine.arena
+    name, key = {"actor": ("actor", "theta"), "critic": ("critic", "theta"),
+                 "actor_target": ("actor", "target"), "critic_target": ("critic", "target")}[which]
+    t_ = ar[name][key]
+    return None if t_ is None else t_.detach().cpu().numpy()
+
+
+def compare_to_fixture(algo, fx, tag):
+    sub = int(fx["subsample"])
+    sq = 0.0
+    for key in ("actor", "critic", "critic_target", "actor_target"):
+        k = f"{tag}_{key}"
+        if k not in fx:
+            continue
+        got = engine_flat(algo, key)[::sub]
+        sq += float(((got.astype(np.float64) - fx[k].astype(np.float64)) ** 2).sum())
+    return np.sqrt(sq * sub)  # subsampled fixtures: scale to the full-vector estimate
+
+
+@pytest.mark.parametrize("name", ["ddpg", "ddpg_b8", "td3"])
+def test_fixture_parity(name):
+    fx = load_case(name)
+    orc = oracle_from_fixture(fx)
+    algo = make_algo(fx)
+    load_initial(algo, orc)
+    K = int(fx["K"])
+    for k in range(K):
+        noise = fixture_noise(fx, k)
+        for i, nz in enumerate(noise):
+            algo.engine.set_noise(i, nz)
+        batch = [x.cuda() for x in fixture_batch(fx, k)]
+        algo.update(*batch)
+        sc = algo.engine.scalars()
+        for key in ("critic_loss", "actor_loss"):
+            fk = f"scalar{k}_{key}"
+            if fk in fx:
+                assert abs(sc[key] - float(fx[fk])) <= LOSS_TOL, (k, key, sc[key], float(fx[fk]))
+        if k == 0:
+            l2 = compare_to_fixture(algo, fx, "first")
+            print(f"{name}: param L2 after 1 update = {l2:.3e}")
+            assert l2 <= PARAM_L2_TOL
+    l2 = compare_to_fixture(algo, fx, "last")
+    print(f"{name}: param L2 after {K} updates = {l2:.3e}")
+    assert l2 <= PARAM_L2_TOL * K
