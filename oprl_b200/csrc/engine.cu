@@ -371,7 +371,7 @@ struct Builder {
           GemmOp o = *dx_epilogue;
           o.a_hi = dz.hi; o.a_lo = dz.lo; o.a_rows = dz.rows;
           o.b_hi = ly.WT.hi; o.b_lo = ly.WT.lo; o.b_rows = ly.WT.rows;
-          o.M = Bp; o.N = 32; o.K = ly.Np;
+          o.M = Bp; o.N = pad32(A); o.K = ly.Np;  // N tiles covering the action columns
           o.passes = passes;
           stage(s).ops.push_back(o);
         }
@@ -537,21 +537,21 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       CU(cudaStreamSynchronize(e->stream));
     }
     // critic dX chain down to the action columns, then tanh'
-    TM dza = e->alloc_tm(Bp, 32);
-    TM dzaT = e->alloc_tm(128, Bp);
     const Layer& a_last = ga.nets[0].L.back();
+    TM dza = e->alloc_tm(Bp, a_last.Np);
+    TM dzaT = e->alloc_tm(pad128(a_last.out), Bp);
     GemmOp dx;
     memset(&dx, 0, sizeof(dx));
     dx.alpha = 1.f;
     dx.rs = a_rm; dx.rs_ld = A; dx.rs_n = A;
     dx.t_hi = dza.hi; dx.t_lo = dza.lo; dx.t_rows = Bp; dx.t_c0 = 0; dx.t_n = A;
-    dx.tt_hi = dzaT.hi; dx.tt_lo = dzaT.lo; dx.tt_rows = 128;
+    dx.tt_hi = dzaT.hi; dx.tt_lo = dzaT.lo; dx.tt_rows = dzaT.rows;
     dx.n_valid = A;  // columns >= A of this tile are pad / state gradients: drop them
-    dx.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * 32);
-    dx.colsum_ld = 32;
+    dx.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * a_last.Np);
+    dx.colsum_ld = a_last.Np;
     dx.colsum_n = a_last.out;
     dx.colsum_out = ga.grad + a_last.b_off;
-    dx.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+    dx.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(a_last.Np / kBN));
     s = b.backward(s, gc.nets[0], nullptr, p_cq, Dm, TM{nullptr, nullptr, 0, 0}, w->XT, false, false, &dx);
     // actor backward
     s = b.backward(s, ga.nets[0], ga.grad, p_a, dza, dzaT, w->XT, true, true, nullptr);
@@ -560,6 +560,237 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     b.stage(s).simt = [e, &ga](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm); };
     ++s;
   }
+}
+
+}  // namespace oprl
+
+// ================================================================== SAC / TQC program
+namespace oprl {
+
+static void fill_constant_seed(oprl_engine* e, const TM& D, int B, int ncols, float value) {
+  // tiled [Bp x 32] matrix with `value` in columns [0, ncols) of rows [0, B)
+  std::vector<float> hi(static_cast<size_t>(D.rows) * D.cols, 0.f), lo(hi.size(), 0.f);
+  auto rnd = [](float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+  };
+  const float h = rnd(value), l = rnd(value - rnd(value));
+  for (int m = 0; m < B; ++m)
+    for (int c = 0; c < ncols; ++c) {
+      hi[ct_index(D.rows, m, c)] = h;
+      lo[ct_index(D.rows, m, c)] = l;
+    }
+  CU(cudaMemcpyAsync(D.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(D.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+}
+
+static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
+  const oprl_cfg& c = e->cfg;
+  const bool tqc = c.algo == OPRL_ALGO_TQC;
+  const int B = w->B, Bp = w->Bp, A = c.action_dim, nc = c.n_critics;
+  const int nq = tqc ? c.n_quantiles : 1;  // outputs per critic
+  const int NT = nc * nq;
+  if (nc > kMaxNets) throw std::runtime_error("too many critics");
+  if (tqc && NT > kTqcThreads) throw std::runtime_error("n_nets * n_quantiles must be <= 128");
+  Builder b{e, w, p, c.gemm_mode == OPRL_GEMM_TC_TF32 ? 1 : 3};
+  Group& ga = e->grp[OPRL_NET_ACTOR];
+  Group& gc = e->grp[OPRL_NET_CRITIC];
+  DevState* st = e->d_state;
+  const float inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
+  const Layer& a_last = ga.nets[0].L.back();
+
+  float* out_n = e->alloc_floats(static_cast<size_t>(Bp) * 2 * A);  // actor(s') raw output
+  float* out_p = e->alloc_floats(static_cast<size_t>(Bp) * 2 * A);  // actor(s)  raw output
+  float* logp2 = e->alloc_floats(Bp);
+  float* logp = e->alloc_floats(Bp);
+  float* a_rm = e->alloc_floats(static_cast<size_t>(Bp) * A);
+  float* z = e->alloc_floats(static_cast<size_t>(Bp) * NT);    // online critics at (s, a)
+  float* zn = e->alloc_floats(static_cast<size_t>(Bp) * NT);   // target critics at (s', a')
+  float* zpi = e->alloc_floats(static_cast<size_t>(Bp) * NT);  // online critics at (s, pi(s))
+
+  std::vector<Pass> p_c(nc), p_ct(nc), p_cq(nc);
+  Pass p_an, p_a;
+  int s = 0;
+  // ---- critic step ------------------------------------------------------------
+  // next action from the ONLINE actor (sac.py:97, tqc.py:131) ; critics at (s, a)
+  int s_act;
+  {
+    GemmOp last;
+    s_act = b.forward(s, ga.nets[0], ga.theta, false, w->Xn, p_an, false, &last);
+    last.rm = out_n; last.rm_ld = 2 * A; last.rm_m = Bp; last.rm_n = 2 * A;
+    b.stage(s_act - 1).ops.push_back(last);
+    for (int i = 0; i < nc; ++i) {
+      GemmOp lq;
+      const int se = b.forward(s, gc.nets[i], gc.theta, false, w->X, p_c[i], true, &lq);
+      lq.rm = z + i * nq; lq.rm_ld = NT; lq.rm_m = Bp; lq.rm_n = nq;
+      b.stage(se - 1).ops.push_back(lq);
+      s = std::max(s, se);
+    }
+  }
+  {
+    HeadFwdArgs h;
+    memset(&h, 0, sizeof(h));
+    h.out = out_n; h.eps = w->noise_raw[0]; h.B = B; h.A = A; h.X = w->Xn; h.a_rm = nullptr; h.logp = logp2;
+    const int blocks = (B + kHeadThreads - 1) / kHeadThreads;
+    b.stage(s_act).simt = [h, blocks](cudaStream_t sm) { head_fwd_kernel<<<blocks, kHeadThreads, 0, sm>>>(h); };
+  }
+  s = std::max(s, s_act + 1);
+  // target critics at (s', a')
+  {
+    int s_end = s;
+    for (int i = 0; i < nc; ++i) {
+      GemmOp lq;
+      s_end = b.forward(s, gc.nets[i], gc.target, true, w->Xn, p_ct[i], false, &lq);
+      lq.rm = zn + i * nq; lq.rm_ld = NT; lq.rm_m = Bp; lq.rm_n = nq;
+      b.stage(s_end - 1).ops.push_back(lq);
+    }
+    s = std::max(s, s_end);
+  }
+  // loss + seeds
+  std::vector<TM> D(nc), DT(nc);
+  for (int i = 0; i < nc; ++i) {
+    D[i] = e->alloc_tm(Bp, 32);
+    DT[i] = e->alloc_tm(128, Bp);
+  }
+  if (!tqc) {
+    TdArgs td;
+    memset(&td, 0, sizeof(td));
+    td.qn = zn; td.q = z; td.r = e->br; td.d = e->bd; td.logpi_next = logp2;
+    td.gamma = static_cast<float>(c.gamma);
+    td.inv_count = inv_count;
+    td.B = B; td.nq = nc;
+    td.bump_actor = 1;
+    for (int i = 0; i < nc; ++i) {
+      td.D3[i] = D[i];
+      td.D3T[i] = DT[i];
+      td.db3[i] = gc.grad + gc.nets[i].L.back().b_off;
+    }
+    b.stage(s).simt = [td, st](cudaStream_t sm) { td_kernel<<<1, kTdThreads, 0, sm>>>(td, st); };
+  } else {
+    TqcArgs t;
+    memset(&t, 0, sizeof(t));
+    t.zn = zn; t.z = z; t.r = e->br; t.d = e->bd; t.logp2 = logp2;
+    t.gamma = static_cast<float>(c.gamma);
+    t.keep = NT - c.top_quantiles_to_drop;
+    t.inv_total = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size * NT * t.keep));
+    t.B = B; t.n_nets = nc; t.nq = nq;
+    t.bump_actor = 1;
+    for (int i = 0; i < nc; ++i) {
+      t.dZ[i] = D[i];
+      t.dZT[i] = DT[i];
+      t.db[i] = gc.grad + gc.nets[i].L.back().b_off;
+    }
+    t.dz_rm = e->alloc_floats(static_cast<size_t>(Bp) * NT);
+    t.loss_part = e->alloc_floats(Bp);
+    t.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+    b.stage(s).simt = [t, st, B](cudaStream_t sm) { tqc_loss_kernel<<<B, kTqcThreads, 0, sm>>>(t, st); };
+  }
+  ++s;
+  {
+    int s_end = s;
+    for (int i = 0; i < nc; ++i)
+      s_end = b.backward(s, gc.nets[i], gc.grad, p_c[i], D[i], DT[i], w->XT, true, false, nullptr);
+    s = s_end;
+  }
+  b.seg = 1;
+  // critic Adam + Polyak (sac.py:85 soft_update at the end of update() touches nothing the actor
+  // step reads; tqc.py:154-159 does it right here) + re-tiling
+  b.stage(s).simt = [e, &gc](cudaStream_t sm) { launch_adam(e, gc, 1 | 2 | 4 | 8, sm); };
+  ++s;
+  // ---- actor step ---------------------------------------------------------------
+  {
+    GemmOp last;
+    const int se = b.forward(s, ga.nets[0], ga.theta, false, w->Xp, p_a, true, &last);
+    last.rm = out_p; last.rm_ld = 2 * A; last.rm_m = Bp; last.rm_n = 2 * A;
+    b.stage(se - 1).ops.push_back(last);
+    s = se;
+    HeadFwdArgs h;
+    memset(&h, 0, sizeof(h));
+    h.out = out_p; h.eps = w->noise_raw[1]; h.B = B; h.A = A; h.X = w->Xp; h.a_rm = a_rm; h.logp = logp;
+    const int blocks = (B + kHeadThreads - 1) / kHeadThreads;
+    b.stage(s).simt = [h, blocks](cudaStream_t sm) { head_fwd_kernel<<<blocks, kHeadThreads, 0, sm>>>(h); };
+    ++s;
+  }
+  // critics at (s, pi(s)) with the just-updated weights
+  {
+    int s_end = s;
+    for (int i = 0; i < nc; ++i) {
+      GemmOp lq;
+      s_end = b.forward(s, gc.nets[i], gc.theta, false, w->Xp, p_cq[i], false, &lq);
+      lq.rm = zpi + i * nq; lq.rm_ld = NT; lq.rm_m = Bp; lq.rm_n = nq;
+      b.stage(s_end - 1).ops.push_back(lq);
+    }
+    s = s_end;
+  }
+  // actor-loss scalars + seeds
+  std::vector<TM> Dq(nc);
+  for (int i = 0; i < nc; ++i) Dq[i] = e->alloc_tm(Bp, 32);
+  {
+    ActorSeedArgs as;
+    memset(&as, 0, sizeof(as));
+    as.q = zpi; as.logp = logp; as.B = B; as.nq = NT; as.tqc = tqc ? 1 : 0;
+    as.inv_count = inv_count;
+    as.target_entropy = static_cast<float>(c.target_entropy);
+    if (!tqc) {
+      as.D[0] = Dq[0];
+      as.D[1] = Dq[1];
+    } else {
+      // d/dz of -mean_rows(mean_{i,j} z): constant
+      for (int i = 0; i < nc; ++i)
+        fill_constant_seed(e, Dq[i], B, nq, static_cast<float>(-1.0 / (static_cast<double>(B) * c.world_size * NT)));
+    }
+    b.stage(s).simt = [as, st](cudaStream_t sm) { actor_seed_kernel<<<1, kTdThreads, 0, sm>>>(as, st); };
+    ++s;
+  }
+  // critic dX chains -> per-critic action gradients (row-major)
+  HeadBwdArgs hb;
+  memset(&hb, 0, sizeof(hb));
+  {
+    int s_end = s;
+    for (int i = 0; i < nc; ++i) {
+      float* da = e->alloc_floats(static_cast<size_t>(Bp) * A);
+      hb.da[i] = da;
+      GemmOp dx;
+      memset(&dx, 0, sizeof(dx));
+      dx.alpha = 1.f;
+      dx.rm = da; dx.rm_ld = A; dx.rm_m = Bp; dx.rm_n = A;
+      s_end = b.backward(s, gc.nets[i], nullptr, p_cq[i], Dq[i], TM{nullptr, nullptr, 0, 0}, w->XT, false, false, &dx);
+    }
+    s = s_end;
+  }
+  // head backward -> dz of the actor's last layer
+  {
+    hb.out = out_p; hb.eps = w->noise_raw[1]; hb.a_rm = a_rm;
+    hb.n_da = nc; hb.B = B; hb.A = A;
+    hb.inv_count = inv_count;
+    hb.dz = e->alloc_tm(Bp, a_last.Np);
+    hb.dzT = e->alloc_tm(pad128(a_last.out), Bp);
+    hb.db = ga.grad + a_last.b_off;
+    const int blocks = (B + kHeadThreads - 1) / kHeadThreads;
+    hb.partial = e->alloc_floats(static_cast<size_t>(blocks) * 2 * A);
+    hb.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+    const size_t smem = static_cast<size_t>(kHeadThreads) * 2 * A * sizeof(float);
+    b.stage(s).simt = [hb, st, blocks, smem](cudaStream_t sm) {
+      head_bwd_kernel<<<blocks, kHeadThreads, smem, sm>>>(hb, st);
+    };
+    ++s;
+  }
+  s = b.backward(s, ga.nets[0], ga.grad, p_a, hb.dz, hb.dzT, w->XT, true, true, nullptr);
+  // actor Adam + temperature step (sac.py:132-141, tqc.py:175-177)
+  b.seg = 2;
+  AlphaStep al;
+  al.enabled = c.tune_alpha ? 1 : 0;
+  al.lr = c.lr_alpha;
+  b.stage(s).simt = [e, &ga, al, st](cudaStream_t sm) {
+    launch_adam(e, ga, 1 | 4, sm);
+    alpha_step_kernel<<<1, 32, 0, sm>>>(st, al);
+  };
+  ++s;
 }
 
 }  // namespace oprl
@@ -1074,8 +1305,3 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
 
 }  // extern "C"
 
-namespace oprl {
-static void build_sac_tqc(oprl_engine*, oprl_engine::Work*, Program*) {
-  throw std::runtime_error("SAC / TQC programs are not built yet");
-}
-}  // namespace oprl

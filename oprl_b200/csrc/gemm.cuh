@@ -12,6 +12,11 @@
 // * fp32-accurate products on tensor cores via 3xTF32:
 //       A*B ~= Alo*Bhi + Ahi*Blo + Ahi*Bhi        (tcgen05.mma.kind::tf32)
 //   (needed for the reference's 1e-5 parameter-L2 parity bar).
+//   The tensor core's accumulator add is not round-to-nearest, so a long accumulation
+//   chain loses ~1 ulp per step (measured: one 96-step chain gave 8x the parameter error of
+//   the FFMA cross-check).  The chain is therefore cut: the two small cross terms go to
+//   their own TMEM accumulator, the Ahi*Bhi terms to one accumulator per group of K
+//   chunks, and the epilogue adds the partial sums with ordinary fp32 adds.
 // * Tile 128 x 32 per CTA, K streamed in 32-wide chunks through a 4-stage
 //   mbarrier ring filled by 1-D bulk async copies (TMA engine, no tensor maps:
 //   the producers already wrote UMMA-canonical core matrices).
@@ -150,7 +155,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     ptx::mbar_init(accum, 1);
     ptx::fence_mbar_init();
   }
-  if (!kSimt && warp == 1) ptx::tmem_alloc(tmem_slot, 32);
+  // accumulators: column block 0 = cross terms, blocks 1.. = hi*hi per group of K chunks
+  const int group = max(2, (nchunks + 14) / 15);
+  const int n_big = (nchunks + group - 1) / group;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(32 * (n_big + 1))) tmem_cols <<= 1;
+  if (!kSimt && warp == 1) ptx::tmem_alloc(tmem_slot, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -209,16 +219,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         for (int j = 0; j < kBK / 8; ++j) {
           const uint64_t da_hi = ptx::smem_desc(sa_hi + j * a_step, a_lbo, a_sbo);
           const uint64_t db_hi = ptx::smem_desc(sb_hi + j * b_step, b_lbo, b_sbo);
-          const uint32_t first = (c | j) ? 1u : 0u;
+          const uint32_t big = tmem_d + 32u * static_cast<uint32_t>(1 + c / group);
+          const uint32_t big_acc = ((c % group) | j) ? 1u : 0u;
           if (passes == 3) {
             const uint64_t da_lo = ptx::smem_desc(sa_lo + j * a_step, a_lbo, a_sbo);
             const uint64_t db_lo = ptx::smem_desc(sb_lo + j * b_step, b_lbo, b_sbo);
-            ptx::mma_tf32(tmem_d, da_lo, db_hi, idesc, first);
+            ptx::mma_tf32(tmem_d, da_lo, db_hi, idesc, (c | j) ? 1u : 0u);
             ptx::mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
-            ptx::mma_tf32(tmem_d, da_hi, db_hi, idesc, 1u);
-          } else {
-            ptx::mma_tf32(tmem_d, da_hi, db_hi, idesc, first);
           }
+          ptx::mma_tf32(big, da_hi, db_hi, idesc, big_acc);
         }
         ptx::mma_commit(&empty[s]);
       }
@@ -234,7 +243,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       ptx::mbar_wait(accum, 0);
       ptx::tc_fence_after();
       if (prof && tid == 64) prof[5] = clock64();
-      ptx::tmem_ld32(*tmem_slot + (static_cast<uint32_t>(q * 32) << 16), v);
+      {
+        const uint32_t lane_base = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16);
+        float part[kBN];
+        ptx::tmem_ld32(lane_base + 32u, v);
+        for (int gi = 1; gi < n_big; ++gi) {
+          ptx::tmem_ld32(lane_base + 32u * static_cast<uint32_t>(1 + gi), part);
+#pragma unroll
+          for (int j = 0; j < kBN; ++j) v[j] += part[j];
+        }
+        if (passes == 3) {
+          ptx::tmem_ld32(lane_base, part);
+#pragma unroll
+          for (int j = 0; j < kBN; ++j) v[j] += part[j];
+        }
+      }
       if (prof && tid == 64) prof[6] = clock64();
     } else {
       // FFMA cross-check path: same smem contents, products on CUDA cores.
@@ -414,7 +437,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   __syncthreads();
   if (!kSimt && warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(*tmem_slot, 32);
+    ptx::tmem_dealloc(*tmem_slot, tmem_cols);
   }
   if (prof && tid == 32) {
     prof[8] = clock64();

@@ -6,7 +6,9 @@ sampled-batch arena are torch CUDA tensors whose ``data_ptr()`` the engine borro
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -53,6 +55,8 @@ class UpdateEngine:
         if not torch.cuda.is_available():
             raise L.EngineError("no CUDA device visible: oprl_b200 has no CPU fallback")
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        if "OPRL_B200_GEMM_MODE" in os.environ:  # 0 = 3xTF32 (default), 1 = single TF32, 2 = FFMA cross-check
+            spec = dataclasses.replace(spec, gemm_mode=int(os.environ["OPRL_B200_GEMM_MODE"]))
         self.spec = spec
         self._lib = L.lib()
         cfg = L.Cfg(

@@ -74,7 +74,54 @@ def n_noise(name):
     return dict(ddpg=0, td3=1, sac=2, tqc=2)[name]
 
 
-def run_case(name, S, A, B, K, seed, subsample=1, synthetic_init=False, **kw):
+MIN_PREACT = 5e-7  # a few times the rounding noise of an fp32-accurate GEMM on these values
+
+
+def first_update_conditioning(name, S, A, B, seed, data_seed, synthetic_init, **kw):
+    """min |hidden ReLU pre-activation| over every forward pass of the FIRST update."""
+    torch.manual_seed(seed)
+    ref = ref_algo(name, S, A, **kw)
+    spec = O.AlgoSpec(algo=name, state_dim=S, action_dim=A, tune_alpha=kw.get("tune_alpha", False),
+                      lr_alpha=3e-4 if name == "tqc" else 1e-3)
+    if synthetic_init:
+        actor0, critics0 = O.init_params(spec, seed)
+    else:
+        actor0 = [p.detach().clone() for p in ref.actor.parameters()]
+        critics0 = [[p.detach().clone() for p in net.parameters()] for net in critic_nets(name, ref.critic)]
+    orc = O.OracleAlgo(spec, actor0, critics0)
+    (batch,) = make_batches(1, B, S, A, data_seed)
+    torch.manual_seed(1000)
+    noise = [torch.randn(B, A) for _ in range(n_noise(name))]
+    O.PREACT_PROBE.update(enabled=True, min_abs=float("inf"))
+    orc.update(*[torch.from_numpy(x) for x in batch], noise=noise)
+    O.PREACT_PROBE["enabled"] = False
+    return O.PREACT_PROBE["min_abs"]
+
+
+def run_case(name, S, A, B, K, seed, subsample=1, synthetic_init=False, min_preact=MIN_PREACT, **kw):
+    """Well-conditioned fixture.  "Parameters after one Adam step" is discontinuous where a hidden
+    ReLU pre-activation sits within rounding noise of zero (the unit's gradient switches on/off and
+    Adam's first step is lr * sign(g)): with ~1e6 pre-activations per update such knife edges are
+    common, and no implementation that is not bit-identical to the reference's BLAS can land on the
+    same side.  So the data seed is advanced until the FIRST update (the one held to the strict
+    1e-5 bar) keeps every pre-activation at least MIN_PREACT away from zero; the margin actually
+    seen over all K updates is recorded for the looser multi-update check."""
+    for data_seed in range(seed + 1, seed + 4000, 10):
+        m0 = first_update_conditioning(name, S, A, B, seed, data_seed, synthetic_init, **kw)
+        if m0 < min_preact:
+            continue
+        O.PREACT_PROBE.update(enabled=True, min_abs=float("inf"))
+        fx = _run_case(name, S, A, B, K, seed, data_seed, subsample, synthetic_init, **kw)
+        O.PREACT_PROBE["enabled"] = False
+        fx["min_abs_preactivation_first"] = np.float64(m0)
+        fx["min_abs_preactivation_all"] = np.float64(O.PREACT_PROBE["min_abs"])
+        print(f"      data seed {data_seed}: min |hidden pre-activation| first update {m0:.3e}, "
+              f"all {K} updates {O.PREACT_PROBE['min_abs']:.3e}")
+        return fx
+    raise RuntimeError("no well-conditioned data seed found")
+
+
+def _run_case(name, S, A, B, K, seed, data_seed, subsample=1, synthetic_init=False, **kw):
     """Returns the fixture dict.  K updates; dumps after update 1 and after update K."""
     torch.manual_seed(seed)
     ref = ref_algo(name, S, A, **kw)
@@ -96,14 +143,14 @@ def run_case(name, S, A, B, K, seed, subsample=1, synthetic_init=False, **kw):
     critics0 = [[p.detach().clone() for p in net.parameters()] for net in critic_nets(name, ref.critic)]
     orc = O.OracleAlgo(spec, actor0, critics0)
 
-    fx = dict(algo=name, S=S, A=A, B=B, K=K, seed=seed, subsample=subsample,
+    fx = dict(algo=name, S=S, A=A, B=B, K=K, seed=seed, data_seed=data_seed, subsample=subsample,
               synthetic_init=int(synthetic_init), tune_alpha=int(spec.tune_alpha),
               torch_version=torch.__version__)
     if not synthetic_init:
         fx["actor0"] = flat(actor0)
         fx["critic0"] = flat([p for net in critics0 for p in net])
 
-    batches = make_batches(K, B, S, A, seed + 1)
+    batches = make_batches(K, B, S, A, data_seed)
     max_dev = 0.0
     for k, (s, a, r, d, s2) in enumerate(batches):
         # the reference draws its noise from torch's global generator; pre-draw the same stream
@@ -220,7 +267,8 @@ def main():
         # fixed alpha + the reference test's batch of 8 (tests/functional/test_rl_algos.py:24)
         "sac_fixed": lambda: run_case("sac", 24, 6, 8, 3, 3, subsample=8, tune_alpha=False),
         # configs[3]: TQC walker-walk 5x25, batch 256; 2.8M params -> seeded init + 1/64 subsample
-        "tqc": lambda: run_case("tqc", 24, 6, 256, 2, 4, subsample=64, synthetic_init=True),
+        # (5.9M pre-activations per update: the margin that can be found is smaller)
+        "tqc": lambda: run_case("tqc", 24, 6, 256, 2, 4, subsample=64, synthetic_init=True, min_preact=1.2e-7),
         # ragged batch of 8 on DDPG (reference test shape)
         "ddpg_b8": lambda: run_case("ddpg", 24, 6, 8, 2, 5, subsample=8),
     }

@@ -110,12 +110,21 @@ def mlp_param_shapes(dims):
 
 
 # ------------------------------------------------------------------------ networks
+# Conditioning probe (gen_golden.py): smallest |pre-activation| seen by any hidden ReLU while
+# enabled.  A pre-activation within fp32 rounding noise of 0 makes "parameters after one Adam
+# step" ill-conditioned (the unit's gradient switches on/off and Adam's first step is
+# lr * sign(g)), so fixtures are generated from seeds that stay clear of that knife edge.
+PREACT_PROBE = {"enabled": False, "min_abs": float("inf")}
+
+
 def mlp_forward(params, x):
     """nn_models.MLP.forward (nn_models.py:106-107): Linear -> ReLU ... -> Linear."""
     n_layers = len(params) // 2
     for i in range(n_layers):
         x = torch.addmm(params[2 * i + 1], x, params[2 * i].t())
         if i < n_layers - 1:
+            if PREACT_PROBE["enabled"]:
+                PREACT_PROBE["min_abs"] = min(PREACT_PROBE["min_abs"], float(x.detach().abs().min()))
             x = torch.relu(x)
     return x
 
