@@ -159,16 +159,19 @@ def run_engine(args):
     B = args.batch or wl["B"]
     algo = make_algo(args.algo, S, A, device)
     buf = EpisodicReplayBuffer(buffer_size_transitions=1_000_000, state_dim=S, action_dim=A, device=device).create()
-    fill_buffer(buf, wl["episodes"], seed=rank)
+    fill_buffer(buf, wl["episodes"], seed=0 if args.mode == "dp" else rank)  # dp: replicated content
     algo.attach_buffer(buf)
     eng = algo.engine
     eng.set_prefix(buf.ep_lens[:buf.episodes_counter])
     td3 = args.algo == "td3"
+    dp = world > 1 and args.mode == "dp"
+    if dp:
+        algo.enable_data_parallel()
     stream = torch.cuda.Stream(device=device)
 
     def learner_steps(n, k0=0):
         for k in range(n):
-            eng.step(B, actor_step=(not td3) or ((k0 + k) % 2 == 0))
+            algo.learner_step(B)
 
     def barrier():
         torch.cuda.synchronize()
@@ -255,7 +258,10 @@ def run_engine(args):
         "dtype": "f32 (3xTF32 split on tcgen05 kind::tf32, fp32 accumulate in TMEM)",
         "data": "synthetic",
         "config": {"workload": wl["name"], "algo": args.algo, "batch": B,
-                   "parallelism": "1 learner" if world == 1 else f"{world} independent learner replicas (no collective)",
+                   "parallelism": "1 learner" if world == 1 else (
+                       f"dp{world}: replicated buffer + parameters, {B} rows/GPU (global minibatch {B * world}), NCCL all-reduce of the "
+                       f"critic and actor gradient arenas before each Adam step; value counts {B}-row minibatch updates job-wide "
+                       f"(optimizer steps/s = value / {world})" if dp else f"{world} independent learner replicas (one seed per GPU, no collective)"),
                    "l2": "replay storage (128 MB) exceeds L2 and is sampled uniformly; parameters/activations (~3 MB) are L2-resident by construction of the learner loop, as in the reference loop",
                    "index_draw": "device Philox (value) / host numpy (api_loop)"},
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "updates/s",
@@ -368,6 +374,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--algo", default="ddpg", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--mode", default="dp", choices=["dp", "replicas"],
+                    help="N>1: data-parallel learners with gradient all-reduce (default) or independent replicas")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -80,7 +80,10 @@ void oprl_engine_destroy(oprl_engine* e);
 
 /* Number of fp32 elements of a network group's flat parameter arena, laid out
  * exactly as torch's parameters() of the reference module: per net, per layer,
- * weight [out,in] then bias [out] (nn_models.py:98-104). */
+ * weight [out,in] then bias [out] (nn_models.py:98-104).  The GRADIENT array of each group
+ * must be OPRL_GRAD_TAIL floats longer: the tail carries per-rank partial sums (temperature
+ * loss) that ride along with the data-parallel gradient all-reduce. */
+#define OPRL_GRAD_TAIL 8
 long long oprl_engine_arena_floats(const oprl_engine* e, int net);
 /* Borrow the caller's flat device arrays (each `arena_floats` long).  theta_target
  * may be NULL for groups without a target network (SAC/TQC actor). */
@@ -127,6 +130,12 @@ void* oprl_stream(oprl_engine* e); /* cudaStream_t the engine currently launches
 /* Redirect the engine's launches to the caller's stream (e.g. torch's current stream) so that
  * ordinary stream ordering holds between the caller's tensors and the engine; NULL = engine-owned. */
 int oprl_engine_set_stream(oprl_engine* e, void* stream);
+
+/* Data-parallel learners: every rank runs the same program on its B rows of a world_size * B
+ * minibatch; all losses / gradient seeds are scaled by 1 / (world_size * B) so that an
+ * all-reduce(SUM) of the gradient arenas between the OPRL_SEG_* segments yields the gradients
+ * of the global-mean losses. */
+int oprl_engine_set_world_size(oprl_engine* e, int world_size);
 
 /* Engine-less sample(): plain row-major gather of B host-chosen (episode, step) pairs out of
  * replay storage shaped as in oprl_buffer_bind (episodic_buffer.py:127-133); next_state is the

@@ -16,6 +16,7 @@ ALGO = {"ddpg": 0, "td3": 1, "sac": 2, "tqc": 3}
 GEMM_3XTF32, GEMM_TF32, GEMM_SIMT = 0, 1, 2
 NET_ACTOR, NET_CRITIC = 0, 1
 UPDATE_ACTOR = 1
+GRAD_TAIL = 8  # OPRL_GRAD_TAIL
 SEG_ALL, SEG_CRITIC_GRAD, SEG_CRITIC_STEP_ACTOR_GRAD, SEG_ACTOR_STEP = -1, 0, 1, 2
 SCALARS = ("critic_loss", "actor_loss", "alpha_loss", "q_mean", "q_target_mean", "logpi_mean",
            "q_err_mean", "alpha")
@@ -59,6 +60,7 @@ _SIGNATURES = {
     "oprl_sync": (C.c_int, [_P]),
     "oprl_stream": (_P, [_P]),
     "oprl_engine_set_stream": (C.c_int, [_P, _P]),
+    "oprl_engine_set_world_size": (C.c_int, [_P, C.c_int]),
     "oprl_update_launches": (C.c_int, [_P, C.c_int, C.c_int]),
     "oprl_profile": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "oprl_gather_rows": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,

@@ -5,6 +5,7 @@ Reference surface: OffPolicyAlgorithm (base_algorithm.py:7-15) + the dataclass f
 """
 from __future__ import annotations
 
+import os
 from typing import Any
 
 import torch as t
@@ -55,6 +56,9 @@ class OffPolicyAlgorithm:
         raise NotImplementedError
 
     def _start_engine(self, spec: EngineSpec) -> None:
+        # replicated learners must draw different minibatch rows / noise: offset the device RNG
+        # streams by the process rank (torchrun's RANK)
+        spec.seed = (spec.seed + 0x9E3779B1 * int(os.environ.get("RANK", "0"))) & 0xFFFFFFFFFFFFFFFF
         self.engine = UpdateEngine(spec, self.device)
         ar = self.engine.arena
         adopt_parameters(ar["actor"]["theta"], [self.actor])
@@ -83,6 +87,56 @@ class OffPolicyAlgorithm:
         """Fuse ``buffer.sample()`` with this algorithm's engine: the gather kernel then writes
         the GEMM operand layout directly and ``update(*batch)`` skips the copy-in."""
         buffer.attach_engine(self.engine)
+
+    # --------------------------------------------------------------- data parallel
+    def enable_data_parallel(self, group=None) -> None:
+        """Replicated learners (one process per GPU, identical parameters and replay content):
+        every rank updates on its own B rows of a world_size * B minibatch and the flat gradient
+        arenas are all-reduced (NCCL over NVLink) before each Adam step, so all replicas stay
+        bit-identical without any parameter broadcast."""
+        import torch.distributed as dist
+
+        self._dp_group = group if group is not None else dist.group.WORLD
+        self.engine.set_world_size(dist.get_world_size(self._dp_group))
+        # start from rank 0's parameters (and targets); Adam state is zero everywhere at creation
+        src = dist.get_global_rank(self._dp_group, 0)
+        for grp in self.engine.arena.values():
+            for key in ("theta", "target"):
+                if grp[key] is not None:
+                    dist.broadcast(grp[key], src=src, group=self._dp_group)
+        self.engine.mark_params_dirty()
+
+    def _run_update(self, actor_step: bool) -> None:
+        eng = self.engine
+        group = getattr(self, "_dp_group", None)
+        if group is None:
+            eng.update(actor_step=actor_step)
+            return
+        import torch.distributed as dist
+
+        from .._lib import SEG_ACTOR_STEP, SEG_CRITIC_GRAD, SEG_CRITIC_STEP_ACTOR_GRAD
+
+        eng.update(actor_step=actor_step, segment=SEG_CRITIC_GRAD)
+        dist.all_reduce(eng.arena["critic"]["grad"], group=group)
+        eng.update(actor_step=actor_step, segment=SEG_CRITIC_STEP_ACTOR_GRAD)
+        if actor_step:
+            dist.all_reduce(eng.arena["actor"]["grad"], group=group)
+            eng.update(actor_step=actor_step, segment=SEG_ACTOR_STEP)
+
+    def _wants_actor_step(self) -> bool:
+        return True
+
+    def learner_step(self, batch_size: int) -> None:
+        """Device-resident learner iteration (extension; the reference's learner loop body
+        ``batch = buffer.sample(B); algo.update(*batch)``, distrib/policy_update_worker.py:66-68,
+        without the host round trip): uniform index draw on the GPU from the attached buffer,
+        gather, update.  Needs ``attach_buffer`` + ``engine.set_prefix``."""
+        self.engine.sample(batch_size, None)
+        self._run_update(self._wants_actor_step())
+        self._after_update()
+
+    def _after_update(self) -> None:
+        self.update_step += 1
 
     def log_scalars_now(self) -> dict:
         """Device-side metrics of the last update (synchronises; only call on logging steps)."""

@@ -55,7 +55,10 @@ class DDPG(OffPolicyAlgorithm):
         self._created = True
         return self
 
+    def _after_update(self) -> None:
+        pass  # reference quirk kept: DDPG never advances update_step
+
     def update(self, state: t.Tensor, action: t.Tensor, reward: t.Tensor, done: t.Tensor,
                next_state: t.Tensor) -> None:
         self._hand_batch(state, action, reward, done, next_state)
-        self.engine.update(actor_step=True)  # reference quirk kept: update_step never advances
+        self._run_update(True)  # reference quirk kept: update_step never advances

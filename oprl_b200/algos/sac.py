@@ -68,7 +68,7 @@ class SAC(OffPolicyAlgorithm):
     def update(self, state: t.Tensor, action: t.Tensor, reward: t.Tensor, done: t.Tensor,
                next_state: t.Tensor) -> None:
         self._hand_batch(state, action, reward, done, next_state)
-        self.engine.update(actor_step=True)
+        self._run_update(True)
         if self.update_step % self.log_every == 0:  # sac.py:112-121,143-155
             sc = self.engine.scalars()
             self.logger.log_scalars({"algo/q1": sc["q_mean"], "algo/q_target": sc["q_target_mean"],

@@ -56,11 +56,14 @@ class TD3(OffPolicyAlgorithm):
         self._created = True
         return self
 
+    def _wants_actor_step(self) -> bool:
+        return self.update_step % self.policy_freq == 0  # td3.py:81
+
     def update(self, state: t.Tensor, action: t.Tensor, reward: t.Tensor, done: t.Tensor,
                next_state: t.Tensor) -> None:
         self._hand_batch(state, action, reward, done, next_state)
         actor_step = self.update_step % self.policy_freq == 0  # td3.py:81
-        self.engine.update(actor_step=actor_step)
+        self._run_update(actor_step)
         if self.update_step % self.log_every == 0:  # td3.py:118-132,143-146
             sc = self.engine.scalars()
             self.logger.log_scalar("algo/q1", sc["q_mean"], self.update_step)

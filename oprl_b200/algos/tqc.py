@@ -80,7 +80,7 @@ class TQC(OffPolicyAlgorithm):
     def update(self, state: t.Tensor, action: t.Tensor, reward: t.Tensor, done: t.Tensor,
                next_state: t.Tensor) -> None:
         self._hand_batch(state, action, reward, done, next_state)
-        self.engine.update(actor_step=True)
+        self._run_update(True)
         if self.update_step % self.log_every == 0:  # tqc.py:179-187
             sc = self.engine.scalars()
             self.logger.log_scalars({"algo/critic_loss": sc["critic_loss"],

@@ -736,6 +736,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     as.q = zpi; as.logp = logp; as.B = B; as.nq = NT; as.tqc = tqc ? 1 : 0;
     as.inv_count = inv_count;
     as.target_entropy = static_cast<float>(c.target_entropy);
+    as.alpha_x = ga.grad + ga.floats;
     if (!tqc) {
       as.D[0] = Dq[0];
       as.D[1] = Dq[1];
@@ -786,6 +787,8 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   AlphaStep al;
   al.enabled = c.tune_alpha ? 1 : 0;
   al.lr = c.lr_alpha;
+  al.alpha_x = ga.grad + ga.floats;
+  al.add = tqc ? 0.f : static_cast<float>(c.target_entropy);
   b.stage(s).simt = [e, &ga, al, st](cudaStream_t sm) {
     launch_adam(e, ga, 1 | 4, sm);
     alpha_step_kernel<<<1, 32, 0, sm>>>(st, al);
@@ -1238,6 +1241,15 @@ void* oprl_stream(oprl_engine* e) { return e ? static_cast<void*>(e->stream) : n
 int oprl_engine_set_stream(oprl_engine* e, void* stream) {
   if (!e) return fail(-1, "null engine");
   e->stream = stream ? static_cast<cudaStream_t>(stream) : e->own_stream;
+  return 0;
+}
+
+int oprl_engine_set_world_size(oprl_engine* e, int world_size) {
+  if (!e || world_size < 1) return fail(-1, "bad world size");
+  if (e->cfg.world_size != world_size) {
+    e->cfg.world_size = world_size;
+    for (auto& kv : e->work) kv.second->prog.clear();  // loss scales are baked into the programs
+  }
   return 0;
 }
 

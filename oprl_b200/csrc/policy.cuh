@@ -135,6 +135,8 @@ struct ActorSeedArgs {
   int tqc;
   float inv_count;
   float target_entropy;
+  float* alpha_x;  // one float behind the actor gradient arena: this rank's share of the mean the
+                   // temperature loss multiplies (all-reduced with the arena under data parallelism)
   TM D[2];  // SAC seeds [Bp x 32], column 0
 };
 __global__ void __launch_bounds__(kTdThreads) actor_seed_kernel(ActorSeedArgs a, DevState* st) {
@@ -165,8 +167,8 @@ __global__ void __launch_bounds__(kTdThreads) actor_seed_kernel(ActorSeedArgs a,
     st->scalars[SC_LOGPI_MEAN] = mean_lp;
     st->scalars[SC_ACTOR_LOSS] = st->alpha * mean_lp - qsum * a.inv_count;
     // what the temperature loss multiplies: SAC target_entropy + mean(logp) (sac.py:133-135),
-    // TQC mean(logp + target_entropy) (tqc.py:163)
-    st->scalars[8] = a.tqc ? ltsum * a.inv_count : a.target_entropy + mean_lp;
+    // TQC mean(logp + target_entropy) (tqc.py:163); the SAC constant is added in alpha_step
+    *a.alpha_x = a.tqc ? ltsum * a.inv_count : mean_lp;
   }
 }
 
@@ -176,9 +178,11 @@ __global__ void __launch_bounds__(kTdThreads) actor_seed_kernel(ActorSeedArgs a,
 struct AlphaStep {
   int enabled;
   double lr;
+  const float* alpha_x;
+  float add;  // SAC: target_entropy ; TQC: 0
 };
 __device__ __forceinline__ void alpha_step(DevState* st, const AlphaStep& as) {
-  const double x = static_cast<double>(st->scalars[8]);
+  const double x = static_cast<double>(as.add + *as.alpha_x);
   const double g = -x;
   st->scalars[SC_ALPHA_LOSS] = static_cast<float>(-st->log_alpha * x);
   const int t = st->step[2] + 1;

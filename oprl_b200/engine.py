@@ -78,9 +78,9 @@ class UpdateEngine:
         self.arena = {}
         for net, name in ((L.NET_ACTOR, "actor"), (L.NET_CRITIC, "critic")):
             n = int(self._lib.oprl_engine_arena_floats(h, net))
-            z = lambda: torch.zeros(n, dtype=torch.float32, device=self.device)
+            z = lambda extra=0: torch.zeros(n + extra, dtype=torch.float32, device=self.device)
             has_target = name == "critic" or spec.algo in ("ddpg", "td3")
-            a = dict(theta=z(), grad=z(), m=z(), v=z(), target=z() if has_target else None)
+            a = dict(theta=z(), grad=z(L.GRAD_TAIL), m=z(), v=z(), target=z() if has_target else None)
             self.arena[name] = a
             L.check(self._lib.oprl_engine_bind_arena(
                 h, net, a["theta"].data_ptr(), a["grad"].data_ptr(), a["m"].data_ptr(),
@@ -199,6 +199,9 @@ class UpdateEngine:
         self._ensure_batch(B)
         self._use_current_stream()
         L.check(self._lib.oprl_step(self._h, B, L.UPDATE_ACTOR if actor_step else 0))
+
+    def set_world_size(self, world_size: int):
+        L.check(self._lib.oprl_engine_set_world_size(self._h, int(world_size)))
 
     def launches(self, B, actor_step=True):
         return L.check(self._lib.oprl_update_launches(self._h, B, L.UPDATE_ACTOR if actor_step else 0))
