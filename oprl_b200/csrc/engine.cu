@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -52,6 +53,27 @@ struct CudaError {
 
 static inline int pad4(int x) { return (x + 3) & ~3; }
 
+// Programmatic dependent launch: inside the update graph every kernel may start (block
+// scheduling, parameter fetch, barrier init, TMEM allocation) while its predecessor drains;
+// each kernel executes griddepcontrol.wait before its first global access.
+static bool g_pdl = true;
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  CU(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+
 // ------------------------------------------------------------------- network specs
 struct Layer {
   int in, out;     // reference dims
@@ -81,9 +103,13 @@ struct Pass {
 
 struct Stage {
   std::vector<GemmOp> ops;
-  std::function<void(cudaStream_t)> simt;
+  std::vector<std::function<void(cudaStream_t)>> simt;
+  std::vector<int> simt_launches;  // kernels each SIMT entry launches
   int segment = 0;
-  int launches() const { return (ops.empty() ? 0 : 1) + (simt ? 1 : 0); }
+  void add_simt(std::function<void(cudaStream_t)> f, int n_launches = 1) {
+    simt.push_back(std::move(f));
+    simt_launches.push_back(n_launches);
+  }
 };
 
 struct Program {
@@ -138,10 +164,7 @@ struct oprl_engine {
     TM t;
     t.rows = rows;
     t.cols = cols;
-    const size_t n = static_cast<size_t>(rows) * cols;
-    float* p = alloc_floats(2 * n);
-    t.hi = p;
-    t.lo = p + n;
+    t.p = alloc_floats(static_cast<size_t>(rows) * cols);
     return t;
   }
 };
@@ -192,7 +215,7 @@ static void build_group(oprl_engine* e, Group& g, int n_nets, const std::vector<
       ly.W = e->alloc_tm(ly.Np, ly.Kp);
       ly.WT = e->alloc_tm(ly.Kp, ly.Np);
       if (want_target) ly.TW = e->alloc_tm(ly.Np, ly.Kp);
-      else ly.TW = TM{nullptr, nullptr, 0, 0};
+      else ly.TW = TM{nullptr, 0, 0};
     }
   }
   (void)is_critic;
@@ -211,10 +234,9 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
       w.m = g.m + ly.w_off;
       w.v = g.v + ly.w_off;
       w.target = g.target ? g.target + ly.w_off : nullptr;
-      w.w_hi = ly.W.hi; w.w_lo = ly.W.lo;
-      w.wt_hi = ly.WT.hi; w.wt_lo = ly.WT.lo;
-      w.tw_hi = g.target ? ly.TW.hi : nullptr;
-      w.tw_lo = g.target ? ly.TW.lo : nullptr;
+      w.w = ly.W.p;
+      w.wt = ly.WT.p;
+      w.tw = g.target ? ly.TW.p : nullptr;
       w.w_rows = ly.Np;
       w.wt_rows = ly.Kp;
       w.n = ly.out * ly.in;
@@ -267,7 +289,8 @@ static AdamHyper make_hyper(const oprl_cfg& c) {
 static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st) {
   const int bx = static_cast<int>(std::min<size_t>((g.max_seg + kAdamThreads * 2 - 1) / (kAdamThreads * 2), 64));
   dim3 grid(std::max(bx, 1), g.n_segs);
-  adam_kernel<<<grid, kAdamThreads, 0, st>>>(g.d_segs, make_hyper(e->cfg), e->d_state, mode);
+  launch_k(adam_kernel, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs), make_hyper(e->cfg),
+           static_cast<const DevState*>(e->d_state), mode);
 }
 
 // --------------------------------------------------------------- program builder
@@ -288,8 +311,8 @@ struct Builder {
   GemmOp base_op(const TM& a, const TM& b, int M, int N, int K) {
     GemmOp o;
     memset(&o, 0, sizeof(o));
-    o.a_hi = a.hi; o.a_lo = a.lo; o.a_rows = a.rows;
-    o.b_hi = b.hi; o.b_lo = b.lo; o.b_rows = b.rows;
+    o.a = a.p; o.a_rows = a.rows;
+    o.b = b.p; o.b_rows = b.rows;
     o.M = M; o.N = N; o.K = K;
     o.passes = passes;
     o.alpha = 1.f;
@@ -315,12 +338,12 @@ struct Builder {
       o.bias_n = ly.out;
       if (l < nl - 1) {
         o.act = ACT_RELU;
-        if (!pass.h[l].hi) pass.h[l] = e->alloc_tm(Bp, ly.Np);
-        o.t_hi = pass.h[l].hi; o.t_lo = pass.h[l].lo;
+        if (!pass.h[l].p) pass.h[l] = e->alloc_tm(Bp, ly.Np);
+        o.t = pass.h[l].p;
         o.t_rows = Bp; o.t_c0 = 0; o.t_n = ly.Np;
         if (train) {
-          if (!pass.hT[l].hi) pass.hT[l] = e->alloc_tm(ly.Np, Bp);
-          o.tt_hi = pass.hT[l].hi; o.tt_lo = pass.hT[l].lo;
+          if (!pass.hT[l].p) pass.hT[l] = e->alloc_tm(ly.Np, Bp);
+          o.tt = pass.hT[l].p;
           o.tt_rows = ly.Np;
         }
         stage(s0 + l).ops.push_back(o);
@@ -369,8 +392,8 @@ struct Builder {
         if (dx_epilogue) {
           // dX (first N tile = the action columns) = dz_0 . W_0
           GemmOp o = *dx_epilogue;
-          o.a_hi = dz.hi; o.a_lo = dz.lo; o.a_rows = dz.rows;
-          o.b_hi = ly.WT.hi; o.b_lo = ly.WT.lo; o.b_rows = ly.WT.rows;
+          o.a = dz.p; o.a_rows = dz.rows;
+          o.b = ly.WT.p; o.b_rows = ly.WT.rows;
           o.M = Bp; o.N = pad32(A); o.K = ly.Np;  // N tiles covering the action columns
           o.passes = passes;
           stage(s).ops.push_back(o);
@@ -380,14 +403,14 @@ struct Builder {
       // dz_{l-1} = (dz_l . W_l) (.) relu'(h_{l-1});  db_{l-1} = column sums
       const Layer& lp = net.L[l - 1];
       GemmOp o = base_op(dz, ly.WT, Bp, ly.Kp, ly.Np);
-      o.mask_hi = pass.h[l - 1].hi;
+      o.mask = pass.h[l - 1].p;
       o.mask_rows = Bp;
       TM ndz = e->alloc_tm(Bp, lp.Np);
-      o.t_hi = ndz.hi; o.t_lo = ndz.lo; o.t_rows = Bp; o.t_c0 = 0; o.t_n = lp.Np;
-      TM ndzT = TM{nullptr, nullptr, 0, 0};
+      o.t = ndz.p; o.t_rows = Bp; o.t_c0 = 0; o.t_n = lp.Np;
+      TM ndzT = TM{nullptr, 0, 0};
       if (want_dw) {
         ndzT = e->alloc_tm(pad128(lp.out), Bp);
-        o.tt_hi = ndzT.hi; o.tt_lo = ndzT.lo; o.tt_rows = pad128(lp.out);
+        o.tt = ndzT.p; o.tt_rows = pad128(lp.out);
         o.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * lp.Np);
         o.colsum_ld = lp.Np;
         o.colsum_n = lp.out;
@@ -407,6 +430,15 @@ struct Builder {
 // ================================================================== DDPG / TD3 program
 namespace oprl {
 
+static void fill_constant_seed(oprl_engine* e, const TM& D, int B, int ncols, float value) {
+  // tiled [Bp x 32] matrix with `value` in columns [0, ncols) of rows [0, B)
+  std::vector<float> h(static_cast<size_t>(D.rows) * D.cols, 0.f);
+  for (int m = 0; m < B; ++m)
+    for (int c = 0; c < ncols; ++c) h[ct_index(D.rows, m, c)] = value;
+  CU(cudaMemcpyAsync(D.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+}
+
 static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   const oprl_cfg& c = e->cfg;
   const bool td3 = c.algo == OPRL_ALGO_TD3;
@@ -423,6 +455,19 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   float* q = e->alloc_floats(static_cast<size_t>(Bp) * nq);
   float* qn = e->alloc_floats(static_cast<size_t>(Bp) * nq);
   Pass p_at, p_ct[2], p_c[2];
+  // The actor-step forward pi(s) depends on neither the critic update nor the targets: it
+  // shares the first forward stages instead of lengthening the chain after the critic Adam.
+  Pass p_a;
+  float* a_rm = nullptr;
+  if (do_actor) {
+    a_rm = e->alloc_floats(static_cast<size_t>(Bp) * A);
+    GemmOp last;
+    const int s_end = b.forward(0, ga.nets[0], ga.theta, false, w->Xp, p_a, true, &last);
+    last.act = ACT_TANH;
+    last.t = w->Xp.p; last.t_rows = Bp; last.t_c0 = 0; last.t_n = A;
+    last.rm = a_rm; last.rm_ld = A; last.rm_m = Bp; last.rm_n = A;
+    b.stage(s_end - 1).ops.push_back(last);
+  }
   // actor_target(s') -> a' into Xn[:, :A]        (ddpg.py:94, td3.py:102-103)
   {
     GemmOp last;
@@ -434,7 +479,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       last.addm_n = A;
       last.clamp = static_cast<float>(c.max_action);
     }
-    last.t_hi = w->Xn.hi; last.t_lo = w->Xn.lo; last.t_rows = Bp; last.t_c0 = 0; last.t_n = A;
+    last.t = w->Xn.p; last.t_rows = Bp; last.t_c0 = 0; last.t_n = A;
     b.stage(s_end - 1).ops.push_back(last);
     // critic(s, a) -> q                          (ddpg.py:96, td3.py:95)
     for (int i = 0; i < nq; ++i) {
@@ -471,7 +516,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   }
   {
     DevState* st = e->d_state;
-    b.stage(s).simt = [td, st](cudaStream_t sm) { td_kernel<<<1, kTdThreads, 0, sm>>>(td, st); };
+    b.stage(s).add_simt([td, st](cudaStream_t sm) { launch_k(td_kernel, dim3(1), dim3(kTdThreads), 0, sm, td, st); });
     ++s;
   }
   // critic backward
@@ -486,23 +531,15 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   {
     const bool polyak = td3 ? do_actor : true;  // td3.py:81-84 ; ddpg.py:72-77
     const int mode = 1 | 4 | (polyak ? (2 | 8) : 0);
-    b.stage(s).simt = [e, &gc, mode](cudaStream_t sm) { launch_adam(e, gc, mode, sm); };
+    b.stage(s).add_simt([e, &gc, mode](cudaStream_t sm) { launch_adam(e, gc, mode, sm); });
     ++s;
   }
   if (do_actor) {
     // ---- actor step ----------------------------------------------------------
-    Pass p_a, p_cq;
-    float* a_rm = e->alloc_floats(static_cast<size_t>(Bp) * A);
-    GemmOp last;
-    int s_end = b.forward(s, ga.nets[0], ga.theta, false, w->Xp, p_a, true, &last);
-    last.act = ACT_TANH;
-    last.t_hi = w->Xp.hi; last.t_lo = w->Xp.lo; last.t_rows = Bp; last.t_c0 = 0; last.t_n = A;
-    last.rm = a_rm; last.rm_ld = A; last.rm_m = Bp; last.rm_n = A;
-    b.stage(s_end - 1).ops.push_back(last);
-    s = s_end;
+    Pass p_cq;
     // critic.Q1(s, pi(s)) with the just-updated critic   (ddpg.py:104, td3.py:135-137)
     GemmOp lq;
-    s_end = b.forward(s, gc.nets[0], gc.theta, false, w->Xp, p_cq, false, &lq);
+    int s_end = b.forward(s, gc.nets[0], gc.theta, false, w->Xp, p_cq, false, &lq);
     // actor_loss = -mean(q): alpha = -1/count, rows >= B dropped, column sum -> scalar
     lq.alpha = -inv_count;
     lq.m_valid = B;
@@ -515,27 +552,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     s = s_end - 1;  // the dX chain starts beside the q head
     // seed: dL/dq = -1/count on valid rows (constant)
     TM Dm = e->alloc_tm(Bp, 32);
-    {
-      std::vector<float> hi(static_cast<size_t>(Bp) * 32, 0.f), lo(hi.size(), 0.f);
-      for (int m = 0; m < B; ++m) {
-        const float x = -inv_count;
-        uint32_t u;
-        memcpy(&u, &x, 4);
-        u = (u + 0x1000u) & 0xFFFFE000u;
-        float h;
-        memcpy(&h, &u, 4);
-        hi[ct_index(Bp, m, 0)] = h;
-        const float l = x - h;
-        memcpy(&u, &l, 4);
-        u = (u + 0x1000u) & 0xFFFFE000u;
-        float l2;
-        memcpy(&l2, &u, 4);
-        lo[ct_index(Bp, m, 0)] = l2;
-      }
-      CU(cudaMemcpyAsync(Dm.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, e->stream));
-      CU(cudaMemcpyAsync(Dm.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, e->stream));
-      CU(cudaStreamSynchronize(e->stream));
-    }
+    fill_constant_seed(e, Dm, B, 1, -inv_count);
     // critic dX chain down to the action columns, then tanh'
     const Layer& a_last = ga.nets[0].L.back();
     TM dza = e->alloc_tm(Bp, a_last.Np);
@@ -544,20 +561,20 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     memset(&dx, 0, sizeof(dx));
     dx.alpha = 1.f;
     dx.rs = a_rm; dx.rs_ld = A; dx.rs_n = A;
-    dx.t_hi = dza.hi; dx.t_lo = dza.lo; dx.t_rows = Bp; dx.t_c0 = 0; dx.t_n = A;
-    dx.tt_hi = dzaT.hi; dx.tt_lo = dzaT.lo; dx.tt_rows = dzaT.rows;
+    dx.t = dza.p; dx.t_rows = Bp; dx.t_c0 = 0; dx.t_n = A;
+    dx.tt = dzaT.p; dx.tt_rows = dzaT.rows;
     dx.n_valid = A;  // columns >= A of this tile are pad / state gradients: drop them
     dx.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * a_last.Np);
     dx.colsum_ld = a_last.Np;
     dx.colsum_n = a_last.out;
     dx.colsum_out = ga.grad + a_last.b_off;
     dx.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(a_last.Np / kBN));
-    s = b.backward(s, gc.nets[0], nullptr, p_cq, Dm, TM{nullptr, nullptr, 0, 0}, w->XT, false, false, &dx);
+    s = b.backward(s, gc.nets[0], nullptr, p_cq, Dm, TM{nullptr, 0, 0}, w->XT, false, false, &dx);
     // actor backward
     s = b.backward(s, ga.nets[0], ga.grad, p_a, dza, dzaT, w->XT, true, true, nullptr);
     // actor Adam + Polyak + re-tiling   (ddpg.py:107,79-84 ; td3.py:141,83-84)
     b.seg = 2;
-    b.stage(s).simt = [e, &ga](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm); };
+    b.stage(s).add_simt([e, &ga](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm); });
     ++s;
   }
 }
@@ -566,28 +583,6 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
 
 // ================================================================== SAC / TQC program
 namespace oprl {
-
-static void fill_constant_seed(oprl_engine* e, const TM& D, int B, int ncols, float value) {
-  // tiled [Bp x 32] matrix with `value` in columns [0, ncols) of rows [0, B)
-  std::vector<float> hi(static_cast<size_t>(D.rows) * D.cols, 0.f), lo(hi.size(), 0.f);
-  auto rnd = [](float x) {
-    uint32_t u;
-    memcpy(&u, &x, 4);
-    u = (u + 0x1000u) & 0xFFFFE000u;
-    float r;
-    memcpy(&r, &u, 4);
-    return r;
-  };
-  const float h = rnd(value), l = rnd(value - rnd(value));
-  for (int m = 0; m < B; ++m)
-    for (int c = 0; c < ncols; ++c) {
-      hi[ct_index(D.rows, m, c)] = h;
-      lo[ct_index(D.rows, m, c)] = l;
-    }
-  CU(cudaMemcpyAsync(D.hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice, e->stream));
-  CU(cudaMemcpyAsync(D.lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice, e->stream));
-  CU(cudaStreamSynchronize(e->stream));
-}
 
 static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   const oprl_cfg& c = e->cfg;
@@ -633,11 +628,21 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     }
   }
   {
-    HeadFwdArgs h;
+    // pi(s) for the actor step: independent of the critic update, so it rides along here
+    GemmOp last;
+    const int se = b.forward(0, ga.nets[0], ga.theta, false, w->Xp, p_a, true, &last);
+    last.rm = out_p; last.rm_ld = 2 * A; last.rm_m = Bp; last.rm_n = 2 * A;
+    b.stage(se - 1).ops.push_back(last);
+    HeadFwdArgs h, hp;
     memset(&h, 0, sizeof(h));
     h.out = out_n; h.eps = w->noise_raw[0]; h.B = B; h.A = A; h.X = w->Xn; h.a_rm = nullptr; h.logp = logp2;
+    hp = h;
+    hp.out = out_p; hp.eps = w->noise_raw[1]; hp.X = w->Xp; hp.a_rm = a_rm; hp.logp = logp;
     const int blocks = (B + kHeadThreads - 1) / kHeadThreads;
-    b.stage(s_act).simt = [h, blocks](cudaStream_t sm) { head_fwd_kernel<<<blocks, kHeadThreads, 0, sm>>>(h); };
+    b.stage(s_act).add_simt([h, hp, blocks](cudaStream_t sm) {
+      launch_k(head_fwd_kernel, dim3(blocks), dim3(kHeadThreads), 0, sm, h);
+      launch_k(head_fwd_kernel, dim3(blocks), dim3(kHeadThreads), 0, sm, hp);
+    }, 2);
   }
   s = std::max(s, s_act + 1);
   // target critics at (s', a')
@@ -670,7 +675,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       td.D3T[i] = DT[i];
       td.db3[i] = gc.grad + gc.nets[i].L.back().b_off;
     }
-    b.stage(s).simt = [td, st](cudaStream_t sm) { td_kernel<<<1, kTdThreads, 0, sm>>>(td, st); };
+    b.stage(s).add_simt([td, st](cudaStream_t sm) { launch_k(td_kernel, dim3(1), dim3(kTdThreads), 0, sm, td, st); });
   } else {
     TqcArgs t;
     memset(&t, 0, sizeof(t));
@@ -688,7 +693,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     t.dz_rm = e->alloc_floats(static_cast<size_t>(Bp) * NT);
     t.loss_part = e->alloc_floats(Bp);
     t.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
-    b.stage(s).simt = [t, st, B](cudaStream_t sm) { tqc_loss_kernel<<<B, kTqcThreads, 0, sm>>>(t, st); };
+    b.stage(s).add_simt([t, st, B](cudaStream_t sm) { launch_k(tqc_loss_kernel, dim3(B), dim3(kTqcThreads), 0, sm, t, st); });
   }
   ++s;
   {
@@ -700,22 +705,9 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   b.seg = 1;
   // critic Adam + Polyak (sac.py:85 soft_update at the end of update() touches nothing the actor
   // step reads; tqc.py:154-159 does it right here) + re-tiling
-  b.stage(s).simt = [e, &gc](cudaStream_t sm) { launch_adam(e, gc, 1 | 2 | 4 | 8, sm); };
+  b.stage(s).add_simt([e, &gc](cudaStream_t sm) { launch_adam(e, gc, 1 | 2 | 4 | 8, sm); });
   ++s;
-  // ---- actor step ---------------------------------------------------------------
-  {
-    GemmOp last;
-    const int se = b.forward(s, ga.nets[0], ga.theta, false, w->Xp, p_a, true, &last);
-    last.rm = out_p; last.rm_ld = 2 * A; last.rm_m = Bp; last.rm_n = 2 * A;
-    b.stage(se - 1).ops.push_back(last);
-    s = se;
-    HeadFwdArgs h;
-    memset(&h, 0, sizeof(h));
-    h.out = out_p; h.eps = w->noise_raw[1]; h.B = B; h.A = A; h.X = w->Xp; h.a_rm = a_rm; h.logp = logp;
-    const int blocks = (B + kHeadThreads - 1) / kHeadThreads;
-    b.stage(s).simt = [h, blocks](cudaStream_t sm) { head_fwd_kernel<<<blocks, kHeadThreads, 0, sm>>>(h); };
-    ++s;
-  }
+  // ---- actor step (its forward + sampling head already ran beside the critic step) ------
   // critics at (s, pi(s)) with the just-updated weights
   {
     int s_end = s;
@@ -745,7 +737,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       for (int i = 0; i < nc; ++i)
         fill_constant_seed(e, Dq[i], B, nq, static_cast<float>(-1.0 / (static_cast<double>(B) * c.world_size * NT)));
     }
-    b.stage(s).simt = [as, st](cudaStream_t sm) { actor_seed_kernel<<<1, kTdThreads, 0, sm>>>(as, st); };
+    b.stage(s).add_simt([as, st](cudaStream_t sm) { launch_k(actor_seed_kernel, dim3(1), dim3(kTdThreads), 0, sm, as, st); });
     ++s;
   }
   // critic dX chains -> per-critic action gradients (row-major)
@@ -760,7 +752,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       memset(&dx, 0, sizeof(dx));
       dx.alpha = 1.f;
       dx.rm = da; dx.rm_ld = A; dx.rm_m = Bp; dx.rm_n = A;
-      s_end = b.backward(s, gc.nets[i], nullptr, p_cq[i], Dq[i], TM{nullptr, nullptr, 0, 0}, w->XT, false, false, &dx);
+      s_end = b.backward(s, gc.nets[i], nullptr, p_cq[i], Dq[i], TM{nullptr, 0, 0}, w->XT, false, false, &dx);
     }
     s = s_end;
   }
@@ -776,9 +768,9 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     hb.partial = e->alloc_floats(static_cast<size_t>(blocks) * 2 * A);
     hb.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
     const size_t smem = static_cast<size_t>(kHeadThreads) * 2 * A * sizeof(float);
-    b.stage(s).simt = [hb, st, blocks, smem](cudaStream_t sm) {
-      head_bwd_kernel<<<blocks, kHeadThreads, smem, sm>>>(hb, st);
-    };
+    b.stage(s).add_simt([hb, st, blocks, smem](cudaStream_t sm) {
+      launch_k(head_bwd_kernel, dim3(blocks), dim3(kHeadThreads), smem, sm, hb, static_cast<const DevState*>(st));
+    });
     ++s;
   }
   s = b.backward(s, ga.nets[0], ga.grad, p_a, hb.dz, hb.dzT, w->XT, true, true, nullptr);
@@ -789,10 +781,10 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   al.lr = c.lr_alpha;
   al.alpha_x = ga.grad + ga.floats;
   al.add = tqc ? 0.f : static_cast<float>(c.target_entropy);
-  b.stage(s).simt = [e, &ga, al, st](cudaStream_t sm) {
+  b.stage(s).add_simt([e, &ga, al, st](cudaStream_t sm) {
     launch_adam(e, ga, 1 | 4, sm);
-    alpha_step_kernel<<<1, 32, 0, sm>>>(st, al);
-  };
+    launch_k(alpha_step_kernel, dim3(1), dim3(32), 0, sm, st, al);
+  }, 2);
   ++s;
 }
 
@@ -809,12 +801,14 @@ static void launch_gemm_ops(oprl_engine* e, const std::vector<GemmOp>& ops, cuda
     L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, ops.size() - i0));
     for (int i = 0; i < L.n_ops; ++i) {
       L.op[i] = ops[i0 + i];
+      gemm_finalize(L.op[i]);
       tiles += gemm_tiles(L.op[i]);
+      L.tile_end[i] = tiles;
     }
     if (e->cfg.gemm_mode == OPRL_GEMM_SIMT)
-      gemm_kernel<true><<<tiles, kGemmThreads, kGemmSmemBytes, st>>>(L);
+      launch_k(gemm_kernel<true>, dim3(tiles), dim3(kGemmThreads), kGemmSmemBytes, st, L);
     else
-      gemm_kernel<false><<<tiles, kGemmThreads, kGemmSmemBytes, st>>>(L);
+      launch_k(gemm_kernel<false>, dim3(tiles), dim3(kGemmThreads), kGemmSmemBytes, st, L);
   }
 }
 
@@ -826,10 +820,11 @@ static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, 
       launch_gemm_ops(e, sg.ops, st);
       n += static_cast<int>((sg.ops.size() + kMaxOps - 1) / kMaxOps);
     }
-    if (sg.simt && !gemm_only) {
-      sg.simt(st);
-      ++n;
-    }
+    if (!gemm_only)
+      for (size_t i = 0; i < sg.simt.size(); ++i) {
+        sg.simt[i](st);
+        n += sg.simt_launches[i];
+      }
   }
   return n;
 }
@@ -969,6 +964,7 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   if (prop.major != 10) return fail(-4, "device sm_%d%d is not Blackwell sm_100", prop.major, prop.minor);
   e = new oprl_engine;
   e->cfg = *cfg;
+  if (const char* v = getenv("OPRL_B200_PDL")) g_pdl = atoi(v) != 0;
   if (e->cfg.world_size < 1) e->cfg.world_size = 1;
   CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   e->stream = e->own_stream;

@@ -3,27 +3,37 @@
 //
 //   D[M x N] = sum_k A(m,k) * B(n,k)       (fp32 accumulate in TMEM)
 //
-// * Operands live in HBM/L2 in the CT32 "core-tiled" layout, pre-split into
-//   tf32 hi/lo halves by whoever produced them (previous epilogue / Adam).
-//   Both operands are always K-major (tcgen05 kind::tf32 only takes MN-major
-//   operands in the 32-bit-swizzled SW128_32B layout), so producers that feed a
-//   dX (= delta * W) or dW (= delta^T * X) product also write a transposed tiled
-//   copy (`tt_*` outputs here, W^T from the Adam kernel).
+// * Operands live in HBM/L2 as plain fp32 in the CT32 "core-tiled" layout.  Both operands
+//   are always K-major (tcgen05 kind::tf32 only takes MN-major operands in the
+//   32-bit-swizzled SW128_32B layout), so producers that feed a dX (= delta * W) or
+//   dW (= delta^T * X) product also write a transposed tiled copy (`tt` output here,
+//   W^T from the Adam kernel).
 // * fp32-accurate products on tensor cores via 3xTF32:
 //       A*B ~= Alo*Bhi + Ahi*Blo + Ahi*Bhi        (tcgen05.mma.kind::tf32)
 //   (needed for the reference's 1e-5 parameter-L2 parity bar).
+//   The hi/lo split (hi = tf32(x), lo = tf32(x - hi)) is done IN the kernel by the four warps
+//   that later run the epilogue: operands cross L2->SMEM once as fp32 instead of twice as
+//   pre-split halves (the K loop is bound by the ~36 B/clk a single SM pulls from L2).  The
+//   split A operand is written registers -> TMEM (tcgen05.st) and the MMAs read A from tensor
+//   memory: with both operands in shared memory the 128 B/clk SMEM port (3 x 4 KB of A per
+//   k-step + the splitter's own traffic) was the K-loop limit.
 //   The tensor core's accumulator add is not round-to-nearest, so a long accumulation
 //   chain loses ~1 ulp per step (measured: one 96-step chain gave 8x the parameter error of
 //   the FFMA cross-check).  The chain is therefore cut: the two small cross terms go to
 //   their own TMEM accumulator, the Ahi*Bhi terms to one accumulator per group of K
 //   chunks, and the epilogue adds the partial sums with ordinary fp32 adds.
-// * Tile 128 x 32 per CTA, K streamed in 32-wide chunks through a 4-stage
-//   mbarrier ring filled by 1-D bulk async copies (TMA engine, no tensor maps:
-//   the producers already wrote UMMA-canonical core matrices).
-// * Warp roles: warp0 = copy producer, warp1 = MMA issuer (+TMEM owner),
-//   warps2-5 = epilogue (TMEM -> regs -> bias/act/mask -> tiled hi/lo + row-major).
-// * `kSimt` variant keeps loads/epilogue identical but does the products with
-//   FFMA from shared memory: the on-device cross-check for the descriptor path.
+// * Tile 128 x 32 per CTA, K streamed in 32-wide chunks through an 8-stage mbarrier ring
+//   filled by 1-D bulk async copies (TMA engine, no tensor maps: the producers already
+//   wrote UMMA-canonical core matrices); the copy warp starts before TMEM allocation is done;
+//   bias and the ReLU-mask tile of the epilogue are prefetched during the K loop; the
+//   transposed output is staged through shared memory and stored as coalesced 16-byte vectors.
+// * Warp roles: warp0 = copy producer, warp1 = MMA issuer (+TMEM owner), warps2-9 =
+//   tf32 splitters during the K loop (two warps per TMEM lane quarter, alternating K chunks so
+//   one group's load/convert/store latency hides behind the other's), then epilogue, 16 of the
+//   32 tile columns each (TMEM -> regs -> bias/act/mask -> tiled + transposed tiled +
+//   row-major + column sums).
+// * `kSimt` variant keeps loads/epilogue identical but does the products with plain fp32
+//   FFMA from shared memory: the on-device cross-check for the tensor-core path.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -46,40 +56,42 @@ __host__ __device__ __forceinline__ int pad128(int x) { return (x + 127) & ~127;
 constexpr int kBM = 128;
 constexpr int kBN = 32;
 constexpr int kBK = 32;
-constexpr int kStages = 4;
-constexpr int kAFloats = kBM * kBK;  // 4096 floats (16 KB) per hi / lo
-constexpr int kBFloats = kBN * kBK;  // 1024 floats ( 4 KB) per hi / lo
-constexpr int kStageFloats = 2 * kAFloats + 2 * kBFloats;
-constexpr int kStageBytes = kStageFloats * 4;  // 40 KB
-constexpr int kGemmThreads = 192;
-constexpr int kGemmSmemBytes = kStages * kStageBytes + 1024;
+constexpr int kStages = 8;  // smem ring depth (raw fp32 chunks in flight: L2 latency x bandwidth)
+constexpr int kASlots = 4;  // TMEM ring depth for the split A operand
+constexpr int kAFloats = kBM * kBK;  // 4096 floats (16 KB)
+constexpr int kBFloats = kBN * kBK;  // 1024 floats ( 4 KB)
+// smem stage = [A raw][B raw -> B hi][B lo]; the split A operand lives in TMEM
+constexpr int kStageFloats = kAFloats + 2 * kBFloats;
+constexpr int kStageBytes = kStageFloats * 4;  // 24 KB
+constexpr int kATmemCols = 2 * kBK;            // per stage: A hi (32 columns) | A lo (32 columns)
+constexpr int kGemmThreads = 320;  // warp 0 copies, warp 1 MMA, warps 2-9 split + epilogue
+constexpr int kEN = kBN / 2;        // epilogue columns per thread (two warps per TMEM lane quarter)
+constexpr int kMaskBytes = kBM * kBN * 4;  // ReLU-mask tile of the epilogue, prefetched
+constexpr int kGemmSmemBytes = kStages * kStageBytes + kMaskBytes + 1024;
+constexpr int kTTPitch = kBM + 4;  // smem pitch of the transposed staging tile (conflict-free)
 constexpr int kMaxOps = 12;
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 
 struct GemmOp {
-  // operands (CT32 hi/lo)
-  const float* a_hi;
-  const float* a_lo;
-  const float* b_hi;
-  const float* b_lo;
+  // operands (CT32 fp32)
+  const float* a;
+  const float* b;
   // epilogue inputs
-  const float* bias;     // v += bias[n] for n < bias_n
-  const float* mask_hi;  // v *= (mask[m][n] > 0), CT32 with mask_rows padded rows
-  const float* rs;       // row-major [m][n] matrix: v *= (1 - rs^2) for n < rs_n (tanh')
-  const float* addm;     // row-major [m][n] matrix added after the activation, n < addm_n
+  const float* bias;  // v += bias[n] for n < bias_n
+  const float* mask;  // v *= (mask[m][n] > 0), CT32 with mask_rows padded rows
+  const float* rs;    // row-major [m][n] matrix: v *= (1 - rs^2) for n < rs_n (tanh')
+  const float* addm;  // row-major [m][n] matrix added after the activation, n < addm_n
   // outputs
-  float* t_hi;  // CT32 output (hi/lo) at column offset t_c0, only columns n < t_n
-  float* t_lo;
-  float* tt_hi;  // transposed CT32 output: element (n, m) of a [tt_rows x M] matrix
-  float* tt_lo;
+  float* t;       // CT32 output at column offset t_c0, only columns n < t_n
+  float* tt;      // transposed CT32 output: element (n, m) of a [tt_rows x M] matrix
   float* rm;      // row-major output, m < rm_m, n < rm_n
   float* colsum;  // per-M-tile partials: colsum[mtile * colsum_ld + n]
-  float* colsum_out;       // if set: the last CTA of each N tile writes the total over M tiles here
+  float* colsum_out;         // if set: the last CTA of each N tile writes the total over M tiles here
   unsigned int* colsum_cnt;  // one arrival counter per N tile (self-resetting)
   int a_rows;  // padded row count of the stored A matrix [M.. x K]
   int b_rows;  // padded row count of the stored B matrix [N.. x K]
-  int M, N, K;       // padded problem (M % 128, N % 32, K % 32)
+  int M, N, K;  // padded problem (M % 128, N % 32, K % 32)
   int bias_n, act;
   int mask_rows;
   int rs_ld, rs_n;
@@ -93,19 +105,40 @@ struct GemmOp {
   // [action | pad4 | state]):  n < map_a -> map_s + n ; n >= map_a4 -> n - map_a4.
   int map_a, map_a4, map_s;
   int colsum_ld, colsum_n;  // partial row stride; colsum_out gets columns n < colsum_n
-  int passes;  // 3 = 3xTF32 (fp32-accurate), 1 = single tf32 pass
+  int passes;   // 3 = 3xTF32 (fp32-accurate), 1 = single tf32 pass
+  int group;    // K chunks per hi*hi accumulator (gemm_finalize)
+  int n_big;    // number of hi*hi accumulators, <= 7
   float alpha;  // v *= alpha (applied last)
   float clamp;  // if > 0: v = min(max(v, -clamp), clamp) after addm
 };
 
 struct GemmLaunch {
-  GemmOp op[kMaxOps];
+  // first cache line of the parameter block: everything the tile -> op lookup needs
   int n_ops;
-  long long* prof;  // selftest only: per-phase clock64 stamps of CTA 0
+  int tile_end[kMaxOps];  // exclusive prefix sums of gemm_tiles(op[i])
+  long long* prof;        // selftest only: per-phase clock64 stamps of CTA 0
+  GemmOp op[kMaxOps];
 };
 
 __host__ __device__ __forceinline__ int gemm_tiles(const GemmOp& o) {
   return (o.M / kBM) * (o.N / kBN);
+}
+// host: derived fields (TMEM accumulator plan) -- call once per op before launching
+inline void gemm_finalize(GemmOp& o) {
+  const int nchunks = o.K / kBK;
+  o.group = (nchunks + 6) / 7 > 2 ? (nchunks + 6) / 7 : 2;
+  o.n_big = (nchunks + o.group - 1) / o.group;
+}
+// keep a value in a register from here on (stops ptxas from re-reading kernel parameters,
+// one dependent constant-bank load per use, inside the latency-critical epilogue)
+template <typename T>
+__device__ __forceinline__ void pin(T& x) {
+  asm volatile("" : "+r"(x));
+}
+__device__ __forceinline__ void pin(float& x) { asm volatile("" : "+f"(x)); }
+template <typename T>
+__device__ __forceinline__ void pin_ptr(T*& x) {
+  asm volatile("" : "+l"(x));
 }
 
 template <bool kSimt>
@@ -113,26 +146,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_kernel(const __grid_constant__ GemmLaunch L) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kStageBytes);
+  float* mask_smem = reinterpret_cast<float*>(smem_raw + kStages * kStageBytes);
+  uint8_t* ctl = smem_raw + kStages * kStageBytes + kMaskBytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ctl);
   uint64_t* empty = full + kStages;
-  uint64_t* accum = empty + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
-  float* cs_smem = reinterpret_cast<float*>(smem_raw + kStages * kStageBytes + 256);  // [4][32]
+  uint64_t* conv = empty + kStages;
+  uint64_t* accum = conv + kStages;
+  uint64_t* mask_bar = accum + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 1);
+  float* cs_smem = reinterpret_cast<float*>(ctl + 256);    // [4][32]
+  float* bias_smem = reinterpret_cast<float*>(ctl + 768);  // [32]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
+  ptx::pdl_trigger();
   // ---- which op / tile is this CTA
   int t = blockIdx.x;
   int oi = 0;
-  for (; oi < L.n_ops; ++oi) {
-    int nt = gemm_tiles(L.op[oi]);
-    if (t < nt) break;
-    t -= nt;
-  }
+  while (oi < L.n_ops && t >= L.tile_end[oi]) ++oi;
   if (oi >= L.n_ops) return;
+  if (oi > 0) t -= L.tile_end[oi - 1];
   const GemmOp& o = L.op[oi];
+  {
+    // Kernel parameters live in a constant bank that is cold at every launch: touch every
+    // 64-byte line of this op's descriptor now, all misses in flight together, instead of
+    // paying them one by one (control-dependent) in the epilogue.
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&o);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < static_cast<int>(sizeof(GemmOp) / 4); i += 16) acc ^= w[i];
+    acc ^= w[sizeof(GemmOp) / 4 - 1];
+    asm volatile("" ::"r"(acc));
+  }
   const int ntn = o.N / kBN;
   const int mt = t / ntn;
   const int m0 = mt * kBM;
@@ -146,236 +193,312 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     prof[9] = static_cast<long long>(gt);
   }
-
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      ptx::mbar_init(&full[s], 1);
-      ptx::mbar_init(&empty[s], 1);
-    }
-    ptx::mbar_init(accum, 1);
-    ptx::fence_mbar_init();
-  }
-  // accumulators: column block 0 = cross terms, blocks 1.. = hi*hi per group of K chunks
-  const int group = max(2, (nchunks + 14) / 15);
-  const int n_big = (nchunks + group - 1) / group;
+  // TMEM map: accumulator column block 0 = cross terms, blocks 1..n_big = hi*hi per group of K
+  // chunks (at most 7), then kASlots x (A hi | A lo) operand blocks written by the splitter warps.
+  const int group = o.group;
+  const int n_big = o.n_big;
+  const uint32_t a_col0 = static_cast<uint32_t>(32 * (n_big + 1));
   uint32_t tmem_cols = 32;
-  while (tmem_cols < static_cast<uint32_t>(32 * (n_big + 1))) tmem_cols <<= 1;
-  if (!kSimt && warp == 1) ptx::tmem_alloc(tmem_slot, tmem_cols);
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  if (prof && tid == 0) prof[1] = clock64();
+  while (tmem_cols < a_col0 + kASlots * kATmemCols) tmem_cols <<= 1;
 
-  float v[kBN];
+  float v[kEN];
 
   if (warp == 0) {
-    // ===================== producer: bulk copies HBM/L2 -> smem ring
+    // ===================== producer: bulk copies HBM/L2 -> smem ring (fp32, once)
+    if (lane < kStages) {
+      ptx::mbar_init(&full[lane], 1);
+      ptx::mbar_init(&empty[lane], 1);
+      ptx::mbar_init(&conv[lane], 4);  // one arrival per splitter warp
+    } else if (lane == kStages) {
+      ptx::mbar_init(accum, 1);
+      ptx::mbar_init(mask_bar, 1);
+    }
+    ptx::fence_mbar_init();
+    __syncwarp();
+    // the other warps wait on this barrier (after TMEM allocation); the copies start now
+    asm volatile("bar.arrive 3, %0;\n" ::"n"(kGemmThreads) : "memory");
+    if (prof && lane == 0) prof[1] = clock64();
+    ptx::pdl_wait();  // operands are the previous kernel's outputs
     const int a_rb = o.a_rows >> 3;
     const int b_rb = o.b_rows >> 3;
-    const uint32_t tx = (passes == 3 ? 2u : 1u) * (kAFloats + kBFloats) * 4u;
+    const uint32_t tx = (kAFloats + kBFloats) * 4u;
     for (int c = 0; c < nchunks; ++c) {
       const int s = c % kStages;
       const uint32_t ph = (c / kStages) & 1;
       ptx::mbar_wait(&empty[s], ph ^ 1);
-      if (lane == 0) ptx::mbar_expect_tx(&full[s], tx);
-      __syncwarp();
-      float* st = smem + s * kStageFloats;
-      const int halves = (passes == 3) ? 2 : 1;
-      // 4 pieces per stage: A hi, B hi, A lo, B lo -- one lane each
-      if (lane < 2 * halves) {
-        const int h = lane >> 1;
-        if ((lane & 1) == 0) {
-          ptx::bulk_g2s(st + h * kAFloats,
-                        (h ? o.a_lo : o.a_hi) + (static_cast<size_t>(c) * a_rb + (m0 >> 3)) * 256,
-                        kAFloats * 4, &full[s]);
-        } else {
-          ptx::bulk_g2s(st + 2 * kAFloats + h * kBFloats,
-                        (h ? o.b_lo : o.b_hi) + (static_cast<size_t>(c) * b_rb + (n0 >> 3)) * 256,
-                        kBFloats * 4, &full[s]);
+      if (ptx::elect_one()) {
+        float* st = smem + s * kStageFloats;
+        ptx::mbar_expect_tx(&full[s], tx);
+        ptx::bulk_g2s(st, o.a + (static_cast<size_t>(c) * a_rb + (m0 >> 3)) * 256, kAFloats * 4, &full[s]);
+        ptx::bulk_g2s(st + kAFloats, o.b + (static_cast<size_t>(c) * b_rb + (n0 >> 3)) * 256, kBFloats * 4,
+                      &full[s]);
+        if (c == 0 && o.mask) {
+          // epilogue ReLU mask: the [128 x 32] tile of the saved activation is one contiguous 16 KB
+          ptx::mbar_expect_tx(mask_bar, kMaskBytes);
+          ptx::bulk_g2s(mask_smem, o.mask + (static_cast<size_t>(n0 >> 5) * (o.mask_rows >> 3) + (m0 >> 3)) * 256,
+                        kMaskBytes, mask_bar);
         }
       }
+      __syncwarp();
     }
     if (prof && lane == 0) prof[2] = clock64();
-  } else if (!kSimt && warp == 1) {
-    // ===================== MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t tmem_d = *tmem_slot;
-      const uint32_t idesc = ptx::idesc_tf32(kBM, kBN, 0, 0);
-      // smem tile = [row group of 8][8 K-cores][8 rows][16 B]: K cores 128 B apart (LBO),
-      // 8-row groups 1 KB apart (SBO); one MMA (K=8) consumes two K cores = 256 B.
-      const uint32_t a_step = 256u, b_step = 256u;
-      const uint32_t a_lbo = 128u, a_sbo = 1024u, b_lbo = 128u, b_sbo = 1024u;
-      for (int c = 0; c < nchunks; ++c) {
-        const int s = c % kStages;
-        const uint32_t ph = (c / kStages) & 1;
-        ptx::mbar_wait(&full[s], ph);
-        ptx::tc_fence_after();
-        if (prof && c == 0) prof[3] = clock64();
-        const uint32_t sa_hi = ptx::smem_u32(smem + s * kStageFloats);
-        const uint32_t sa_lo = sa_hi + kAFloats * 4;
-        const uint32_t sb_hi = sa_hi + 2 * kAFloats * 4;
+  } else {
+    if (!kSimt && warp == 1) ptx::tmem_alloc(tmem_slot, tmem_cols);
+    ptx::tc_fence_before();
+    asm volatile("bar.sync 3, %0;\n" ::"n"(kGemmThreads) : "memory");
+    ptx::tc_fence_after();
+  }
+
+  if (!kSimt && warp == 1) {
+    // ===================== MMA issuer (warp converged, one elected lane issues)
+    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t idesc = ptx::idesc_tf32(kBM, kBN, 0, 0);
+    // B smem tile = [row group of 8][8 K-cores][8 rows][16 B]: K cores 128 B apart (LBO),
+    // 8-row groups 1 KB apart (SBO); one MMA (K=8) consumes two K cores = 256 B.
+    const uint32_t b_step = 256u;
+    const uint32_t b_lbo = 128u, b_sbo = 1024u;
+    int in_group = 0;
+    uint32_t big = tmem_d + 32u;
+    for (int c = 0; c < nchunks; ++c) {
+      const int s = c % kStages;
+      const uint32_t ph = (c / kStages) & 1;
+      ptx::mbar_wait(&conv[s], ph);
+      ptx::tc_fence_after();
+      if (prof && c == 0 && lane == 0) prof[3] = clock64();
+      if (ptx::elect_one()) {
+        const uint32_t sb_hi = ptx::smem_u32(smem + s * kStageFloats + kAFloats);
         const uint32_t sb_lo = sb_hi + kBFloats * 4;
+        const uint32_t ta_hi = tmem_d + a_col0 + static_cast<uint32_t>((c % kASlots) * kATmemCols);
+        const uint32_t ta_lo = ta_hi + kBK;
 #pragma unroll
         for (int j = 0; j < kBK / 8; ++j) {
-          const uint64_t da_hi = ptx::smem_desc(sa_hi + j * a_step, a_lbo, a_sbo);
           const uint64_t db_hi = ptx::smem_desc(sb_hi + j * b_step, b_lbo, b_sbo);
-          const uint32_t big = tmem_d + 32u * static_cast<uint32_t>(1 + c / group);
-          const uint32_t big_acc = ((c % group) | j) ? 1u : 0u;
+          const uint32_t big_acc = (in_group | j) ? 1u : 0u;
           if (passes == 3) {
-            const uint64_t da_lo = ptx::smem_desc(sa_lo + j * a_step, a_lbo, a_sbo);
             const uint64_t db_lo = ptx::smem_desc(sb_lo + j * b_step, b_lbo, b_sbo);
-            ptx::mma_tf32(tmem_d, da_lo, db_hi, idesc, (c | j) ? 1u : 0u);
-            ptx::mma_tf32(tmem_d, da_hi, db_lo, idesc, 1u);
+            ptx::mma_tf32_ts(tmem_d, ta_lo + 8u * j, db_hi, idesc, (c | j) ? 1u : 0u);
+            ptx::mma_tf32_ts(tmem_d, ta_hi + 8u * j, db_lo, idesc, 1u);
           }
-          ptx::mma_tf32(big, da_hi, db_hi, idesc, big_acc);
+          ptx::mma_tf32_ts(big, ta_hi + 8u * j, db_hi, idesc, big_acc);
         }
         ptx::mma_commit(&empty[s]);
       }
-      ptx::mma_commit(accum);
-      if (prof) prof[4] = clock64();
+      __syncwarp();
+      if (++in_group == group) {
+        in_group = 0;
+        big += 32u;
+      }
     }
+    if (ptx::elect_one()) ptx::mma_commit(accum);
     __syncwarp();
+    if (prof && lane == 0) prof[4] = clock64();
   } else if (warp >= 2) {
-    // ===================== epilogue warps (TMEM lane quarter = warp % 4)
+    // ===================== splitter + epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;  // 0: warps 2-5 (even chunks, columns 0-15), 1: warps 6-9
+    const int cn0 = half * kEN;        // first tile column this thread finishes
     const int row = q * 32 + lane;
+    const int ct = (tid - 64) & 127;   // 0..127 inside the group
+    ptx::pdl_wait();  // bias / mask / outputs alias buffers the previous kernel may still use
+    if (tid - 64 < kBN) bias_smem[tid - 64] = (o.bias && n0 + tid - 64 < o.bias_n) ? __ldg(o.bias + n0 + tid - 64) : 0.f;
+    // epilogue plan, read from the kernel parameters now (while the first copies are in flight)
+    enum : uint32_t { F_BIAS = 1, F_RELU = 2, F_TANH = 4, F_MASK = 8, F_RS = 16, F_ADDM = 32, F_CLAMP = 64,
+                      F_ALPHA = 128, F_MVALID = 256, F_NVALID = 512, F_T = 1024, F_TT = 2048, F_RM = 4096,
+                      F_COLSUM = 8192 };
+    uint32_t fl = (o.bias ? F_BIAS : 0u) | (o.act == ACT_RELU ? F_RELU : 0u) | (o.act == ACT_TANH ? F_TANH : 0u) |
+                  (o.mask ? F_MASK : 0u) | (o.rs ? F_RS : 0u) | (o.addm ? F_ADDM : 0u) |
+                  (o.clamp > 0.f ? F_CLAMP : 0u) | (o.alpha != 1.f ? F_ALPHA : 0u) |
+                  (o.m_valid > 0 ? F_MVALID : 0u) | (o.n_valid > 0 ? F_NVALID : 0u) | (o.t ? F_T : 0u) |
+                  (o.tt ? F_TT : 0u) | (o.rm ? F_RM : 0u) | (o.colsum ? F_COLSUM : 0u);
+    float* out_t = o.t;
+    float* out_tt = o.tt;
+    int t_rows = o.t_rows, t_c0 = o.t_c0, t_n = o.t_n, tt_rows = o.tt_rows;
+    pin(fl); pin_ptr(out_t); pin_ptr(out_tt); pin(t_rows); pin(t_c0); pin(t_n); pin(tt_rows);
     if (!kSimt) {
+      // ---- K loop: split every landed fp32 chunk into tf32 hi / lo.  A: this thread's row
+      // (32 k) goes registers -> TMEM (the MMA reads A from tensor memory, so shared memory only
+      // serves the narrow B operand); B: in place (hi) + a second 4 KB buffer (lo).
+      const uint32_t ta_lane = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16) + a_col0;
+      for (int c = half; c < nchunks; c += 2) {
+        const int s = c % kStages;
+        const uint32_t ph = (c / kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        const float* st = smem + s * kStageFloats;
+        float hi[kBK], lo[kBK];
+#pragma unroll
+        for (int j = 0; j < kBK / 4; ++j) {
+          const float4 x = *reinterpret_cast<const float4*>(st + ((row >> 3) * 8 + j) * 32 + (row & 7) * 4);
+          ptx::split_tf32(x.x, hi[4 * j + 0], lo[4 * j + 0]);
+          ptx::split_tf32(x.y, hi[4 * j + 1], lo[4 * j + 1]);
+          ptx::split_tf32(x.z, hi[4 * j + 2], lo[4 * j + 2]);
+          ptx::split_tf32(x.w, hi[4 * j + 3], lo[4 * j + 3]);
+        }
+        if (c >= kASlots) {
+          // the TMEM slot is free once the MMAs of chunk c - kASlots retired (their commit
+          // arrives on that chunk's `empty` barrier)
+          const int cp = c - kASlots;
+          ptx::mbar_wait(&empty[cp % kStages], (cp / kStages) & 1);
+          ptx::tc_fence_after();
+        }
+        const uint32_t ta = ta_lane + static_cast<uint32_t>((c % kASlots) * kATmemCols);
+        ptx::tmem_st32(ta, hi);
+        if (passes == 3) ptx::tmem_st32(ta + kBK, lo);
+        float4* braw = reinterpret_cast<float4*>(smem + s * kStageFloats + kAFloats);
+        float4* blo = braw + kBFloats / 4;
+#pragma unroll
+        for (int i = 0; i < kBFloats / 4 / 128; ++i) {
+          const int idx = ct + i * 128;
+          const float4 x = braw[idx];
+          float4 h, l;
+          ptx::split_tf32(x.x, h.x, l.x);
+          ptx::split_tf32(x.y, h.y, l.y);
+          ptx::split_tf32(x.z, h.z, l.z);
+          ptx::split_tf32(x.w, h.w, l.w);
+          braw[idx] = h;
+          if (passes == 3) blo[idx] = l;
+        }
+        ptx::fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&conv[s]);
+      }
       ptx::mbar_wait(accum, 0);
       ptx::tc_fence_after();
       if (prof && tid == 64) prof[5] = clock64();
       {
-        const uint32_t lane_base = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16);
-        float part[kBN];
-        ptx::tmem_ld32(lane_base + 32u, v);
+        const uint32_t lane_base = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cn0);
+        float part[kEN];
+        ptx::tmem_ld16(lane_base + 32u, v);
         for (int gi = 1; gi < n_big; ++gi) {
-          ptx::tmem_ld32(lane_base + 32u * static_cast<uint32_t>(1 + gi), part);
+          ptx::tmem_ld16(lane_base + 32u * static_cast<uint32_t>(1 + gi), part);
 #pragma unroll
-          for (int j = 0; j < kBN; ++j) v[j] += part[j];
+          for (int j = 0; j < kEN; ++j) v[j] += part[j];
         }
         if (passes == 3) {
-          ptx::tmem_ld32(lane_base, part);
+          ptx::tmem_ld16(lane_base, part);
 #pragma unroll
-          for (int j = 0; j < kBN; ++j) v[j] += part[j];
+          for (int j = 0; j < kEN; ++j) v[j] += part[j];
         }
       }
       if (prof && tid == 64) prof[6] = clock64();
     } else {
-      // FFMA cross-check path: same smem contents, products on CUDA cores.
+      // FFMA cross-check path: same smem contents, products on CUDA cores in plain fp32.
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) v[j] = 0.f;
+      for (int j = 0; j < kEN; ++j) v[j] = 0.f;
       for (int c = 0; c < nchunks; ++c) {
         const int s = c % kStages;
         const uint32_t ph = (c / kStages) & 1;
         ptx::mbar_wait(&full[s], ph);
-        const float* sa_hi = smem + s * kStageFloats;
-        const float* sa_lo = sa_hi + kAFloats;
-        const float* sb_hi = sa_hi + 2 * kAFloats;
-        const float* sb_lo = sb_hi + kBFloats;
+        const float* sa = smem + s * kStageFloats;
+        const float* sb = sa + kAFloats;
         for (int k = 0; k < kBK; ++k) {
-          const int ia = ((row >> 3) * 8 + (k >> 2)) * 32 + (row & 7) * 4 + (k & 3);
-          float a = sa_hi[ia];
-          if (passes == 3) a += sa_lo[ia];
+          const float a = sa[((row >> 3) * 8 + (k >> 2)) * 32 + (row & 7) * 4 + (k & 3)];
 #pragma unroll
-          for (int j = 0; j < kBN; ++j) {
-            const int ib = ((j >> 3) * 8 + (k >> 2)) * 32 + (j & 7) * 4 + (k & 3);
-            float b = sb_hi[ib];
-            if (passes == 3) b += sb_lo[ib];
-            v[j] = fmaf(a, b, v[j]);
+          for (int j = 0; j < kEN; ++j) {
+            const int n = cn0 + j;
+            v[j] = fmaf(a, sb[((n >> 3) * 8 + (k >> 2)) * 32 + (n & 7) * 4 + (k & 3)], v[j]);
           }
         }
-        asm volatile("bar.sync 1, 128;\n" ::: "memory");
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (tid == 64) ptx::mbar_arrive(&empty[s]);
       }
     }
+    // every MMA (or FFMA pass) of this tile is done: the smem ring is free for epilogue staging
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");  // also publishes bias_smem
+    if (prof && tid == 64) prof[11] = clock64();
 
     const int m = m0 + row;
+    const int nb = n0 + cn0;  // first global column of this thread
     // ---- epilogue math
-    if (o.bias) {
+    if (fl & F_BIAS) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j)
-        if (n0 + j < o.bias_n) v[j] += __ldg(o.bias + n0 + j);
+      for (int j = 0; j < kEN; ++j) v[j] += bias_smem[cn0 + j];
     }
-    if (o.act == ACT_RELU) {
+    if (fl & F_RELU) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if (o.act == ACT_TANH) {
+      for (int j = 0; j < kEN; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (fl & F_TANH) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) v[j] = tanhf(v[j]);
+      for (int j = 0; j < kEN; ++j) v[j] = tanhf(v[j]);
     }
-    if (o.mask_hi) {
+    if (fl & F_MASK) {
+      ptx::mbar_wait(mask_bar, 0);
 #pragma unroll
-      for (int j4 = 0; j4 < kBN / 4; ++j4) {
-        const float4 mk =
-            *reinterpret_cast<const float4*>(o.mask_hi + ct_index(o.mask_rows, m, n0 + 4 * j4));
+      for (int j4 = 0; j4 < kEN / 4; ++j4) {
+        const float4 mk = *reinterpret_cast<const float4*>(mask_smem + ((row >> 3) * 8 + cn0 / 4 + j4) * 32 + (row & 7) * 4);
         v[4 * j4 + 0] = mk.x > 0.f ? v[4 * j4 + 0] : 0.f;
         v[4 * j4 + 1] = mk.y > 0.f ? v[4 * j4 + 1] : 0.f;
         v[4 * j4 + 2] = mk.z > 0.f ? v[4 * j4 + 2] : 0.f;
         v[4 * j4 + 3] = mk.w > 0.f ? v[4 * j4 + 3] : 0.f;
       }
     }
-    if (o.rs) {
+    if (fl & F_RS) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j)
-        if (n0 + j < o.rs_n) {
-          const float a = o.rs[static_cast<size_t>(m) * o.rs_ld + n0 + j];
+      for (int j = 0; j < kEN; ++j)
+        if (nb + j < o.rs_n) {
+          const float a = o.rs[static_cast<size_t>(m) * o.rs_ld + nb + j];
           v[j] *= (1.f - a * a);
         }
     }
-    if (o.addm) {
+    if (fl & F_ADDM) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j)
-        if (n0 + j < o.addm_n) v[j] += o.addm[static_cast<size_t>(m) * o.addm_ld + n0 + j];
+      for (int j = 0; j < kEN; ++j)
+        if (nb + j < o.addm_n) v[j] += o.addm[static_cast<size_t>(m) * o.addm_ld + nb + j];
     }
-    if (o.clamp > 0.f) {
+    if (fl & F_CLAMP) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) v[j] = fminf(fmaxf(v[j], -o.clamp), o.clamp);
+      for (int j = 0; j < kEN; ++j) v[j] = fminf(fmaxf(v[j], -o.clamp), o.clamp);
     }
-    if (o.alpha != 1.f) {
+    if (fl & F_ALPHA) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) v[j] *= o.alpha;
+      for (int j = 0; j < kEN; ++j) v[j] *= o.alpha;
     }
-    if (o.m_valid > 0 && m >= o.m_valid) {
+    if ((fl & F_MVALID) && m >= o.m_valid) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) v[j] = 0.f;
+      for (int j = 0; j < kEN; ++j) v[j] = 0.f;
     }
-    if (o.n_valid > 0) {
+    if (fl & F_NVALID) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j)
-        if (n0 + j >= o.n_valid) v[j] = 0.f;
+      for (int j = 0; j < kEN; ++j)
+        if (nb + j >= o.n_valid) v[j] = 0.f;
     }
+    if (prof && tid == 64) prof[12] = clock64();
     // ---- outputs
-    if (o.t_hi) {
+    if (fl & F_T) {
 #pragma unroll
-      for (int j4 = 0; j4 < kBN / 4; ++j4) {
-        if (n0 + 4 * j4 < o.t_n) {
-          float4 hi, lo;
-          ptx::split_tf32(v[4 * j4 + 0], hi.x, lo.x);
-          ptx::split_tf32(v[4 * j4 + 1], hi.y, lo.y);
-          ptx::split_tf32(v[4 * j4 + 2], hi.z, lo.z);
-          ptx::split_tf32(v[4 * j4 + 3], hi.w, lo.w);
-          const size_t off = ct_index(o.t_rows, m, o.t_c0 + n0 + 4 * j4);
-          *reinterpret_cast<float4*>(o.t_hi + off) = hi;
-          *reinterpret_cast<float4*>(o.t_lo + off) = lo;
+      for (int j4 = 0; j4 < kEN / 4; ++j4) {
+        if (nb + 4 * j4 < t_n) {
+          *reinterpret_cast<float4*>(out_t + ct_index(t_rows, m, t_c0 + nb + 4 * j4)) =
+              make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
         }
       }
     }
-    if (o.tt_hi) {
-      // element (n, m) of the transposed matrix; lanes cover 32 consecutive m.
+    if (fl & F_TT) {
+      // transposed output [32 n x 128 m]: stage through smem (lanes = consecutive m, conflict
+      // free), then each thread stores 4 coalesced float4 = (n, 4 consecutive m) of the CT32 blocks
+      float* sT = smem;  // [32][kTTPitch]
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) {
-        float hi, lo;
-        ptx::split_tf32(v[j], hi, lo);
-        const size_t off = ct_index(o.tt_rows, n0 + j, m);
-        o.tt_hi[off] = hi;
-        o.tt_lo[off] = lo;
+      for (int j = 0; j < kEN; ++j) sT[(cn0 + j) * kTTPitch + row] = v[j];
+      asm volatile("bar.sync 2, 256;\n" ::: "memory");
+#pragma unroll
+      for (int i = 0; i < (kBM * kBN / 4) / 256; ++i) {
+        const int f = (tid - 64) + i * 256;  // float4 index inside the tile, block-contiguous order
+        const int blk = f >> 6;              // 1 KB block: n-group (0..3) x m-chunk (0..3), m-chunk major
+        const int mc = blk >> 2, ng = blk & 3;
+        const int core = (f >> 3) & 7;       // 4-m core inside the block
+        const int nr = f & 7;                // n inside the group
+        const int n = ng * 8 + nr, mm = mc * 32 + core * 4;
+        const float4 x = *reinterpret_cast<const float4*>(sT + n * kTTPitch + mm);
+        *reinterpret_cast<float4*>(out_tt + ct_index(tt_rows, n0 + n, m0 + mm)) = x;
       }
     }
-    if (o.rm) {
+    if (fl & F_RM) {
       if (!o.rm_trans) {
         if (m < o.rm_m) {
 #pragma unroll
-          for (int j = 0; j < kBN; ++j) {
-            const int n = n0 + j;
+          for (int j = 0; j < kEN; ++j) {
+            const int n = nb + j;
             int col = n;
             bool ok = n < o.rm_n;
             if (o.map_a4 > 0) {  // [action | pad4 | state] -> [state | action]
@@ -390,23 +513,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       } else {
         if (m < o.rm_m) {
 #pragma unroll
-          for (int j = 0; j < kBN; ++j)
-            if (n0 + j < o.rm_n) o.rm[static_cast<size_t>(n0 + j) * o.rm_ld + m] = v[j];
+          for (int j = 0; j < kEN; ++j)
+            if (nb + j < o.rm_n) o.rm[static_cast<size_t>(nb + j) * o.rm_ld + m] = v[j];
         }
       }
     }
-    if (o.colsum) {
+    if (fl & F_COLSUM) {
 #pragma unroll
-      for (int j = 0; j < kBN; ++j) {
+      for (int j = 0; j < kEN; ++j) {
         float s = v[j];
         s += __shfl_xor_sync(0xffffffffu, s, 16);
         s += __shfl_xor_sync(0xffffffffu, s, 8);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (lane == j) cs_smem[q * 32 + j] = s;
+        if (lane == j) cs_smem[q * 32 + cn0 + j] = s;
       }
-      asm volatile("bar.sync 2, 128;\n" ::: "memory");
+      asm volatile("bar.sync 2, 256;\n" ::: "memory");
       if (warp == 2) {
         const float s = cs_smem[lane] + cs_smem[32 + lane] + cs_smem[64 + lane] + cs_smem[96 + lane];
         o.colsum[static_cast<size_t>(mt) * o.colsum_ld + n0 + lane] = s;

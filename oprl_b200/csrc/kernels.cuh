@@ -7,9 +7,8 @@
 
 namespace oprl {
 
-struct TM {  // CT32 tiled matrix, tf32 hi/lo halves
-  float* hi;
-  float* lo;
+struct TM {  // CT32 tiled fp32 matrix (gemm.cuh)
+  float* p;
   int rows;  // padded
   int cols;  // padded
 };
@@ -38,11 +37,7 @@ enum Scalar : int {
 };
 
 __device__ __forceinline__ void store_tiled(const TM& t, int r, int c, float x) {
-  float hi, lo;
-  ptx::split_tf32(x, hi, lo);
-  const size_t off = ct_index(t.rows, r, c);
-  t.hi[off] = hi;
-  t.lo[off] = lo;
+  t.p[ct_index(t.rows, r, c)] = x;
 }
 
 // Standard-normal draws of one update.  raw[i] is either injected by the caller
@@ -253,6 +248,8 @@ struct TdArgs {
 };
 constexpr int kTdThreads = 256;
 __global__ void __launch_bounds__(kTdThreads) td_kernel(TdArgs a, DevState* st) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   __shared__ float sh[kTdThreads];
   const float invB = a.inv_count;
   float loss[2] = {0.f, 0.f}, dsum[2] = {0.f, 0.f}, qsum = 0.f, ysum = 0.f, esum = 0.f;
@@ -303,16 +300,16 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(TdArgs a, DevState* st) 
 // Reference: torch.optim.Adam single-tensor path (ddpg.py:51,56,101,107) and the
 // Polyak loops (ddpg.py:72-84, nn_functions.py:5-10).  One pass over
 // [theta, g, m, v, theta_target]; also refreshes the CT32 hi/lo operand copies
-// (W and W^T, target W) that the GEMM kernel consumes.
+// (W and W^T, target W) that the GEMM kernel consumes (plain fp32; the GEMM splits to tf32).
 struct AdamSeg {
   float* theta;
   const float* grad;
   float* m;
   float* v;
   float* target;  // nullable
-  float *w_hi, *w_lo;    // tiled [rows_pad x cols_pad] (nullable for biases)
-  float *wt_hi, *wt_lo;  // tiled transposed (nullable)
-  float *tw_hi, *tw_lo;  // tiled target weights (nullable)
+  float* w;   // tiled [rows_pad x cols_pad] (nullable for biases)
+  float* wt;  // tiled transposed (nullable)
+  float* tw;  // tiled target weights (nullable)
   int w_rows, wt_rows;   // padded row counts of the tiled copies
   int n, rows, cols;     // row-major [rows x cols]
   int split, off_lo, off_hi;  // tiled col = j < split ? j + off_lo : j - split + off_hi
@@ -329,6 +326,8 @@ constexpr int kAdamThreads = 256;
 // mode: bit0 = Adam step, bit1 = Polyak, bit2 = (re)tile online weights, bit3 = tile targets
 __global__ void __launch_bounds__(kAdamThreads)
     adam_kernel(const AdamSeg* segs, AdamHyper hp, const DevState* st, int mode) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const AdamSeg sg = segs[blockIdx.y];
   __shared__ float s_step_size, s_bc2_sqrt;
   if (threadIdx.x == 0 && (mode & 1)) {
@@ -363,29 +362,15 @@ __global__ void __launch_bounds__(kAdamThreads)
         sg.target[i] = tp;
       }
     }
-    if (sg.w_hi) {
+    if (sg.w) {
       const int r = i / sg.cols;
       const int j = i - r * sg.cols;
       const int c = j < sg.split ? j + sg.off_lo : j - sg.split + sg.off_hi;
       if (mode & 4) {
-        float hi, lo;
-        ptx::split_tf32(p, hi, lo);
-        const size_t o1 = ct_index(sg.w_rows, r, c);
-        sg.w_hi[o1] = hi;
-        sg.w_lo[o1] = lo;
-        if (sg.wt_hi) {
-          const size_t o2 = ct_index(sg.wt_rows, c, r);
-          sg.wt_hi[o2] = hi;
-          sg.wt_lo[o2] = lo;
-        }
+        sg.w[ct_index(sg.w_rows, r, c)] = p;
+        if (sg.wt) sg.wt[ct_index(sg.wt_rows, c, r)] = p;
       }
-      if (sg.tw_hi && (mode & 8)) {
-        float hi, lo;
-        ptx::split_tf32(tp, hi, lo);
-        const size_t o1 = ct_index(sg.w_rows, r, c);
-        sg.tw_hi[o1] = hi;
-        sg.tw_lo[o1] = lo;
-      }
+      if (sg.tw && (mode & 8)) sg.tw[ct_index(sg.w_rows, r, c)] = tp;
     }
   }
 }

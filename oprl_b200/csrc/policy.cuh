@@ -30,6 +30,8 @@ struct HeadFwdArgs {
   float* logp;   // [Bp]
 };
 __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(HeadFwdArgs g) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   const int m = blockIdx.x * kHeadThreads + threadIdx.x;
   if (m >= g.B) return;
   const float* o = g.out + static_cast<size_t>(m) * 2 * g.A;
@@ -73,6 +75,8 @@ struct HeadBwdArgs {
   unsigned int* counter;
 };
 __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadBwdArgs g, const DevState* st) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   extern __shared__ float sh[];  // [kHeadThreads x 2A]
   const int m = blockIdx.x * kHeadThreads + threadIdx.x;
   const int W = 2 * g.A;
@@ -140,6 +144,8 @@ struct ActorSeedArgs {
   TM D[2];  // SAC seeds [Bp x 32], column 0
 };
 __global__ void __launch_bounds__(kTdThreads) actor_seed_kernel(ActorSeedArgs a, DevState* st) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   __shared__ float sh[kTdThreads];
   float qs = 0.f, ls = 0.f, lts = 0.f;
   for (int m = threadIdx.x; m < a.B; m += kTdThreads) {
@@ -197,6 +203,8 @@ __device__ __forceinline__ void alpha_step(DevState* st, const AlphaStep& as) {
   st->alpha = static_cast<float>(exp(st->log_alpha));
 }
 __global__ void alpha_step_kernel(DevState* st, AlphaStep as) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0 && as.enabled) alpha_step(st, as);
 }
 
@@ -222,6 +230,8 @@ struct TqcArgs {
 };
 constexpr int kTqcThreads = 128;  // NT <= 128
 __global__ void __launch_bounds__(kTqcThreads) tqc_loss_kernel(TqcArgs a, DevState* st) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
   __shared__ float srt[kTqcThreads];
   __shared__ float red[kTqcThreads];
   const int m = blockIdx.x;

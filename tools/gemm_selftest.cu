@@ -21,42 +21,30 @@ using namespace oprl;
     }                                                                                 \
   } while (0)
 
-static float tf32_host(float x) {
-  uint32_t u;
-  memcpy(&u, &x, 4);
-  u = (u + 0x1000u) & 0xFFFFE000u;
-  float r;
-  memcpy(&r, &u, 4);
-  return r;
-}
-
 struct HostMat {  // logical [rows x cols] row-major + tiled device copies
   int rows, cols;
   std::vector<float> v;
-  float *d_hi = nullptr, *d_lo = nullptr;
+  float* d = nullptr;
   void upload() {
-    std::vector<float> hi((size_t)rows * cols), lo((size_t)rows * cols);
+    std::vector<float> tiled((size_t)rows * cols);
     for (int r = 0; r < rows; ++r)
-      for (int c = 0; c < cols; ++c) {
-        float x = v[(size_t)r * cols + c];
-        float h = tf32_host(x);
-        float l = tf32_host(x - h);
-        hi[ct_index(rows, r, c)] = h;
-        lo[ct_index(rows, r, c)] = l;
-      }
-    CK(cudaMalloc(&d_hi, hi.size() * 4));
-    CK(cudaMalloc(&d_lo, lo.size() * 4));
-    CK(cudaMemcpy(d_hi, hi.data(), hi.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_lo, lo.data(), lo.size() * 4, cudaMemcpyHostToDevice));
+      for (int c = 0; c < cols; ++c) tiled[ct_index(rows, r, c)] = v[(size_t)r * cols + c];
+    CK(cudaMalloc(&d, tiled.size() * 4));
+    CK(cudaMemcpy(d, tiled.data(), tiled.size() * 4, cudaMemcpyHostToDevice));
   }
 };
 
 static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
 
 template <bool kSimt>
-static void launch(const GemmLaunch& L, cudaStream_t st = 0) {
+static void launch(const GemmLaunch& Lin, cudaStream_t st = 0) {
+  GemmLaunch L = Lin;
   int tiles = 0;
-  for (int i = 0; i < L.n_ops; ++i) tiles += gemm_tiles(L.op[i]);
+  for (int i = 0; i < L.n_ops; ++i) {
+    gemm_finalize(L.op[i]);
+    tiles += gemm_tiles(L.op[i]);
+    L.tile_end[i] = tiles;
+  }
   gemm_kernel<kSimt><<<tiles, kGemmThreads, kGemmSmemBytes, st>>>(L);
 }
 
@@ -71,14 +59,12 @@ static double run_case(int M, int N, int K, bool simt, int passes) {
   B.upload();
   std::vector<float> bias(N);
   for (auto& x : bias) x = frand();
-  float *d_bias, *d_rm, *d_thi, *d_tlo, *d_tthi, *d_ttlo, *d_cs;
+  float *d_bias, *d_rm, *d_t, *d_tt, *d_cs;
   CK(cudaMalloc(&d_bias, N * 4));
   CK(cudaMemcpy(d_bias, bias.data(), N * 4, cudaMemcpyHostToDevice));
   CK(cudaMalloc(&d_rm, (size_t)M * N * 4));
-  CK(cudaMalloc(&d_thi, (size_t)M * N * 4));
-  CK(cudaMalloc(&d_tlo, (size_t)M * N * 4));
-  CK(cudaMalloc(&d_tthi, (size_t)M * N * 4));
-  CK(cudaMalloc(&d_ttlo, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_t, (size_t)M * N * 4));
+  CK(cudaMalloc(&d_tt, (size_t)M * N * 4));
   CK(cudaMalloc(&d_cs, (size_t)(M / 128) * N * 4));
   CK(cudaMemset(d_rm, 0xff, (size_t)M * N * 4));
 
@@ -86,12 +72,12 @@ static double run_case(int M, int N, int K, bool simt, int passes) {
   memset(&L, 0, sizeof(L));
   L.n_ops = 1;
   GemmOp& o = L.op[0];
-  o.a_hi = A.d_hi; o.a_lo = A.d_lo; o.a_rows = M;
-  o.b_hi = B.d_hi; o.b_lo = B.d_lo; o.b_rows = N;
+  o.a = A.d; o.a_rows = M;
+  o.b = B.d; o.b_rows = N;
   o.M = M; o.N = N; o.K = K;
   o.bias = d_bias; o.bias_n = N; o.act = ACT_RELU;
-  o.t_hi = d_thi; o.t_lo = d_tlo; o.t_rows = M; o.t_c0 = 0; o.t_n = N;
-  o.tt_hi = d_tthi; o.tt_lo = d_ttlo; o.tt_rows = N;
+  o.t = d_t; o.t_rows = M; o.t_c0 = 0; o.t_n = N;
+  o.tt = d_tt; o.tt_rows = N;
   o.rm = d_rm; o.rm_ld = N; o.rm_m = M; o.rm_n = N;
   o.colsum = d_cs; o.colsum_ld = N;
   o.passes = passes; o.alpha = 1.f;
@@ -102,12 +88,10 @@ static double run_case(int M, int N, int K, bool simt, int passes) {
     exit(3);
   }
   size_t mn = (size_t)M * N;
-  std::vector<float> out(mn), thi(mn), tlo(mn), tthi(mn), ttlo(mn), cs((size_t)(M / 128) * N);
+  std::vector<float> out(mn), tv(mn), ttv(mn), cs((size_t)(M / 128) * N);
   CK(cudaMemcpy(out.data(), d_rm, mn * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(thi.data(), d_thi, mn * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(tlo.data(), d_tlo, mn * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(tthi.data(), d_tthi, mn * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(ttlo.data(), d_ttlo, mn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(tv.data(), d_t, mn * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(ttv.data(), d_tt, mn * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(cs.data(), d_cs, cs.size() * 4, cudaMemcpyDeviceToHost));
   double max_err = 0, max_terr = 0, max_tterr = 0, max_cerr = 0;
   std::vector<double> colref((size_t)(M / 128) * N, 0.0);
@@ -125,10 +109,10 @@ static double run_case(int M, int N, int K, bool simt, int passes) {
       double got = out[(size_t)m * N + n];
       double err = fabs(got - acc) / (mag + 1.0);
       if (!(err <= max_err)) max_err = err;  // NaN-propagating
-      double tgot = (double)thi[ct_index(M, m, n)] + (double)tlo[ct_index(M, m, n)];
+      double tgot = (double)tv[ct_index(M, m, n)];
       double terr = fabs(tgot - got) / (fabs(got) + 1e-3);
       if (!(terr <= max_terr)) max_terr = terr;
-      double ttgot = (double)tthi[ct_index(N, n, m)] + (double)ttlo[ct_index(N, n, m)];
+      double ttgot = (double)ttv[ct_index(N, n, m)];
       double tterr = fabs(ttgot - got) / (fabs(got) + 1e-3);
       if (!(tterr <= max_tterr)) max_tterr = tterr;
       colref[(size_t)(m / 128) * N + n] += got;
@@ -139,9 +123,8 @@ static double run_case(int M, int N, int K, bool simt, int passes) {
   }
   printf("  M=%d N=%d K=%d %s passes=%d: rel_err=%.3e tiled=%.3e ttiled=%.3e colsum=%.3e\n", M, N, K,
          simt ? "SIMT" : "TC  ", passes, max_err, max_terr, max_tterr, max_cerr);
-  cudaFree(A.d_hi); cudaFree(A.d_lo); cudaFree(B.d_hi); cudaFree(B.d_lo);
-  cudaFree(d_bias); cudaFree(d_rm); cudaFree(d_thi); cudaFree(d_tlo); cudaFree(d_tthi);
-  cudaFree(d_ttlo); cudaFree(d_cs);
+  cudaFree(A.d); cudaFree(B.d);
+  cudaFree(d_bias); cudaFree(d_rm); cudaFree(d_t); cudaFree(d_tt); cudaFree(d_cs);
   double worst = max_err;
   if (!(max_terr < 1e-6)) worst = 1;
   if (!(max_tterr < 1e-6)) worst = 1;
@@ -154,18 +137,18 @@ static GemmLaunch make_bench(int nops, int M, int N, int K, int passes, bool tt)
   memset(&L, 0, sizeof(L));
   L.n_ops = nops;
   for (int i = 0; i < nops; ++i) {
-    float *a_hi, *a_lo, *b_hi, *b_lo, *t_hi, *t_lo, *tt_hi, *tt_lo;
-    CK(cudaMalloc(&a_hi, (size_t)M * K * 4)); CK(cudaMalloc(&a_lo, (size_t)M * K * 4));
-    CK(cudaMalloc(&b_hi, (size_t)N * K * 4)); CK(cudaMalloc(&b_lo, (size_t)N * K * 4));
-    CK(cudaMalloc(&t_hi, (size_t)M * N * 4)); CK(cudaMalloc(&t_lo, (size_t)M * N * 4));
-    CK(cudaMalloc(&tt_hi, (size_t)M * N * 4)); CK(cudaMalloc(&tt_lo, (size_t)M * N * 4));
-    CK(cudaMemset(a_hi, 0, (size_t)M * K * 4)); CK(cudaMemset(a_lo, 0, (size_t)M * K * 4));
-    CK(cudaMemset(b_hi, 0, (size_t)N * K * 4)); CK(cudaMemset(b_lo, 0, (size_t)N * K * 4));
+    float *a, *b, *t, *ttp;
+    CK(cudaMalloc(&a, (size_t)M * K * 4));
+    CK(cudaMalloc(&b, (size_t)N * K * 4));
+    CK(cudaMalloc(&t, (size_t)M * N * 4));
+    CK(cudaMalloc(&ttp, (size_t)M * N * 4));
+    CK(cudaMemset(a, 0, (size_t)M * K * 4));
+    CK(cudaMemset(b, 0, (size_t)N * K * 4));
     GemmOp& o = L.op[i];
-    o.a_hi = a_hi; o.a_lo = a_lo; o.a_rows = M; o.b_hi = b_hi; o.b_lo = b_lo; o.b_rows = N;
+    o.a = a; o.a_rows = M; o.b = b; o.b_rows = N;
     o.M = M; o.N = N; o.K = K; o.act = ACT_RELU;
-    o.t_hi = t_hi; o.t_lo = t_lo; o.t_rows = M; o.t_n = N; o.passes = passes; o.alpha = 1.f;
-    if (tt) { o.tt_hi = tt_hi; o.tt_lo = tt_lo; o.tt_rows = N; }
+    o.t = t; o.t_rows = M; o.t_n = N; o.passes = passes; o.alpha = 1.f;
+    if (tt) { o.tt = ttp; o.tt_rows = N; }
   }
   return L;
 }
@@ -228,8 +211,8 @@ static void bench(int nops, int M, int N, int K, int passes, bool simt, bool tt)
   long long h[16];
   CK(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
   double ns = (double)(h[10] - h[9]);
-  printf("  prof cycles: setup=%lld issue_all=%lld first_full=%lld last_commit=%lld accum=%lld tmem_ld=%lld epi_end=%lld exit=%lld | %.0f ns => %.0f MHz\n",
-         h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0],
+  printf("  prof cycles: setup=%lld issue_all=%lld first_full=%lld last_commit=%lld accum=%lld tmem_ld=%lld bar=%lld math=%lld epi_end=%lld exit=%lld | %.0f ns => %.0f MHz\n",
+         h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[11] - h[0], h[12] - h[0], h[7] - h[0],
          h[8] - h[0], ns, (h[8] - h[0]) / ns * 1e3);
 }
 
