@@ -109,6 +109,10 @@ int oprl_sample(oprl_engine* e, const int* ep_step_host, int B);
 /* Generic path: load a caller-provided dense device batch instead of gathering. */
 int oprl_load_batch(oprl_engine* e, const float* s, const float* a, const float* r,
                     const float* d, const float* s2, int B);
+/* Same with HOST arrays (fp32, contiguous): packed into a pinned staging ring and moved with a
+ * single asynchronous H2D copy -- the path a CPU-resident replay buffer / trainer would use. */
+int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const float* r,
+                         const float* d, const float* s2, int B);
 /* Inject the standard-normal draws of the next update (parity tests).  which = 0:
  * first draw of the update (TD3 smoothing noise / SAC-TQC next-action noise),
  * 1: second draw (SAC-TQC actor-step noise).  noise: device pointer [B, A]. */

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "oprl_batch_bind": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int]),
     "oprl_sample": (C.c_int, [_P, _P, C.c_int]),
     "oprl_load_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int]),
+    "oprl_load_batch_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int]),
     "oprl_set_noise": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "oprl_update": (C.c_int, [_P, C.c_int, C.c_int]),
     "oprl_step": (C.c_int, [_P, C.c_int, C.c_int]),

@@ -149,6 +149,13 @@ struct oprl_engine {
   int* h_idx = nullptr;  // pinned staging for host-chosen (episode, step) pairs
   int h_idx_cap = 0;
   int* h_flag = nullptr;  // pinned: ext_noise mask staging
+  // host-batch staging ring (pinned) + its device mirror, for oprl_load_batch_host
+  static constexpr int kHostSlots = 4;
+  float* h_stage[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t h_stage_done[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
+  float* d_stage = nullptr;
+  size_t stage_floats = 0;
+  int stage_next = 0;
   int ext_mask = 0;
   int cur_B = 0;
 
@@ -348,8 +355,10 @@ struct Builder {
         }
         stage(s0 + l).ops.push_back(o);
         in = pass.h[l];
-      } else {
+      } else if (last) {
         *last = o;
+      } else {
+        return s0 + nl - 1;  // hidden layers only: the scalar head runs in critic_head_kernel
       }
     }
     return s0 + nl;
@@ -362,13 +371,15 @@ struct Builder {
   // want_dw = false: only the dX chain (critic inside the actor step).  If dx_last is
   // set, the layer-0 input gradient GEMM is emitted with that (half-configured) epilogue.
   // Returns the stage after the last emitted op.
+  // l_start: first layer to process (default: the last one; nl - 2 when critic_head_kernel
+  // already produced dz of the last hidden layer).
   int backward(int s0, const Net& net, float* grad, const Pass& pass, TM dz, TM dzT,
-               const TM& XT, bool want_dw, bool is_actor, GemmOp* dx_epilogue) {
+               const TM& XT, bool want_dw, bool is_actor, GemmOp* dx_epilogue, int l_start = -1) {
     const int Bp = w->Bp;
     const int nl = static_cast<int>(net.L.size());
     const int S = e->cfg.state_dim, A = e->cfg.action_dim, A4 = e->A4;
     int s = s0;
-    for (int l = nl - 1; l >= 0; --l, ++s) {
+    for (int l = (l_start < 0 ? nl - 1 : l_start); l >= 0; --l, ++s) {
       const Layer& ly = net.L[l];
       if (want_dw) {
         // dW_l [out x in] = sum_b dzT(o, b) * hprevT(i, b)
@@ -430,6 +441,67 @@ struct Builder {
 // ================================================================== DDPG / TD3 program
 namespace oprl {
 
+static bool use_simt_head(const oprl_engine* e) {
+  static const bool force_gemm = getenv("OPRL_B200_HEAD_GEMM") && atoi(getenv("OPRL_B200_HEAD_GEMM")) != 0;
+  const oprl_cfg& c = e->cfg;
+  return !force_gemm && c.algo != OPRL_ALGO_TQC && c.critic_hidden <= 256 && c.critic_hidden % 32 == 0 &&
+         c.n_critics <= 2;
+}
+
+// Adds the fused scalar-head stage (policy.cuh critic_head_kernel) and returns the dz2 / dz2T
+// matrices it writes for each critic.
+static void add_critic_head(oprl_engine* e, Builder& b, int stage, int mode, int nq, const Pass* p_on,
+                            const Pass* p_tg, const float* logp2, const float* logp, float* alpha_x,
+                            bool bump_actor, bool want_T, TM* dz2, TM* dz2T) {
+  const oprl_cfg& c = e->cfg;
+  Group& gc = e->grp[OPRL_NET_CRITIC];
+  const int B = b.w->B, Bp = b.w->Bp, H = c.critic_hidden;
+  CriticHeadArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode; a.nq = nq; a.B = B; a.H = H;
+  a.h_rows = Bp;
+  a.dzT_rows = pad128(H);
+  a.gamma = static_cast<float>(c.gamma);
+  a.inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
+  a.target_entropy = static_cast<float>(c.target_entropy);
+  for (int i = 0; i < nq; ++i) {
+    const Net& net = gc.nets[i];
+    const Layer& last = net.L.back();
+    const int hl = static_cast<int>(net.L.size()) - 2;  // last hidden layer
+    a.h2[i] = p_on[i].h[hl].p;
+    a.w3[i] = gc.theta + last.w_off;
+    a.b3[i] = gc.theta + last.b_off;
+    if (mode == 0) {
+      a.h2t[i] = p_tg[i].h[hl].p;
+      a.w3t[i] = gc.target + last.w_off;
+      a.b3t[i] = gc.target + last.b_off;
+      a.gw3[i] = gc.grad + last.w_off;
+      a.gb3[i] = gc.grad + last.b_off;
+      a.gb2[i] = gc.grad + net.L[hl].b_off;
+    }
+    dz2[i] = e->alloc_tm(Bp, pad32(H));
+    a.dz2[i] = dz2[i].p;
+    if (want_T) {
+      dz2T[i] = e->alloc_tm(pad128(H), Bp);
+      a.dz2T[i] = dz2T[i].p;
+    } else {
+      dz2T[i] = TM{nullptr, 0, 0};
+    }
+  }
+  a.r = e->br; a.d = e->bd; a.logp2 = logp2; a.logp = logp;
+  const int blocks = (B + kHeadRows - 1) / kHeadRows;
+  a.part = e->alloc_floats(static_cast<size_t>(blocks) * (nq * 2 * H + 8));
+  a.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+  a.alpha_x = alpha_x;
+  a.bump_actor = bump_actor ? 1 : 0;
+  const int threads = pad32(H);
+  const size_t smem = std::max<size_t>(static_cast<size_t>(threads / 32) * 32 + 32, static_cast<size_t>(blocks) * 8) * sizeof(float);
+  DevState* st = e->d_state;
+  b.stage(stage).add_simt([a, st, blocks, threads, smem](cudaStream_t sm) {
+    launch_k(critic_head_kernel, dim3(blocks), dim3(threads), smem, sm, a, st);
+  });
+}
+
 static void fill_constant_seed(oprl_engine* e, const TM& D, int B, int ncols, float value) {
   // tiled [Bp x 32] matrix with `value` in columns [0, ncols) of rows [0, B)
   std::vector<float> h(static_cast<size_t>(D.rows) * D.cols, 0.f);
@@ -448,6 +520,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   Group& ga = e->grp[OPRL_NET_ACTOR];
   Group& gc = e->grp[OPRL_NET_CRITIC];
   const float inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
+  const bool simt_head = use_simt_head(e);
 
   // S0: gather / dense load + noise (launched by oprl_sample / oprl_load_batch, not here)
   int s = 0;
@@ -484,7 +557,8 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     // critic(s, a) -> q                          (ddpg.py:96, td3.py:95)
     for (int i = 0; i < nq; ++i) {
       GemmOp lq;
-      b.forward(s, gc.nets[i], gc.theta, false, w->X, p_c[i], true, &lq);
+      b.forward(s, gc.nets[i], gc.theta, false, w->X, p_c[i], true, simt_head ? nullptr : &lq);
+      if (simt_head) continue;
       lq.rm = q + i; lq.rm_ld = nq; lq.rm_m = Bp; lq.rm_n = 1;
       b.stage(s_end - 1).ops.push_back(lq);
     }
@@ -495,12 +569,25 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     int s_end = s;
     for (int i = 0; i < nq; ++i) {
       GemmOp lq;
-      s_end = b.forward(s, gc.nets[i], gc.target, true, w->Xn, p_ct[i], false, &lq);
+      s_end = b.forward(s, gc.nets[i], gc.target, true, w->Xn, p_ct[i], false, simt_head ? nullptr : &lq);
+      if (simt_head) continue;
       lq.rm = qn + i; lq.rm_ld = nq; lq.rm_m = Bp; lq.rm_n = 1;
       b.stage(s_end - 1).ops.push_back(lq);
     }
     s = s_end;
   }
+  if (simt_head) {
+    // heads, TD target, MSE seeds, head gradients and dz of the last hidden layer: one launch
+    TM dz2[2], dz2T[2];
+    add_critic_head(e, b, s, 0, nq, p_c, p_ct, nullptr, nullptr, nullptr, do_actor, true, dz2, dz2T);
+    ++s;
+    int s_end = s;
+    for (int i = 0; i < nq; ++i) {
+      const int nl = static_cast<int>(gc.nets[i].L.size());
+      s_end = b.backward(s, gc.nets[i], gc.grad, p_c[i], dz2[i], dz2T[i], w->XT, true, false, nullptr, nl - 2);
+    }
+    s = s_end;
+  } else {
   // TD target + MSE seeds                        (ddpg.py:95-98, td3.py:105-112)
   TdArgs td;
   memset(&td, 0, sizeof(td));
@@ -526,6 +613,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       s_end = b.backward(s, gc.nets[i], gc.grad, p_c[i], td.D3[i], td.D3T[i], w->XT, true, false, nullptr);
     s = s_end;
   }
+  }
   b.seg = 1;
   // critic Adam (+ Polyak when the reference does it in this update) + re-tiling
   {
@@ -539,7 +627,16 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     Pass p_cq;
     // critic.Q1(s, pi(s)) with the just-updated critic   (ddpg.py:104, td3.py:135-137)
     GemmOp lq;
-    int s_end = b.forward(s, gc.nets[0], gc.theta, false, w->Xp, p_cq, false, &lq);
+    int s_end = b.forward(s, gc.nets[0], gc.theta, false, w->Xp, p_cq, false, simt_head ? nullptr : &lq);
+    TM Dm = TM{nullptr, 0, 0};
+    int l_start = -1;
+    if (simt_head) {
+      TM dz2[2], dz2T[2];
+      add_critic_head(e, b, s_end, 1, 1, &p_cq, nullptr, nullptr, nullptr, nullptr, false, false, dz2, dz2T);
+      Dm = dz2[0];
+      s = s_end + 1;
+      l_start = static_cast<int>(gc.nets[0].L.size()) - 2;
+    } else {
     // actor_loss = -mean(q): alpha = -1/count, rows >= B dropped, column sum -> scalar
     lq.alpha = -inv_count;
     lq.m_valid = B;
@@ -551,8 +648,9 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     b.stage(s_end - 1).ops.push_back(lq);
     s = s_end - 1;  // the dX chain starts beside the q head
     // seed: dL/dq = -1/count on valid rows (constant)
-    TM Dm = e->alloc_tm(Bp, 32);
+    Dm = e->alloc_tm(Bp, 32);
     fill_constant_seed(e, Dm, B, 1, -inv_count);
+    }
     // critic dX chain down to the action columns, then tanh'
     const Layer& a_last = ga.nets[0].L.back();
     TM dza = e->alloc_tm(Bp, a_last.Np);
@@ -569,7 +667,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     dx.colsum_n = a_last.out;
     dx.colsum_out = ga.grad + a_last.b_off;
     dx.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(a_last.Np / kBN));
-    s = b.backward(s, gc.nets[0], nullptr, p_cq, Dm, TM{nullptr, 0, 0}, w->XT, false, false, &dx);
+    s = b.backward(s, gc.nets[0], nullptr, p_cq, Dm, TM{nullptr, 0, 0}, w->XT, false, false, &dx, l_start);
     // actor backward
     s = b.backward(s, ga.nets[0], ga.grad, p_a, dza, dzaT, w->XT, true, true, nullptr);
     // actor Adam + Polyak + re-tiling   (ddpg.py:107,79-84 ; td3.py:141,83-84)
@@ -598,6 +696,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   DevState* st = e->d_state;
   const float inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
   const Layer& a_last = ga.nets[0].L.back();
+  const bool simt_head = use_simt_head(e);  // SAC: scalar critic heads run in critic_head_kernel
 
   float* out_n = e->alloc_floats(static_cast<size_t>(Bp) * 2 * A);  // actor(s') raw output
   float* out_p = e->alloc_floats(static_cast<size_t>(Bp) * 2 * A);  // actor(s)  raw output
@@ -621,10 +720,11 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     b.stage(s_act - 1).ops.push_back(last);
     for (int i = 0; i < nc; ++i) {
       GemmOp lq;
-      const int se = b.forward(s, gc.nets[i], gc.theta, false, w->X, p_c[i], true, &lq);
+      const int se = b.forward(s, gc.nets[i], gc.theta, false, w->X, p_c[i], true, simt_head ? nullptr : &lq);
+      s = std::max(s, se);
+      if (simt_head) continue;
       lq.rm = z + i * nq; lq.rm_ld = NT; lq.rm_m = Bp; lq.rm_n = nq;
       b.stage(se - 1).ops.push_back(lq);
-      s = std::max(s, se);
     }
   }
   {
@@ -650,7 +750,8 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     int s_end = s;
     for (int i = 0; i < nc; ++i) {
       GemmOp lq;
-      s_end = b.forward(s, gc.nets[i], gc.target, true, w->Xn, p_ct[i], false, &lq);
+      s_end = b.forward(s, gc.nets[i], gc.target, true, w->Xn, p_ct[i], false, simt_head ? nullptr : &lq);
+      if (simt_head) continue;
       lq.rm = zn + i * nq; lq.rm_ld = NT; lq.rm_m = Bp; lq.rm_n = nq;
       b.stage(s_end - 1).ops.push_back(lq);
     }
@@ -658,11 +759,15 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   }
   // loss + seeds
   std::vector<TM> D(nc), DT(nc);
-  for (int i = 0; i < nc; ++i) {
+  for (int i = 0; i < nc && !simt_head; ++i) {
     D[i] = e->alloc_tm(Bp, 32);
     DT[i] = e->alloc_tm(128, Bp);
   }
-  if (!tqc) {
+  int critic_l_start = -1;
+  if (simt_head) {
+    add_critic_head(e, b, s, 0, nc, p_c.data(), p_ct.data(), logp2, nullptr, nullptr, true, true, D.data(), DT.data());
+    critic_l_start = static_cast<int>(gc.nets[0].L.size()) - 2;
+  } else if (!tqc) {
     TdArgs td;
     memset(&td, 0, sizeof(td));
     td.qn = zn; td.q = z; td.r = e->br; td.d = e->bd; td.logpi_next = logp2;
@@ -699,7 +804,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   {
     int s_end = s;
     for (int i = 0; i < nc; ++i)
-      s_end = b.backward(s, gc.nets[i], gc.grad, p_c[i], D[i], DT[i], w->XT, true, false, nullptr);
+      s_end = b.backward(s, gc.nets[i], gc.grad, p_c[i], D[i], DT[i], w->XT, true, false, nullptr, critic_l_start);
     s = s_end;
   }
   b.seg = 1;
@@ -713,7 +818,8 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     int s_end = s;
     for (int i = 0; i < nc; ++i) {
       GemmOp lq;
-      s_end = b.forward(s, gc.nets[i], gc.theta, false, w->Xp, p_cq[i], false, &lq);
+      s_end = b.forward(s, gc.nets[i], gc.theta, false, w->Xp, p_cq[i], false, simt_head ? nullptr : &lq);
+      if (simt_head) continue;
       lq.rm = zpi + i * nq; lq.rm_ld = NT; lq.rm_m = Bp; lq.rm_n = nq;
       b.stage(s_end - 1).ops.push_back(lq);
     }
@@ -721,8 +827,15 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   }
   // actor-loss scalars + seeds
   std::vector<TM> Dq(nc);
-  for (int i = 0; i < nc; ++i) Dq[i] = e->alloc_tm(Bp, 32);
-  {
+  int actor_l_start = -1;
+  if (simt_head) {
+    std::vector<TM> unused(nc);
+    add_critic_head(e, b, s, 1, nc, p_cq.data(), nullptr, nullptr, logp, ga.grad + ga.floats, false, false,
+                    Dq.data(), unused.data());
+    actor_l_start = static_cast<int>(gc.nets[0].L.size()) - 2;
+    ++s;
+  } else {
+    for (int i = 0; i < nc; ++i) Dq[i] = e->alloc_tm(Bp, 32);
     ActorSeedArgs as;
     memset(&as, 0, sizeof(as));
     as.q = zpi; as.logp = logp; as.B = B; as.nq = NT; as.tqc = tqc ? 1 : 0;
@@ -752,7 +865,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       memset(&dx, 0, sizeof(dx));
       dx.alpha = 1.f;
       dx.rm = da; dx.rm_ld = A; dx.rm_m = Bp; dx.rm_n = A;
-      s_end = b.backward(s, gc.nets[i], nullptr, p_cq[i], Dq[i], TM{nullptr, 0, 0}, w->XT, false, false, &dx);
+      s_end = b.backward(s, gc.nets[i], nullptr, p_cq[i], Dq[i], TM{nullptr, 0, 0}, w->XT, false, false, &dx, actor_l_start);
     }
     s = s_end;
   }
@@ -920,8 +1033,9 @@ static oprl_engine::Work* get_work(oprl_engine* e, int B) {
 static void launch_gather(oprl_engine* e, oprl_engine::Work* w, GatherArgs g) {
   g.bs = e->bs; g.ba = e->ba; g.br = e->br; g.bd = e->bd; g.bs2 = e->bs2;
   const int total = g.noise[0].n + g.noise[1].n;
-  const int nblocks = total ? std::min((total + kGatherThreads * 4 - 1) / (kGatherThreads * 4), 64) : 0;
-  gather_kernel<<<g.B + nblocks, kGatherThreads, 0, e->stream>>>(g, e->d_state);
+  const int nblocks = total ? std::min((total + kGatherBlock * 4 - 1) / (kGatherBlock * 4), 64) : 0;
+  const int row_blocks = (g.B + kGatherRows - 1) / kGatherRows;
+  gather_kernel<<<row_blocks + nblocks, kGatherBlock, 0, e->stream>>>(g, e->d_state);
   CU(cudaGetLastError());
 }
 
@@ -989,6 +1103,9 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   memset(e->h_state, 0, sizeof(DevState));
   e->h_state->log_alpha = std::log(cfg->alpha_init > 0 ? cfg->alpha_init : 1.0);
   e->h_state->alpha = static_cast<float>(cfg->alpha_init);
+  e->h_state->lr[0] = cfg->lr_actor;
+  e->h_state->lr[1] = cfg->lr_critic;
+  for (int k = 0; k < 2; ++k) e->h_state->b1pow[k] = e->h_state->b2pow[k] = 1.0;
   CU(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(DevState), cudaMemcpyHostToDevice, e->stream));
   CU(cudaMallocHost(&p, 64));
   e->h_flag = static_cast<int*>(p);
@@ -1008,6 +1125,10 @@ void oprl_engine_destroy(oprl_engine* e) {
   for (void* p : e->blocks) cudaFree(p);
   if (e->h_state) cudaFreeHost(e->h_state);
   if (e->h_flag) cudaFreeHost(e->h_flag);
+  for (int i = 0; i < oprl_engine::kHostSlots; ++i) {
+    if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
+    if (e->h_stage_done[i]) cudaEventDestroy(e->h_stage_done[i]);
+  }
   if (e->d_prefix) cudaFree(e->d_prefix);
   cudaStreamDestroy(e->own_stream);
   delete e;
@@ -1142,6 +1263,42 @@ int oprl_load_batch(oprl_engine* e, const float* s, const float* a, const float*
   API_END
 }
 
+int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const float* r, const float* d,
+                         const float* s2, int B) {
+  if (!e || !s || !a || !r || !d || !s2 || B <= 0) return fail(-1, "bad batch");
+  API_BEGIN
+  const int S = e->cfg.state_dim, A = e->cfg.action_dim;
+  const size_t n = static_cast<size_t>(B) * (2 * S + A + 2);
+  if (n > e->stage_floats) {
+    CU(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < oprl_engine::kHostSlots; ++i) {
+      if (e->h_stage[i]) CU(cudaFreeHost(e->h_stage[i]));
+      void* p;
+      CU(cudaMallocHost(&p, n * sizeof(float)));
+      e->h_stage[i] = static_cast<float*>(p);
+      if (!e->h_stage_done[i]) CU(cudaEventCreateWithFlags(&e->h_stage_done[i], cudaEventDisableTiming));
+    }
+    e->d_stage = e->alloc_floats(n);
+    e->stage_floats = n;
+  }
+  // one pinned slot per in-flight step: pack the five host arrays, one H2D copy
+  const int slot = e->stage_next;
+  e->stage_next = (slot + 1) % oprl_engine::kHostSlots;
+  CU(cudaEventSynchronize(e->h_stage_done[slot]));  // the copy that last used this slot is done
+  float* h = e->h_stage[slot];
+  const size_t ns = static_cast<size_t>(B) * S, na = static_cast<size_t>(B) * A;
+  memcpy(h, s, ns * 4);
+  memcpy(h + ns, a, na * 4);
+  memcpy(h + ns + na, r, static_cast<size_t>(B) * 4);
+  memcpy(h + ns + na + B, d, static_cast<size_t>(B) * 4);
+  memcpy(h + ns + na + 2 * B, s2, ns * 4);
+  CU(cudaMemcpyAsync(e->d_stage, h, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaEventRecord(e->h_stage_done[slot], e->stream));
+  const float* ds = e->d_stage;
+  return oprl_load_batch(e, ds, ds + ns, ds + ns + na, ds + ns + na + B, ds + ns + na + 2 * B, B);
+  API_END
+}
+
 int oprl_set_noise(oprl_engine* e, int which, const float* noise_dev, int n) {
   if (!e || which < 0 || which > 1 || !noise_dev) return fail(-1, "bad noise call");
   const int A = e->cfg.action_dim;
@@ -1218,6 +1375,12 @@ int oprl_set_state(oprl_engine* e, const oprl_state* in) {
   s.m_alpha = in->m_alpha;
   s.v_alpha = in->v_alpha;
   s.alpha = static_cast<float>(std::exp(in->log_alpha));
+  for (int k = 0; k < 2; ++k) {
+    s.b1pow[k] = std::pow(kBeta1, static_cast<double>(s.step[k]));
+    s.b2pow[k] = std::pow(kBeta2, static_cast<double>(s.step[k]));
+    s.step_size[k] = static_cast<float>(s.lr[k] / (1.0 - s.b1pow[k]));
+    s.bc2_sqrt[k] = static_cast<float>(std::sqrt(1.0 - s.b2pow[k]));
+  }
   CU(cudaMemcpyAsync(e->d_state, e->h_state, sizeof(DevState), cudaMemcpyHostToDevice, e->stream));
   CU(cudaStreamSynchronize(e->stream));
   return 0;

@@ -23,7 +23,32 @@ struct DevState {
   float alpha;                         // exp(log_alpha) rounded to fp32
   float pad1;
   float scalars[32];  // see enum Scalar
+  // torch.optim.Adam bias corrections, kept current by the kernel that advances the step
+  // counters so that the Adam launches do no double-precision pow() on their critical path:
+  //   step_size = lr / (1 - beta1^t),  bc2_sqrt = sqrt(1 - beta2^t)      (0 actor, 1 critic)
+  double lr[2];
+  double b1pow[2], b2pow[2];  // beta1^t, beta2^t as running products
+  float step_size[2], bc2_sqrt[2];
 };
+
+constexpr double kBeta1 = 0.9, kBeta2 = 0.999;
+
+// Advance the per-update counters (one thread, at the end of the loss kernel): everything that
+// consumed the old tick (sampling, noise) ran in earlier launches; the Adam launches that need
+// the new step counts run later.
+__device__ __forceinline__ void bump_counters(DevState* st, int bump_actor) {
+  st->tick += 1;
+  st->ext_noise = 0;
+#pragma unroll
+  for (int opt = 0; opt < 2; ++opt) {
+    if (opt == 0 && !bump_actor) continue;
+    st->step[opt] += 1;
+    st->b1pow[opt] *= kBeta1;
+    st->b2pow[opt] *= kBeta2;
+    st->step_size[opt] = static_cast<float>(st->lr[opt] / (1.0 - st->b1pow[opt]));
+    st->bc2_sqrt[opt] = static_cast<float>(sqrt(1.0 - st->b2pow[opt]));
+  }
+}
 
 enum Scalar : int {
   SC_CRITIC_LOSS = 0,
@@ -74,17 +99,21 @@ struct GatherArgs {
   NoiseSpec noise[2];  // blocks >= B draw the update's normals (n == 0: none)
 };
 
-constexpr int kGatherThreads = 64;
-__global__ void __launch_bounds__(kGatherThreads)
+constexpr int kGatherThreads = 64;   // noise blocks / row-major gather
+constexpr int kGatherRows = 8;       // batch rows per block, one warp each
+constexpr int kGatherBlock = 32 * kGatherRows;
+constexpr int kPrefixSmem = 4096;    // episode prefix sums cached in shared memory up to this many
+__global__ void __launch_bounds__(kGatherBlock)
     gather_kernel(const __grid_constant__ GatherArgs g, const DevState* st) {
-  const int b = blockIdx.x;
-  if (b >= g.B) {
+  const int row_blocks = (g.B + kGatherRows - 1) / kGatherRows;
+  if (static_cast<int>(blockIdx.x) >= row_blocks) {
     // ---- noise blocks: 4 normals per thread, one Philox subsequence per quad
     const int total = g.noise[0].n + g.noise[1].n;
     const unsigned long long tick = st->tick;
     const int ext = st->ext_noise;
-    for (int base = ((b - g.B) * kGatherThreads + threadIdx.x) * 4; base < total;
-         base += (gridDim.x - g.B) * kGatherThreads * 4) {
+    const int nb = gridDim.x - row_blocks;
+    for (int base = ((blockIdx.x - row_blocks) * kGatherBlock + threadIdx.x) * 4; base < total;
+         base += nb * kGatherBlock * 4) {
       curandStatePhilox4_32_10_t rng;
       curand_init(g.seed, static_cast<unsigned long long>(base >> 2), tick * 8ull, &rng);
       const float4 z = curand_normal4(&rng);
@@ -108,36 +137,46 @@ __global__ void __launch_bounds__(kGatherThreads)
     }
     return;
   }
-  __shared__ int s_ep, s_step;
-  if (threadIdx.x == 0) {
-    int ep = 0, step = 0;
-    if (!g.dense) {
-      if (g.ep_step) {
-        ep = g.ep_step[2 * b];
-        step = g.ep_step[2 * b + 1];
-      } else {
+  // ---- gather blocks: one warp per sampled transition
+  __shared__ int s_prefix[kPrefixSmem];
+  const bool device_draw = !g.dense && !g.ep_step;
+  const bool cached = device_draw && g.n_eps + 1 <= kPrefixSmem;
+  if (cached) {
+    // one coalesced pass instead of a dependent global-memory binary search per row
+    for (int i = threadIdx.x; i <= g.n_eps; i += kGatherBlock) s_prefix[i] = g.prefix[i];
+    __syncthreads();
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kGatherRows + warp;
+  if (b >= g.B) return;
+  int ep = 0, step = 0;
+  if (!g.dense) {
+    if (g.ep_step) {
+      ep = g.ep_step[2 * b];
+      step = g.ep_step[2 * b + 1];
+    } else {
+      if (lane == 0) {
         curandStatePhilox4_32_10_t rng;
         curand_init(g.seed ^ 0x9E3779B97F4A7C15ull, static_cast<unsigned long long>(b), st->tick * 4ull, &rng);
         const unsigned int u = curand(&rng);
-        int t = static_cast<int>((static_cast<unsigned long long>(u) * g.n_trans) >> 32);
+        const int t = static_cast<int>((static_cast<unsigned long long>(u) * g.n_trans) >> 32);
+        const int* pre = cached ? s_prefix : g.prefix;
         int lo = 0, hi = g.n_eps;  // find ep with prefix[ep] <= t < prefix[ep+1]
         while (hi - lo > 1) {
           const int mid = (lo + hi) >> 1;
-          if (g.prefix[mid] <= t) lo = mid; else hi = mid;
+          if (pre[mid] <= t) lo = mid; else hi = mid;
         }
         ep = lo;
-        step = t - g.prefix[lo];
+        step = t - pre[lo];
         if (g.out_ep_step) {
           g.out_ep_step[2 * b] = ep;
           g.out_ep_step[2 * b + 1] = step;
         }
       }
+      ep = __shfl_sync(0xffffffffu, ep, 0);
+      step = __shfl_sync(0xffffffffu, step, 0);
     }
-    s_ep = ep;
-    s_step = step;
   }
-  __syncthreads();
-  const int ep = s_ep, step = s_step;
   const float* src_a;
   const float* src_s;
   const float* src_s2;
@@ -158,7 +197,7 @@ __global__ void __launch_bounds__(kGatherThreads)
     d = g.dones[row];
   }
   const int W = g.A + 2 * g.S;
-  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+  for (int c = lane; c < W; c += 32) {
     if (c < g.A) {
       const float v = src_a[c];
       if (g.ba) g.ba[static_cast<size_t>(b) * g.A + c] = v;
@@ -178,7 +217,7 @@ __global__ void __launch_bounds__(kGatherThreads)
       store_tiled(g.Xn, b, g.A4 + j, v);
     }
   }
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     g.br[b] = r;
     g.bd[b] = d;
   }
@@ -287,12 +326,7 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(TdArgs a, DevState* st) 
     st->scalars[SC_Q_MEAN] = qs * invB;
     st->scalars[SC_QT_MEAN] = ys * invB;
     st->scalars[SC_Q_ERR_MEAN] = es * invB;
-    // Everything that consumed the old tick (sampling, noise) ran in earlier launches;
-    // everything that needs the new Adam step counts runs in later ones.
-    st->tick += 1;
-    st->step[1] += 1;
-    st->step[0] += a.bump_actor;
-    st->ext_noise = 0;
+    bump_counters(st, a.bump_actor);
   }
 }
 
@@ -329,15 +363,8 @@ __global__ void __launch_bounds__(kAdamThreads)
   ptx::pdl_trigger();
   ptx::pdl_wait();
   const AdamSeg sg = segs[blockIdx.y];
-  __shared__ float s_step_size, s_bc2_sqrt;
-  if (threadIdx.x == 0 && (mode & 1)) {
-    const int t = st->step[sg.opt];
-    const double bc1 = 1.0 - pow(hp.beta1, static_cast<double>(t));
-    const double bc2 = 1.0 - pow(hp.beta2, static_cast<double>(t));
-    s_step_size = static_cast<float>(hp.lr[sg.opt] / bc1);
-    s_bc2_sqrt = static_cast<float>(sqrt(bc2));
-  }
-  __syncthreads();
+  const float s_step_size = st->step_size[sg.opt];
+  const float s_bc2_sqrt = st->bc2_sqrt[sg.opt];
   const float w1 = hp.w1;
   const float w2 = hp.w2;
   for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.n; i += gridDim.x * kAdamThreads) {

@@ -300,12 +300,233 @@ __global__ void __launch_bounds__(kTqcThreads) tqc_loss_kernel(TqcArgs a, DevSta
     const float tot = block_sum<kTqcThreads>(l, red);
     if (tid == 0) {
       st->scalars[SC_CRITIC_LOSS] = tot * a.inv_total;
-      st->tick += 1;
-      st->step[1] += 1;
-      st->step[0] += a.bump_actor;
-      st->ext_noise = 0;
+      bump_counters(st, a.bump_actor);
       *a.counter = 0u;
     }
+  }
+}
+
+}  // namespace oprl
+
+namespace oprl {
+
+// ------------------------------------------------ scalar critic head, forward + backward (SIMT)
+// For critics with ONE output (DDPG / TD3 / SAC, nn_models.py:27-81) the last Linear layer is a
+// dot product per row: running it -- and the first backward step it seeds -- as padded tensor-core
+// GEMM stages costs three launches of the dependency chain for ~0.1 % of the FLOPs.  This kernel
+// does the whole neighbourhood of the loss in one launch, one block per 8 batch rows, one thread
+// per hidden unit:
+//   mode 0 (critic step; ddpg.py:94-98, td3.py:95-112, sac.py:96-105)
+//     q_i = h2_i . w3_i + b3_i ; qn_i likewise from the target nets ; y = r + (1-d) gamma (min_i qn_i - alpha logp')
+//     L = sum_i mean (q_i - y)^2 ; dq_i = (2/count)(q_i - y)
+//   mode 1 (actor step; ddpg.py:104, td3.py:135-137, sac.py:124-126)
+//     q_i = h2_i . w3_i + b3_i at (s, pi(s)) ; L = alpha mean(logp) - mean(min_i q_i) ; dq_i = -(1/count)[i = argmin]
+//   both: dz2_i = dq_i w3_i^T (.) relu'(h2_i)  (tiled + transposed), and in mode 0 the gradients of
+//   w3_i, b3_i and of the previous layer's bias (column sums of dz2_i), reduced in a fixed order.
+struct CriticHeadArgs {
+  int mode, nq, B, H;
+  int h_rows;    // padded rows of the tiled h2 / dz2 matrices (Bp)
+  int dzT_rows;  // padded rows of the transposed dz2 (pad128(H))
+  float gamma, inv_count, target_entropy;
+  const float* h2[2];
+  const float* h2t[2];
+  const float* w3[2];
+  const float* b3[2];
+  const float* w3t[2];
+  const float* b3t[2];
+  const float* r;
+  const float* d;
+  const float* logp2;  // mode 0, SAC (nullable)
+  const float* logp;   // mode 1, SAC (nullable)
+  float* dz2[2];
+  float* dz2T[2];  // nullable (mode 1: no weight gradients needed)
+  float* gw3[2];
+  float* gb3[2];
+  float* gb2[2];
+  float* part;  // [gridDim.x][nq * 2 * H + 8]
+  unsigned int* counter;
+  float* alpha_x;  // mode 1, SAC: share of mean(logp) behind the actor gradient arena (nullable)
+  int bump_actor;
+};
+constexpr int kHeadRows = 8;
+__global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant__ CriticHeadArgs a, DevState* st) {
+  ptx::pdl_trigger();
+  ptx::pdl_wait();
+  extern __shared__ float sh[];  // [warps][32] dot partials, then [8][4] results
+  const int n = threadIdx.x;     // hidden unit
+  const int lane = n & 31, warp = n >> 5, nwarps = blockDim.x >> 5;
+  const int m0 = blockIdx.x * kHeadRows;
+  const bool live = n < a.H;
+  // ---- phase 1: the dot products of this block's 8 rows
+  float hv[2][kHeadRows];  // online hidden activations of this thread's unit (kept for phase 2)
+  float w3v[2] = {0.f, 0.f};
+  float prod[4][kHeadRows];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (i >= a.nq) break;
+    w3v[i] = live ? a.w3[i][n] : 0.f;
+    const float w3t = (a.mode == 0 && live) ? a.w3t[i][n] : 0.f;
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+      const size_t off = ct_index(a.h_rows, m0 + r, n);
+      const float h = live ? a.h2[i][off] : 0.f;
+      hv[i][r] = h;
+      prod[i][r] = h * w3v[i];
+      if (a.mode == 0) prod[2 + i][r] = live ? a.h2t[i][off] * w3t : 0.f;
+    }
+  }
+  float* red = sh;  // [nwarps][32]
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    // streams 0-1: online critics, 2-3: target critics (critic step only)
+    const bool valid = (s < 2) ? (s < a.nq) : (a.mode == 0 && s - 2 < a.nq);
+    if (!valid) continue;
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+      float x = prod[s][r];
+      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      x += __shfl_xor_sync(0xffffffffu, x, 8);
+      x += __shfl_xor_sync(0xffffffffu, x, 4);
+      x += __shfl_xor_sync(0xffffffffu, x, 2);
+      x += __shfl_xor_sync(0xffffffffu, x, 1);
+      if (lane == 0) red[warp * 32 + s * kHeadRows + r] = x;
+    }
+  }
+  __syncthreads();
+  float* res = sh + nwarps * 32;  // [4][8] dot products, then dq[2][8]
+  if (n < 32) {
+    float x = 0.f;
+    for (int wv = 0; wv < nwarps; ++wv) x += red[wv * 32 + n];
+    res[n] = x;
+  }
+  __syncthreads();
+  // ---- per-row loss terms and seeds (every thread computes them redundantly: no extra barrier)
+  float dq[2][kHeadRows];
+  float loss = 0.f, qsum = 0.f, ysum = 0.f, esum = 0.f, dsum[2] = {0.f, 0.f}, lpsum = 0.f;
+  const float alpha = st->alpha;
+#pragma unroll
+  for (int r = 0; r < kHeadRows; ++r) {
+    const int m = m0 + r;
+    dq[0][r] = dq[1][r] = 0.f;
+    if (m >= a.B) continue;
+    float q[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) q[i] = i < a.nq ? res[i * kHeadRows + r] + a.b3[i][0] : 0.f;
+    if (a.mode == 0) {
+      float qn = res[2 * kHeadRows + r] + a.b3t[0][0];
+      if (a.nq == 2) qn = fminf(qn, res[3 * kHeadRows + r] + a.b3t[1][0]);
+      if (a.logp2) qn = qn - alpha * a.logp2[m];
+      const float y = a.r[m] + ((1.0f - a.d[m]) * a.gamma) * qn;
+      ysum += y;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (i >= a.nq) break;
+        const float diff = q[i] - y;
+        loss += diff * diff;
+        dq[i][r] = a.inv_count * (2.0f * diff);
+        dsum[i] += dq[i][r];
+        if (i == 0) { qsum += q[0]; esum += diff; }
+      }
+    } else {
+      if (a.nq == 2) {
+        // torch.min backward: the smaller input gets the gradient, ties split evenly
+        const float g1 = (q[0] < q[1]) ? 1.f : (q[0] == q[1] ? 0.5f : 0.f);
+        dq[0][r] = -a.inv_count * g1;
+        dq[1][r] = -a.inv_count * (1.f - g1);
+        qsum += fminf(q[0], q[1]);
+      } else {
+        dq[0][r] = -a.inv_count;
+        qsum += q[0];
+      }
+      if (a.logp) lpsum += a.logp[m];
+    }
+  }
+  // ---- phase 2: dz2 = dq w3^T (.) relu'(h2), column sums
+  const int W = a.nq * 2 * a.H + 8;
+  float* mypart = a.part + static_cast<size_t>(blockIdx.x) * W;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (i >= a.nq) break;
+    float gw = 0.f, gb = 0.f;
+    float dzv[kHeadRows];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+      const float dz = hv[i][r] > 0.f ? dq[i][r] * w3v[i] : 0.f;
+      dzv[r] = dz;
+      gw = fmaf(dq[i][r], hv[i][r], gw);
+      gb += dz;
+      if (live) a.dz2[i][ct_index(a.h_rows, m0 + r, n)] = dz;
+    }
+    if (live && a.dz2T[i]) {
+      float* dst = a.dz2T[i] + ct_index(a.dzT_rows, n, m0);
+      *reinterpret_cast<float4*>(dst) = make_float4(dzv[0], dzv[1], dzv[2], dzv[3]);
+      *reinterpret_cast<float4*>(dst + 32) = make_float4(dzv[4], dzv[5], dzv[6], dzv[7]);
+    }
+    if (live && a.mode == 0) {
+      mypart[i * 2 * a.H + n] = gw;
+      mypart[i * 2 * a.H + a.H + n] = gb;
+    }
+  }
+  if (n == 0) {
+    float* tail = mypart + a.nq * 2 * a.H;
+    tail[0] = loss; tail[1] = qsum; tail[2] = ysum; tail[3] = esum;
+    tail[4] = dsum[0]; tail[5] = dsum[1]; tail[6] = lpsum;
+  }
+  // ---- last block: fixed-order reduction over blocks
+  __threadfence();
+  __syncthreads();
+  __shared__ unsigned int ticket;
+  if (n == 0) ticket = atomicAdd(a.counter, 1u);
+  __syncthreads();
+  if (ticket != gridDim.x - 1) return;
+  __threadfence();
+  if (a.mode == 0 && live) {
+    for (int i = 0; i < a.nq; ++i) {
+      // loads batched eight blocks at a time (independent L2 round trips), adds in block order
+      float gw = 0.f, gb = 0.f;
+      for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 8) {
+        float tw[8], tb[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool ok = b0 + k < gridDim.x;
+          const float* p = a.part + static_cast<size_t>(ok ? b0 + k : 0) * W + i * 2 * a.H;
+          tw[k] = ok ? __ldcg(p + n) : 0.f;
+          tb[k] = ok ? __ldcg(p + a.H + n) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          gw += tw[k];
+          gb += tb[k];
+        }
+      }
+      a.gw3[i][n] = gw;
+      a.gb2[i][n] = gb;
+    }
+  }
+  // per-block scalar tails: gathered by (block, k) threads in parallel, summed in block order
+  __syncthreads();
+  for (unsigned int idx = n; idx < gridDim.x * 8; idx += blockDim.x)
+    sh[idx] = __ldcg(a.part + static_cast<size_t>(idx >> 3) * W + a.nq * 2 * a.H + (idx & 7));
+  __syncthreads();
+  if (n == 0) {
+    float t[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (unsigned int b = 0; b < gridDim.x; ++b)
+      for (int k = 0; k < 7; ++k) t[k] += sh[b * 8 + k];
+    if (a.mode == 0) {
+      st->scalars[SC_CRITIC_LOSS] = t[0] * a.inv_count;
+      st->scalars[SC_Q_MEAN] = t[1] * a.inv_count;
+      st->scalars[SC_QT_MEAN] = t[2] * a.inv_count;
+      st->scalars[SC_Q_ERR_MEAN] = t[3] * a.inv_count;
+      a.gb3[0][0] = t[4];
+      if (a.nq == 2) a.gb3[1][0] = t[5];
+      bump_counters(st, a.bump_actor);
+    } else {
+      const float mean_lp = t[6] * a.inv_count;
+      st->scalars[SC_LOGPI_MEAN] = mean_lp;
+      st->scalars[SC_ACTOR_LOSS] = (a.logp ? st->alpha * mean_lp : 0.f) - t[1] * a.inv_count;
+      if (a.alpha_x) *a.alpha_x = mean_lp;
+    }
+    *a.counter = 0u;
   }
 }
 

@@ -169,6 +169,19 @@ class UpdateEngine:
         B = s.shape[0]
         self._ensure_batch(B)
         self._use_current_stream()
+        if not s.is_cuda:
+            # host batch: one packed pinned staging copy inside the engine
+            hs = []
+            for t, w in ((s, self.spec.state_dim), (a, self.spec.action_dim), (r, 1), (d, 1),
+                         (s2, self.spec.state_dim)):
+                if t.is_cuda:
+                    t = t.cpu()
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    t = t.to(torch.float32).contiguous()
+                assert t.numel() == B * w, "batch tensor has the wrong shape"
+                hs.append(t)
+            L.check(self._lib.oprl_load_batch_host(self._h, *[t.data_ptr() for t in hs], B))
+            return
         ts = []
         for t, w in ((s, self.spec.state_dim), (a, self.spec.action_dim), (r, 1), (d, 1),
                      (s2, self.spec.state_dim)):
