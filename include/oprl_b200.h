@@ -141,6 +141,16 @@ int oprl_engine_set_stream(oprl_engine* e, void* stream);
  * of the global-mean losses. */
 int oprl_engine_set_world_size(oprl_engine* e, int world_size);
 
+/* Fused NVLink all-reduce (one process per GPU, one node): instead of an NCCL call between the
+ * segments, every rank maps its peers' gradient arenas through CUDA IPC and the Adam kernel sums
+ * them in rank order after a flag handshake.  oprl_comm_init allocates this rank's exportable
+ * gradient arenas + flag block and writes three 64-byte IPC handles to handles_out;
+ * exchange them (e.g. torch.distributed.all_gather_object) and pass all world x 3 handles, rank
+ * major, plus each rank's CUDA device ordinal to oprl_comm_connect.  Afterwards oprl_update(...,
+ * OPRL_SEG_ALL) performs the whole data-parallel update. */
+int oprl_comm_init(oprl_engine* e, int rank, int world, void* handles_out);
+int oprl_comm_connect(oprl_engine* e, const void* all_handles, const int* device_of_rank);
+
 /* Engine-less sample(): plain row-major gather of B host-chosen (episode, step) pairs out of
  * replay storage shaped as in oprl_buffer_bind (episodic_buffer.py:127-133); next_state is the
  * adjacent row states[ep, step + 1].  ep_step_dev: device scratch of 2*B ints. */

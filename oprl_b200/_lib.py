@@ -62,6 +62,8 @@ _SIGNATURES = {
     "oprl_stream": (_P, [_P]),
     "oprl_engine_set_stream": (C.c_int, [_P, _P]),
     "oprl_engine_set_world_size": (C.c_int, [_P, C.c_int]),
+    "oprl_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "oprl_comm_connect": (C.c_int, [_P, _P, _P]),
     "oprl_update_launches": (C.c_int, [_P, C.c_int, C.c_int]),
     "oprl_profile": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "oprl_gather_rows": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,

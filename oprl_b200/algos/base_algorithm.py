@@ -89,7 +89,7 @@ class OffPolicyAlgorithm:
         buffer.attach_engine(self.engine)
 
     # --------------------------------------------------------------- data parallel
-    def enable_data_parallel(self, group=None) -> None:
+    def enable_data_parallel(self, group=None, fused: bool = True) -> None:
         """Replicated learners (one process per GPU, identical parameters and replay content):
         every rank updates on its own B rows of a world_size * B minibatch and the flat gradient
         arenas are all-reduced (NCCL over NVLink) before each Adam step, so all replicas stay
@@ -105,11 +105,21 @@ class OffPolicyAlgorithm:
                 if grp[key] is not None:
                     dist.broadcast(grp[key], src=src, group=self._dp_group)
         self.engine.mark_params_dirty()
+        if fused and os.environ.get("OPRL_B200_DP_NCCL", "0") != "1":
+            # native path: peers' gradient arenas mapped over NVLink (CUDA IPC), the Adam kernel
+            # sums them itself -- no NCCL launch between the segments
+            rank = dist.get_rank(self._dp_group)
+            world = dist.get_world_size(self._dp_group)
+            mine = (self.engine.comm_init(rank, world), self.engine.device.index)
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine, group=self._dp_group)
+            self.engine.comm_connect([h for h, _ in gathered], [d for _, d in gathered])
+            dist.barrier(group=self._dp_group)
 
     def _run_update(self, actor_step: bool) -> None:
         eng = self.engine
         group = getattr(self, "_dp_group", None)
-        if group is None:
+        if group is None or eng.fused_comm:
             eng.update(actor_step=actor_step)
             return
         import torch.distributed as dist

@@ -158,6 +158,17 @@ struct oprl_engine {
   int stage_next = 0;
   int ext_mask = 0;
   int cur_B = 0;
+  // fused NVLink gradient all-reduce (oprl_comm_*)
+  struct Comm {
+    int world = 1, rank = 0;
+    bool connected = false;
+    float* grad[2] = {nullptr, nullptr};       // own, cudaMalloc'ed (IPC-exportable)
+    unsigned int* flags = nullptr;              // own flag block
+    unsigned int* done_counter = nullptr;       // [2]
+    float* peer_grad[2][kMaxRanks] = {};
+    unsigned int* peer_flags[kMaxRanks] = {};
+    std::vector<void*> opened;
+  } comm;
 
   float* alloc_floats(size_t n) {
     void* p = nullptr;
@@ -251,6 +262,7 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
       w.cols = ly.in;
       w.split = ly.split; w.off_lo = ly.off_lo; w.off_hi = ly.off_hi;
       w.opt = opt;
+      w.goff = static_cast<int>(ly.w_off);
       segs.push_back(w);
       AdamSeg b;
       memset(&b, 0, sizeof(b));
@@ -263,6 +275,7 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
       b.rows = 1;
       b.cols = ly.out;
       b.opt = opt;
+      b.goff = static_cast<int>(ly.b_off);
       segs.push_back(b);
       g.max_seg = std::max(g.max_seg, static_cast<size_t>(w.n));
     }
@@ -293,11 +306,29 @@ static AdamHyper make_hyper(const oprl_cfg& c) {
   return hp;
 }
 
-static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st) {
-  const int bx = static_cast<int>(std::min<size_t>((g.max_seg + kAdamThreads * 2 - 1) / (kAdamThreads * 2), 64));
+static CommArgs make_comm(oprl_engine* e, int group, bool exit_barrier) {
+  CommArgs cm;
+  memset(&cm, 0, sizeof(cm));
+  cm.world = e->comm.connected ? e->comm.world : 1;
+  cm.rank = e->comm.rank;
+  cm.group = group;
+  cm.exit_barrier = exit_barrier ? 1 : 0;
+  for (int r = 0; r < cm.world && e->comm.connected; ++r) {
+    cm.peer_grad[r] = e->comm.peer_grad[group][r];
+    cm.peer_flags[r] = e->comm.peer_flags[r];
+  }
+  cm.done_counter = e->comm.done_counter ? e->comm.done_counter + group : nullptr;
+  return cm;
+}
+
+static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, bool exit_barrier = false) {
+  // one element per thread (a single load -> compute -> store round trip, which matters most when the
+  // gradient loads cross NVLink); very large tensors loop
+  const int bx = static_cast<int>(std::min<size_t>((g.max_seg + kAdamThreads - 1) / kAdamThreads, 2048));
   dim3 grid(std::max(bx, 1), g.n_segs);
+  const int group = (&g == &e->grp[OPRL_NET_ACTOR]) ? 0 : 1;
   launch_k(adam_kernel, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs), make_hyper(e->cfg),
-           static_cast<const DevState*>(e->d_state), mode);
+           static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier));
 }
 
 // --------------------------------------------------------------- program builder
@@ -619,7 +650,8 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   {
     const bool polyak = td3 ? do_actor : true;  // td3.py:81-84 ; ddpg.py:72-77
     const int mode = 1 | 4 | (polyak ? (2 | 8) : 0);
-    b.stage(s).add_simt([e, &gc, mode](cudaStream_t sm) { launch_adam(e, gc, mode, sm); });
+    const bool exit_barrier = !do_actor;  // no actor handshake follows to fence the critic gradients
+    b.stage(s).add_simt([e, &gc, mode, exit_barrier](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier); });
     ++s;
   }
   if (do_actor) {
@@ -894,6 +926,8 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   al.lr = c.lr_alpha;
   al.alpha_x = ga.grad + ga.floats;
   al.add = tqc ? 0.f : static_cast<float>(c.target_entropy);
+  al.world = e->comm.connected ? e->comm.world : 1;
+  for (int r = 0; r < al.world && e->comm.connected; ++r) al.peer_x[r] = e->comm.peer_grad[0][r] + ga.floats;
   b.stage(s).add_simt([e, &ga, al, st](cudaStream_t sm) {
     launch_adam(e, ga, 1 | 4, sm);
     launch_k(alpha_step_kernel, dim3(1), dim3(32), 0, sm, st, al);
@@ -1122,6 +1156,7 @@ void oprl_engine_destroy(oprl_engine* e) {
     for (auto& pv : kv.second->prog)
       for (int k = 0; k < 5; ++k)
         if (pv.second->graph[k]) cudaGraphExecDestroy(pv.second->graph[k]);
+  for (void* p : e->comm.opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->blocks) cudaFree(p);
   if (e->h_state) cudaFreeHost(e->h_state);
   if (e->h_flag) cudaFreeHost(e->h_flag);
@@ -1410,6 +1445,69 @@ int oprl_engine_set_world_size(oprl_engine* e, int world_size) {
     for (auto& kv : e->work) kv.second->prog.clear();  // loss scales are baked into the programs
   }
   return 0;
+}
+
+int oprl_comm_init(oprl_engine* e, int rank, int world, void* handles_out) {
+  if (!e || !handles_out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+    return fail(-1, "bad comm arguments (world <= %d)", kMaxRanks);
+  for (int k = 0; k < 2; ++k)
+    if (!e->grp[k].theta) return fail(-1, "bind the arenas before oprl_comm_init");
+  API_BEGIN
+  oprl_engine::Comm& cm = e->comm;
+  cm.world = world;
+  cm.rank = rank;
+  cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
+  for (int k = 0; k < 2; ++k) {
+    if (!cm.grad[k]) cm.grad[k] = e->alloc_floats(e->grp[k].floats + OPRL_GRAD_TAIL);
+    CU(cudaIpcGetMemHandle(&h[k], cm.grad[k]));
+  }
+  if (!cm.flags) {
+    cm.flags = reinterpret_cast<unsigned int*>(e->alloc_floats(2 * 2 * kMaxRanks));
+    cm.done_counter = reinterpret_cast<unsigned int*>(e->alloc_floats(2));
+  }
+  CU(cudaIpcGetMemHandle(&h[2], cm.flags));
+  CU(cudaStreamSynchronize(e->stream));  // buffers zeroed before anybody maps them
+  return 0;
+  API_END
+}
+
+int oprl_comm_connect(oprl_engine* e, const void* all_handles, const int* device_of_rank) {
+  if (!e || !all_handles || !device_of_rank) return fail(-1, "null argument");
+  oprl_engine::Comm& cm = e->comm;
+  if (!cm.grad[0]) return fail(-1, "oprl_comm_init first");
+  API_BEGIN
+  const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(all_handles);
+  for (int r = 0; r < cm.world; ++r) {
+    if (r == cm.rank) {
+      cm.peer_grad[0][r] = cm.grad[0];
+      cm.peer_grad[1][r] = cm.grad[1];
+      cm.peer_flags[r] = cm.flags;
+      continue;
+    }
+    if (device_of_rank[r] != e->cfg.device) {
+      const cudaError_t pe = cudaDeviceEnablePeerAccess(device_of_rank[r], 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) throw CudaError{pe, "cudaDeviceEnablePeerAccess", __LINE__};
+      cudaGetLastError();
+    }
+    void* p[3];
+    for (int k = 0; k < 3; ++k) {
+      CU(cudaIpcOpenMemHandle(&p[k], h[r * 3 + k], cudaIpcMemLazyEnablePeerAccess));
+      cm.opened.push_back(p[k]);
+    }
+    cm.peer_grad[0][r] = static_cast<float*>(p[0]);
+    cm.peer_grad[1][r] = static_cast<float*>(p[1]);
+    cm.peer_flags[r] = static_cast<unsigned int*>(p[2]);
+  }
+  // gradients are produced straight into the exported arenas from now on
+  for (int k = 0; k < 2; ++k) {
+    e->grp[k].grad = cm.grad[k];
+    upload_segs(e, e->grp[k], k);
+  }
+  cm.connected = true;
+  e->cfg.world_size = cm.world;
+  for (auto& kv : e->work) kv.second->prog.clear();
+  return 0;
+  API_END
 }
 
 int oprl_gather_rows(const float* states, const float* actions, const float* rewards,

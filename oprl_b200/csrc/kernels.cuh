@@ -348,7 +348,52 @@ struct AdamSeg {
   int n, rows, cols;     // row-major [rows x cols]
   int split, off_lo, off_hi;  // tiled col = j < split ? j + off_lo : j - split + off_hi
   int opt;                    // 0 actor, 1 critic
+  int goff;                   // element offset of this tensor inside the group's gradient arena
 };
+
+// ---- fused gradient all-reduce (data-parallel learners on one NVLink domain) ----------------
+// Every rank maps every other rank's gradient arena and flag block (CUDA IPC).  The Adam kernel
+// itself performs the reduction: after a flag handshake ("my gradients of step t are complete")
+// each thread sums the same element from all ranks IN RANK ORDER -- so all replicas compute
+// bit-identical sums -- and goes straight on to the Adam update.  No NCCL launch, no extra pass
+// over the gradients, no parameter broadcast.
+constexpr int kMaxRanks = 8;
+struct CommArgs {
+  int world, rank;  // world <= 1: disabled
+  int group;        // 0 actor, 1 critic: which flag rows to use
+  int exit_barrier; // also wait until every peer has finished reading this rank's gradients
+  const float* peer_grad[kMaxRanks];    // this group's gradient arena on every rank (own included)
+  unsigned int* peer_flags[kMaxRanks];  // every rank's flag block: [2 groups][2 phases][kMaxRanks]
+  unsigned int* done_counter;           // local: blocks of this launch that finished reading
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// phase 0: "gradients of step `epoch` are complete here"; phase 1: "I have read everybody's".
+__device__ __forceinline__ void comm_signal(const CommArgs& cm, int phase, unsigned int epoch) {
+  __threadfence_system();
+  for (int r = 0; r < cm.world; ++r)
+    st_release_sys(cm.peer_flags[r] + (cm.group * 2 + phase) * kMaxRanks + cm.rank, epoch);
+}
+__device__ __forceinline__ void comm_wait(const CommArgs& cm, int phase, unsigned int epoch) {
+  const unsigned int* mine = cm.peer_flags[cm.rank] + (cm.group * 2 + phase) * kMaxRanks;
+  for (int r = 0; r < cm.world; ++r) {
+    unsigned int spins = 0;
+    // steps only grow: ">=" tolerates a peer that is already one handshake ahead
+    while (static_cast<int>(ld_acquire_sys(mine + r) - epoch) < 0) {
+      if (++spins > (1u << 28)) {
+        printf("oprl: rank %d timed out waiting for rank %d (group %d phase %d epoch %u)\n", cm.rank, r, cm.group,
+               phase, epoch);
+        __trap();
+      }
+    }
+  }
+}
 struct AdamHyper {  // python doubles of torch.optim.Adam, rounded to fp32 where torch does
   double lr[2];
   double beta1, beta2;
@@ -359,10 +404,19 @@ struct AdamHyper {  // python doubles of torch.optim.Adam, rounded to fp32 where
 constexpr int kAdamThreads = 256;
 // mode: bit0 = Adam step, bit1 = Polyak, bit2 = (re)tile online weights, bit3 = tile targets
 __global__ void __launch_bounds__(kAdamThreads)
-    adam_kernel(const AdamSeg* segs, AdamHyper hp, const DevState* st, int mode) {
+    adam_kernel(const AdamSeg* segs, AdamHyper hp, const DevState* st, int mode, const __grid_constant__ CommArgs cm) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   const AdamSeg sg = segs[blockIdx.y];
+  const bool reduce = cm.world > 1 && (mode & 1);
+  const unsigned int epoch = static_cast<unsigned int>(st->step[sg.opt]);
+  if (reduce) {
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0 && blockIdx.y == 0) comm_signal(cm, 0, epoch);
+      comm_wait(cm, 0, epoch);
+    }
+    __syncthreads();
+  }
   const float s_step_size = st->step_size[sg.opt];
   const float s_bc2_sqrt = st->bc2_sqrt[sg.opt];
   const float w1 = hp.w1;
@@ -370,7 +424,13 @@ __global__ void __launch_bounds__(kAdamThreads)
   for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.n; i += gridDim.x * kAdamThreads) {
     float p = sg.theta[i];
     if (mode & 1) {
-      const float g = sg.grad[i];
+      float g;
+      if (reduce) {
+        g = 0.f;
+        for (int r = 0; r < cm.world; ++r) g += cm.peer_grad[r][sg.goff + i];
+      } else {
+        g = sg.grad[i];
+      }
       float m = sg.m[i];
       float v = sg.v[i];
       m = fmaf(w1, g - m, m);                              // exp_avg.lerp_(grad, 1 - beta1)
@@ -398,6 +458,19 @@ __global__ void __launch_bounds__(kAdamThreads)
         if (sg.wt) sg.wt[ct_index(sg.wt_rows, c, r)] = p;
       }
       if (sg.tw && (mode & 8)) sg.tw[ct_index(sg.w_rows, r, c)] = tp;
+    }
+  }
+  if (reduce && cm.exit_barrier) {
+    // nobody overwrites gradients another rank may still be reading: the last block of this launch
+    // announces "done reading" and waits for the same from every peer
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      if (atomicAdd(cm.done_counter, 1u) == gridDim.x * gridDim.y - 1) {
+        *cm.done_counter = 0u;
+        comm_signal(cm, 1, epoch);
+        comm_wait(cm, 1, epoch);
+      }
     }
   }
 }

@@ -186,9 +186,17 @@ struct AlphaStep {
   double lr;
   const float* alpha_x;
   float add;  // SAC: target_entropy ; TQC: 0
+  int world;  // data-parallel learners: sum the per-rank shares (runs after the actor Adam's handshake)
+  const float* peer_x[kMaxRanks];
 };
 __device__ __forceinline__ void alpha_step(DevState* st, const AlphaStep& as) {
-  const double x = static_cast<double>(as.add + *as.alpha_x);
+  float share = 0.f;
+  if (as.world > 1) {
+    for (int r = 0; r < as.world; ++r) share += *as.peer_x[r];
+  } else {
+    share = *as.alpha_x;
+  }
+  const double x = static_cast<double>(as.add + share);
   const double g = -x;
   st->scalars[SC_ALPHA_LOSS] = static_cast<float>(-st->log_alpha * x);
   const int t = st->step[2] + 1;

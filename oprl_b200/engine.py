@@ -91,6 +91,7 @@ class UpdateEngine:
         self._params_dirty = True
         self._keep = []  # tensors the engine holds pointers into
         self.last_batch_token = None
+        self.fused_comm = False
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -215,6 +216,18 @@ class UpdateEngine:
 
     def set_world_size(self, world_size: int):
         L.check(self._lib.oprl_engine_set_world_size(self._h, int(world_size)))
+
+    def comm_init(self, rank: int, world: int) -> bytes:
+        """This rank's three CUDA-IPC handles (actor grads, critic grads, flags)."""
+        buf = C.create_string_buffer(3 * 64)
+        L.check(self._lib.oprl_comm_init(self._h, rank, world, buf))
+        return buf.raw
+
+    def comm_connect(self, handles: list, devices: list):
+        blob = b"".join(handles)
+        dev = (C.c_int * len(devices))(*devices)
+        L.check(self._lib.oprl_comm_connect(self._h, blob, dev))
+        self.fused_comm = True
 
     def launches(self, B, actor_step=True):
         return L.check(self._lib.oprl_update_launches(self._h, B, L.UPDATE_ACTOR if actor_step else 0))

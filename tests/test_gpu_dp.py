@@ -13,7 +13,7 @@ from tests.util import fixture_batch, load_case, oracle_from_fixture
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, name, out):
+def _worker(rank, world, port, name, fused, out):
     import torch.distributed as dist
 
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -25,7 +25,8 @@ def _worker(rank, world, port, name, out):
     orc = oracle_from_fixture(fx)
     algo = make_algo(fx, device=f"cuda:{rank}")
     load_initial(algo, orc)
-    algo.enable_data_parallel()
+    algo.enable_data_parallel(fused=fused)
+    assert algo.engine.fused_comm == fused
     batch = fixture_batch(fx, 0)
     B = batch[0].shape[0]
     lo, hi = rank * B // world, (rank + 1) * B // world
@@ -40,13 +41,14 @@ def _worker(rank, world, port, name, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_learners_reproduce_the_full_batch_update():
+@pytest.mark.parametrize("fused", [True, False], ids=["fused-nvlink-adam", "nccl-allreduce"])
+def test_two_learners_reproduce_the_full_batch_update(fused):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, "ddpg", out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, "ddpg", fused, out)) for r in range(2)]
     for p in procs:
         p.start()
     l2, losses = out.get(timeout=300)
@@ -54,7 +56,7 @@ def test_two_learners_reproduce_the_full_batch_update():
         p.join(timeout=60)
         assert p.exitcode == 0
     fx = load_case("ddpg")
-    print(f"dp2 ddpg: param L2 after 1 update = {l2:.3e}, losses {losses}")
+    print(f"dp2 ddpg fused={fused}: param L2 after 1 update = {l2:.3e}, losses {losses}")
     assert l2 <= 1e-5
     assert abs(losses[0] - float(fx["scalar0_critic_loss"])) <= 1e-4
     assert abs(losses[1] - float(fx["scalar0_actor_loss"])) <= 1e-4
