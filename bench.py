@@ -231,6 +231,7 @@ def run_engine(args):
 
         # ---- roofline of the dominant kernel: only the update's GEMM launches, replayed
         gemm_ms, gemm_launches = eng.time_gemm_only(B, iters=200)
+        simt_ms = eng.time_simt_only(B, iters=200)
         gather_us = eng.time_gather_only(B, iters=200)
 
     t_ms = torch.tensor([ms, e2e_ms, api_ms], device=device, dtype=torch.float64)
@@ -275,6 +276,7 @@ def run_engine(args):
                      "frac": achieved_tf / pk["tf"], "traffic": None,
                      "kernel": "oprl::gemm_kernel<false> (grouped 128x32 tcgen05 3xTF32 tiles)",
                      "launches_per_update": gemm_launches, "gemm_us_per_update": gemm_ms * 1e3,
+                     "simt_us_per_update": simt_ms * 1e3,
                      "algorithmic_mflop_per_update": ALGO_MFLOP[args.algo], "peak_source": pk["src"],
                      "note": "latency-bound by construction: 365 MFLOP/update is 0.26 us of tensor time; tf32 peak is 1/2 of bf16 and 3xTF32 needs 3 passes"},
         "roofline_gather": {"bound": "hbm", "achieved": gather_bytes / (gather_us * 1e-6) / 1e9, "peak": pk["hbm"],

@@ -91,7 +91,9 @@ struct Group {  // actor (1 net) or critic (n_critics nets) -- one flat arena, o
   float *theta = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr, *target = nullptr;
   bool want_target = false;
   AdamSeg* d_segs = nullptr;
+  int2* d_blocks = nullptr;  // block -> (segment, first element)
   int n_segs = 0;
+  int n_blocks = 0;
   size_t max_seg = 0;
 };
 
@@ -116,7 +118,7 @@ struct Program {
   int B = 0, Bp = 0;
   int flags = 0;
   std::vector<Stage> stages;
-  cudaGraphExec_t graph[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] segments, [3] all, [4] GEMM launches only (profiling)
+  cudaGraphExec_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] segments, [3] all, [4] GEMM launches only, [5] SIMT launches only (profiling)
   int n_gemm_launches = 0;
   int n_launches = 0;
 };
@@ -286,6 +288,17 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
     g.d_segs = static_cast<AdamSeg*>(p);
   }
   g.n_segs = static_cast<int>(segs.size());
+  std::vector<int2> blocks;
+  for (int si = 0; si < g.n_segs; ++si)
+    for (int off = 0; off < segs[si].n; off += kAdamThreads) blocks.push_back(make_int2(si, off));
+  if (!g.d_blocks) {
+    void* p;
+    CU(cudaMalloc(&p, blocks.size() * sizeof(int2)));
+    e->blocks.push_back(p);
+    g.d_blocks = static_cast<int2*>(p);
+  }
+  g.n_blocks = static_cast<int>(blocks.size());
+  CU(cudaMemcpyAsync(g.d_blocks, blocks.data(), blocks.size() * sizeof(int2), cudaMemcpyHostToDevice, e->stream));
   CU(cudaMemcpyAsync(g.d_segs, segs.data(), segs.size() * sizeof(AdamSeg), cudaMemcpyHostToDevice,
                      e->stream));
   CU(cudaStreamSynchronize(e->stream));
@@ -322,12 +335,12 @@ static CommArgs make_comm(oprl_engine* e, int group, bool exit_barrier) {
 }
 
 static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, bool exit_barrier = false) {
-  // one element per thread (a single load -> compute -> store round trip, which matters most when the
-  // gradient loads cross NVLink); very large tensors loop
-  const int bx = static_cast<int>(std::min<size_t>((g.max_seg + kAdamThreads - 1) / kAdamThreads, 2048));
-  dim3 grid(std::max(bx, 1), g.n_segs);
+  // one element per thread: a single load -> compute -> store round trip (which matters most when
+  // the gradient loads cross NVLink)
+  dim3 grid(g.n_blocks);
   const int group = (&g == &e->grp[OPRL_NET_ACTOR]) ? 0 : 1;
-  launch_k(adam_kernel, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs), make_hyper(e->cfg),
+  launch_k(adam_kernel, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs),
+           static_cast<const int2*>(g.d_blocks), make_hyper(e->cfg),
            static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier));
 }
 
@@ -959,11 +972,12 @@ static void launch_gemm_ops(oprl_engine* e, const std::vector<GemmOp>& ops, cuda
   }
 }
 
-static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, bool gemm_only = false) {
+static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, bool gemm_only = false,
+                      bool simt_only = false) {
   int n = 0;
   for (auto& sg : p->stages) {
     if (segment >= 0 && sg.segment != segment) continue;
-    if (!sg.ops.empty()) {
+    if (!sg.ops.empty() && !simt_only) {
       launch_gemm_ops(e, sg.ops, st);
       n += static_cast<int>((sg.ops.size() + kMaxOps - 1) / kMaxOps);
     }
@@ -989,13 +1003,13 @@ static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
   else build_sac_tqc(e, w, p.get());
   CU(cudaStreamSynchronize(e->stream));  // workspace memsets / constant uploads done
   // capture: one graph per segment + one for the whole update
-  for (int k = 0; k < 5; ++k) {
+  for (int k = 0; k < 6; ++k) {
     const int segment = (k >= 3) ? -1 : k;
     cudaGraph_t g = nullptr;
     CU(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
     int n = 0;
     try {
-      n = run_stages(e, p.get(), segment, e->own_stream, k == 4);
+      n = run_stages(e, p.get(), segment, e->own_stream, k == 4, k == 5);
     } catch (...) {
       cudaStreamEndCapture(e->own_stream, &g);
       if (g) cudaGraphDestroy(g);
@@ -1154,7 +1168,7 @@ void oprl_engine_destroy(oprl_engine* e) {
   cudaStreamSynchronize(e->stream);
   for (auto& kv : e->work)
     for (auto& pv : kv.second->prog)
-      for (int k = 0; k < 5; ++k)
+      for (int k = 0; k < 6; ++k)
         if (pv.second->graph[k]) cudaGraphExecDestroy(pv.second->graph[k]);
   for (void* p : e->comm.opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->blocks) cudaFree(p);
@@ -1540,8 +1554,8 @@ int oprl_update_launches(oprl_engine* e, int B, int flags) {
   API_END
 }
 
-/* what = 0: replay only the GEMM launches of one update `iters` times; what = 1: the gather
- * (device-side index draw) `iters` times.  Timed with CUDA events on the launch stream. */
+/* what = 0: replay only the GEMM launches of one update `iters` times; what = 2: only its SIMT
+ * launches; what = 1: the gather (device-side index draw) `iters` times.  Timed with CUDA events on the launch stream. */
 int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* ms_total, int* launches_per_iter) {
   if (!e || B <= 0 || iters <= 0 || !ms_total) return fail(-1, "bad argument");
   API_BEGIN
@@ -1551,8 +1565,9 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
   auto body = [&]() -> int {
-    if (what == 0) {
-      if (p->graph[4]) CU(cudaGraphLaunch(p->graph[4], e->stream));
+    if (what == 0 || what == 2) {
+      cudaGraphExec_t ge = p->graph[what == 0 ? 4 : 5];
+      if (ge) CU(cudaGraphLaunch(ge, e->stream));
       return 0;
     }
     return oprl_sample(e, nullptr, B);

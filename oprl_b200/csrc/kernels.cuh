@@ -404,15 +404,19 @@ struct AdamHyper {  // python doubles of torch.optim.Adam, rounded to fp32 where
 constexpr int kAdamThreads = 256;
 // mode: bit0 = Adam step, bit1 = Polyak, bit2 = (re)tile online weights, bit3 = tile targets
 __global__ void __launch_bounds__(kAdamThreads)
-    adam_kernel(const AdamSeg* segs, AdamHyper hp, const DevState* st, int mode, const __grid_constant__ CommArgs cm) {
+    adam_kernel(const AdamSeg* segs, const int2* blocks, AdamHyper hp, const DevState* st, int mode,
+                const __grid_constant__ CommArgs cm) {
   ptx::pdl_trigger();
+  // block -> (tensor, first element): one block per 256 consecutive elements of one tensor, so the
+  // grid holds no idle blocks (a [6] bias does not get the grid width of a [256 x 256] weight)
+  const int2 bt = blocks[blockIdx.x];
   ptx::pdl_wait();
-  const AdamSeg sg = segs[blockIdx.y];
+  const AdamSeg sg = segs[bt.x];
   const bool reduce = cm.world > 1 && (mode & 1);
   const unsigned int epoch = static_cast<unsigned int>(st->step[sg.opt]);
   if (reduce) {
     if (threadIdx.x == 0) {
-      if (blockIdx.x == 0 && blockIdx.y == 0) comm_signal(cm, 0, epoch);
+      if (blockIdx.x == 0) comm_signal(cm, 0, epoch);
       comm_wait(cm, 0, epoch);
     }
     __syncthreads();
@@ -421,7 +425,9 @@ __global__ void __launch_bounds__(kAdamThreads)
   const float s_bc2_sqrt = st->bc2_sqrt[sg.opt];
   const float w1 = hp.w1;
   const float w2 = hp.w2;
-  for (int i = blockIdx.x * kAdamThreads + threadIdx.x; i < sg.n; i += gridDim.x * kAdamThreads) {
+  {
+    const int i = bt.y + threadIdx.x;
+    if (i < sg.n) {
     float p = sg.theta[i];
     if (mode & 1) {
       float g;
@@ -459,6 +465,7 @@ __global__ void __launch_bounds__(kAdamThreads)
       }
       if (sg.tw && (mode & 8)) sg.tw[ct_index(sg.w_rows, r, c)] = tp;
     }
+    }
   }
   if (reduce && cm.exit_barrier) {
     // nobody overwrites gradients another rank may still be reading: the last block of this launch
@@ -466,7 +473,7 @@ __global__ void __launch_bounds__(kAdamThreads)
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
-      if (atomicAdd(cm.done_counter, 1u) == gridDim.x * gridDim.y - 1) {
+      if (atomicAdd(cm.done_counter, 1u) == gridDim.x - 1) {
         *cm.done_counter = 0u;
         comm_signal(cm, 1, epoch);
         comm_wait(cm, 1, epoch);

@@ -365,6 +365,25 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
   const int lane = n & 31, warp = n >> 5, nwarps = blockDim.x >> 5;
   const int m0 = blockIdx.x * kHeadRows;
   const bool live = n < a.H;
+  // Nothing in this kernel reads the step counters / tick, and everything that consumed the old
+  // values ran in earlier launches: advance them first, off the critical tail.
+  if (a.mode == 0 && blockIdx.x == 0 && n == 0) bump_counters(st, a.bump_actor);
+  // per-row inputs of the loss, fetched now so that their latency overlaps the dot products
+  float rr[kHeadRows], dd[kHeadRows], lp[kHeadRows];
+#pragma unroll
+  for (int r = 0; r < kHeadRows; ++r) {
+    const int m = min(m0 + r, a.B - 1);
+    rr[r] = a.mode == 0 ? a.r[m] : 0.f;
+    dd[r] = a.mode == 0 ? a.d[m] : 0.f;
+    lp[r] = a.mode == 0 ? (a.logp2 ? a.logp2[m] : 0.f) : (a.logp ? a.logp[m] : 0.f);
+  }
+  float b3v[2] = {0.f, 0.f}, b3tv[2] = {0.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    if (i >= a.nq) break;
+    b3v[i] = a.b3[i][0];
+    if (a.mode == 0) b3tv[i] = a.b3t[i][0];
+  }
   // ---- phase 1: the dot products of this block's 8 rows
   float hv[2][kHeadRows];  // online hidden activations of this thread's unit (kept for phase 2)
   float w3v[2] = {0.f, 0.f};
@@ -419,12 +438,12 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
     if (m >= a.B) continue;
     float q[2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) q[i] = i < a.nq ? res[i * kHeadRows + r] + a.b3[i][0] : 0.f;
+    for (int i = 0; i < 2; ++i) q[i] = i < a.nq ? res[i * kHeadRows + r] + b3v[i] : 0.f;
     if (a.mode == 0) {
-      float qn = res[2 * kHeadRows + r] + a.b3t[0][0];
-      if (a.nq == 2) qn = fminf(qn, res[3 * kHeadRows + r] + a.b3t[1][0]);
-      if (a.logp2) qn = qn - alpha * a.logp2[m];
-      const float y = a.r[m] + ((1.0f - a.d[m]) * a.gamma) * qn;
+      float qn = res[2 * kHeadRows + r] + b3tv[0];
+      if (a.nq == 2) qn = fminf(qn, res[3 * kHeadRows + r] + b3tv[1]);
+      if (a.logp2) qn = qn - alpha * lp[r];
+      const float y = rr[r] + ((1.0f - dd[r]) * a.gamma) * qn;
       ysum += y;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
@@ -446,7 +465,7 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
         dq[0][r] = -a.inv_count;
         qsum += q[0];
       }
-      if (a.logp) lpsum += a.logp[m];
+      if (a.logp) lpsum += lp[r];
     }
   }
   // ---- phase 2: dz2 = dq w3^T (.) relu'(h2), column sums
@@ -490,19 +509,19 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
   __threadfence();
   if (a.mode == 0 && live) {
     for (int i = 0; i < a.nq; ++i) {
-      // loads batched eight blocks at a time (independent L2 round trips), adds in block order
+      // loads batched sixteen blocks at a time (independent L2 round trips), adds in block order
       float gw = 0.f, gb = 0.f;
-      for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 8) {
-        float tw[8], tb[8];
+      for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 16) {
+        float tw[16], tb[16];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 16; ++k) {
           const bool ok = b0 + k < gridDim.x;
           const float* p = a.part + static_cast<size_t>(ok ? b0 + k : 0) * W + i * 2 * a.H;
           tw[k] = ok ? __ldcg(p + n) : 0.f;
           tb[k] = ok ? __ldcg(p + a.H + n) : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 16; ++k) {
           gw += tw[k];
           gb += tb[k];
         }
@@ -527,7 +546,6 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
       st->scalars[SC_Q_ERR_MEAN] = t[3] * a.inv_count;
       a.gb3[0][0] = t[4];
       if (a.nq == 2) a.gb3[1][0] = t[5];
-      bump_counters(st, a.bump_actor);
     } else {
       const float mean_lp = t[6] * a.inv_count;
       st->scalars[SC_LOGPI_MEAN] = mean_lp;

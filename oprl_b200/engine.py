@@ -241,6 +241,14 @@ class UpdateEngine:
                                        C.byref(ms), C.byref(n)))
         return ms.value / iters, n.value
 
+    def time_simt_only(self, B, iters=200, actor_step=True):
+        """(ms per update spent in the update's non-GEMM launches, launches per update)."""
+        self._use_current_stream()
+        ms, n = C.c_float(), C.c_int()
+        L.check(self._lib.oprl_profile(self._h, B, L.UPDATE_ACTOR if actor_step else 0, 2, iters,
+                                       C.byref(ms), C.byref(n)))
+        return ms.value / iters
+
     def time_gather_only(self, B, iters=200):
         """Microseconds per gather launch (device-side index draw)."""
         self._use_current_stream()
