@@ -1,0 +1,127 @@
+"""GPU: size-independent properties at BASELINE.json's full sizes (1e6-transition replay, batch 256):
+bit-exact gather, run-to-run determinism, and the Adam / Polyak update rules checked in place."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+class NullLogger:
+    log_dir = "/tmp"
+
+    def log_scalar(self, *a, **k):
+        pass
+
+    def log_scalars(self, *a, **k):
+        pass
+
+
+def full_buffer(S, A, episodes=1000, seed=0):
+    from oprl_b200.buffers.episodic_buffer import EpisodicReplayBuffer
+
+    buf = EpisodicReplayBuffer(buffer_size_transitions=1_000_000, state_dim=S, action_dim=A).create()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    buf.states[:episodes, :1000].normal_(generator=g)
+    buf.actions[:episodes].uniform_(-1, 1, generator=g)
+    buf.rewards[:episodes].uniform_(0, 1, generator=g)
+    for e in range(episodes):
+        buf.ep_lens[e] = 1000
+    buf._number_transitions = episodes * 1000
+    buf._ep_pointer = 0
+    buf.episodes_counter = episodes
+    return buf
+
+
+@pytest.mark.parametrize("attached", [False, True])
+def test_gather_is_bit_exact_at_full_buffer_size(attached):
+    from oprl_b200.algos.ddpg import DDPG
+
+    S, A, B = 24, 6, 256
+    buf = full_buffer(S, A)
+    if attached:
+        algo = DDPG(logger=NullLogger(), state_dim=S, action_dim=A).create()
+        algo.attach_buffer(buf)
+    np.random.seed(3)
+    ep_step = buf.draw_indices(B)
+    # include the edges: first / last transition of the first / last episode
+    ep_step[:4] = [[0, 0], [0, 999], [999, 0], [999, 999]]
+    np.random.seed(3)
+    _ = np.random.randint(0, 1, 1)
+    out = buf._engine.sample(B, ep_step) if attached else buf.gather(ep_step)
+    ep = torch.from_numpy(ep_step[:, 0].astype(np.int64)).cuda()
+    st = torch.from_numpy(ep_step[:, 1].astype(np.int64)).cuda()
+    ref = (buf.states[ep, st], buf.actions[ep, st], buf.rewards[ep, st], buf.dones[ep, st], buf.states[ep, st + 1])
+    for got, want in zip(out, ref):
+        assert torch.equal(got, want)
+
+
+def make_pair(cls, **kw):
+    torch.manual_seed(0)
+    a = cls(logger=NullLogger(), state_dim=24, action_dim=6, **kw).create()
+    b = cls(logger=NullLogger(), state_dim=24, action_dim=6, **kw).create()
+    for grp in ("actor", "critic"):
+        for key in ("theta", "target"):
+            if a.engine.arena[grp][key] is not None:
+                b.engine.arena[grp][key].copy_(a.engine.arena[grp][key])
+    b.engine.mark_params_dirty()
+    return a, b
+
+
+@pytest.mark.parametrize("name", ["ddpg", "td3", "sac"])
+def test_device_resident_learner_is_deterministic(name):
+    from oprl_b200.algos.ddpg import DDPG
+    from oprl_b200.algos.sac import SAC
+    from oprl_b200.algos.td3 import TD3
+
+    cls, kw = dict(ddpg=(DDPG, {}), td3=(TD3, {}), sac=(SAC, dict(tune_alpha=True)))[name]
+    a, b = make_pair(cls, **kw)
+    buf = full_buffer(24, 6, episodes=100)
+    for algo in (a, b):
+        algo.attach_buffer(buf)
+        algo.engine.set_prefix(buf.ep_lens[:buf.episodes_counter])
+    for _ in range(40):
+        a.learner_step(256)
+    for _ in range(40):
+        b.learner_step(256)
+    torch.cuda.synchronize()
+    for grp in ("actor", "critic"):
+        for key in ("theta", "m", "v", "target"):
+            x, y = a.engine.arena[grp][key], b.engine.arena[grp][key]
+            if x is not None:
+                assert torch.equal(x, y), (grp, key)
+                assert torch.isfinite(x).all()
+    assert a.engine.state().log_alpha == b.engine.state().log_alpha
+    assert a.engine.state().tick == 40 and a.engine.state().step_critic == 40
+    assert a.engine.state().step_actor == (20 if name == "td3" else 40)
+
+
+def test_first_update_obeys_adam_and_polyak_rules_exactly():
+    """After one DDPG update at full size: m = lerp(0, g, 1-b1), v = (1-b2) g g, target = tau*theta +
+    (1-tau)*target_old, theta = theta_old - lr/(1-b1) * m / (sqrt(v)/sqrt(1-b2) + eps) -- evaluated with
+    torch's own fp32 operators on the engine's gradient arena (bit-exact for m, v, target)."""
+    from oprl_b200.algos.ddpg import DDPG
+
+    torch.manual_seed(1)
+    algo = DDPG(logger=NullLogger(), state_dim=24, action_dim=6).create()
+    buf = full_buffer(24, 6, episodes=100)
+    algo.attach_buffer(buf)
+    algo.engine.set_prefix(buf.ep_lens[:buf.episodes_counter])
+    ar = algo.engine.arena
+    before = {g: {k: v.clone() for k, v in a.items() if v is not None} for g, a in ar.items()}
+    algo.learner_step(256)
+    torch.cuda.synchronize()
+    for grp, lr in (("critic", 3e-4), ("actor", 3e-4)):
+        n = before[grp]["theta"].numel()
+        # the reference runs torch's CPU operators: evaluate the rule there (1 ulp slack for fma choices)
+        g = ar[grp]["grad"][:n].cpu()
+        m = torch.zeros_like(g).lerp_(g, 1 - 0.9)
+        v = torch.zeros_like(g).mul_(0.999).addcmul_(g, g, value=1 - 0.999)
+        torch.testing.assert_close(ar[grp]["m"].cpu(), m, rtol=1.3e-7, atol=0)
+        torch.testing.assert_close(ar[grp]["v"].cpu(), v, rtol=1.3e-7, atol=0)
+        denom = (v.sqrt() / (1 - 0.999) ** 0.5).add_(1e-8)
+        theta = before[grp]["theta"].cpu().addcdiv_(m, denom, value=-lr / (1 - 0.9))
+        assert (ar[grp]["theta"].cpu() - theta).abs().max().item() <= 1.6e-8  # 1 ulp at |theta| < 0.25
+        target = 5e-3 * ar[grp]["theta"].cpu() + (1 - 5e-3) * before[grp]["target"].cpu()
+        assert torch.equal(ar[grp]["target"].cpu(), target), grp
+        assert g.abs().max().item() > 0

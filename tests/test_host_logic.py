@@ -159,3 +159,27 @@ def test_data_parallel_gradient_equals_global_batch_gradient():
     ref = np.concatenate([g.reshape(-1).numpy() for g in orc.last_critic_grads])
     np.testing.assert_allclose(got, ref, rtol=0, atol=2e-7)
     np.testing.assert_allclose(ref, fx["first_critic_grad"], rtol=0, atol=1e-8)
+
+
+def test_compat_overlay_redirects_reference_imports():
+    import importlib
+    import sys
+
+    from oprl_b200 import compat
+
+    saved = {k: sys.modules.get(k) for k in compat.OVERLAY}
+    try:
+        names = compat.install()
+        assert set(names) == set(compat.OVERLAY)
+        from oprl.algos.ddpg import DDPG  # the reference's import line (configs/ddpg.py:4)
+        from oprl.buffers.episodic_buffer import EpisodicReplayBuffer
+
+        assert DDPG.__module__ == "oprl_b200.algos.ddpg"
+        assert EpisodicReplayBuffer.__module__ == "oprl_b200.buffers.episodic_buffer"
+        assert importlib.import_module("oprl.algos.tqc").TQC.__module__ == "oprl_b200.algos.tqc"
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
