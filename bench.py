@@ -42,6 +42,10 @@ WORKLOADS = {
 }
 # algorithmic MFLOP per update and gathered bytes per update
 ALGO_MFLOP = {"ddpg": 365.4, "td3": 413.5, "sac": 2738.4, "tqc": 8564.8}
+# dram__bytes_read.sum + dram__bytes_write.sum per gemm_kernel launch from the committed
+# `ncu --set full` capture (profiles/r1_ncu_gemm_kernel_summary.csv: 9.42 MB over the 14 launches of one
+# DDPG update, cold L2 as ncu replays it; in the live loop the operands are L2-resident)
+GEMM_DRAM_BYTES_PER_LAUNCH = {"ddpg": 673_207}
 L_EP = 1000
 
 
@@ -273,12 +277,13 @@ def run_engine(args):
         "gpu_launches": int(round(launches_per_update * args.steps)),
         "launches_per_update": launches_per_update,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / pk["tf"], "traffic": None,
+                     "frac": achieved_tf / pk["tf"], "traffic": GEMM_DRAM_BYTES_PER_LAUNCH.get(args.algo),
                      "kernel": "oprl::gemm_kernel<false> (grouped 128x32 tcgen05 3xTF32 tiles)",
                      "launches_per_update": gemm_launches, "gemm_us_per_update": gemm_ms * 1e3,
                      "simt_us_per_update": simt_ms * 1e3,
                      "algorithmic_mflop_per_update": ALGO_MFLOP[args.algo], "peak_source": pk["src"],
-                     "note": "latency-bound by construction: 365 MFLOP/update is 0.26 us of tensor time; tf32 peak is 1/2 of bf16 and 3xTF32 needs 3 passes"},
+                     "achieved_per_launch_note": "achieved = algorithmic FLOPs of one update / summed duration of its GEMM launches (CUDA events around a GEMM-only graph replay); traffic = DRAM bytes per launch under ncu (cold L2)",
+                     "note": "latency-bound by construction: %.1f MFLOP/update is %.2f us of tensor time at the measured peak; tf32 peak is 1/2 of bf16 and 3xTF32 needs 3 passes" % (ALGO_MFLOP[args.algo], ALGO_MFLOP[args.algo] * 1e6 / (pk["tf"] * 1e12) * 1e6)},
         "roofline_gather": {"bound": "hbm", "achieved": gather_bytes / (gather_us * 1e-6) / 1e9, "peak": pk["hbm"],
                             "unit": "GB/s", "frac": gather_bytes / (gather_us * 1e-6) / 1e9 / pk["hbm"],
                             "bytes_per_launch": gather_bytes, "us_per_launch": gather_us},
