@@ -183,3 +183,32 @@ def test_compat_overlay_redirects_reference_imports():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def test_in_node_queue_surface():
+    """distrib/queue.py:4-19 surface (push / pop -> bytes | None) on the broker-less transport."""
+    import pickle
+
+    from oprl_b200.distrib.queue import Queue, QueueServer
+
+    os.environ["OPRL_B200_QUEUE_PORT"] = str(_free_port())
+    try:
+        with QueueServer():
+            a, b = Queue("env_0"), Queue("env_0")
+            assert b.pop() is None
+            a.push(pickle.dumps([1, 2]))
+            assert pickle.loads(b.pop_wait(1.0)) == [1, 2]
+            assert b.pop_wait(0.05) is None
+            assert Queue("policy_0").pop() is None
+    finally:
+        del os.environ["OPRL_B200_QUEUE_PORT"]
+
+
+def test_config_records_match_reference_defaults():
+    from oprl_b200.runners.config import CommonParameters, DistribConfig
+
+    d = DistribConfig()
+    assert (d.batch_size, d.num_env_workers, d.episodes_per_worker, d.warmup_epochs, d.episode_length,
+            d.learner_num_waits, d.warmup_env_steps) == (128, 4, 100, 16, 1000, 10, 1000)
+    c = CommonParameters(state_dim=24, action_dim=6, num_steps=100)
+    assert (c.eval_every, c.estimate_q_every, c.log_every) == (2500, 5000, 2500)
