@@ -101,3 +101,23 @@ def test_fixture_parity(name):
     # rounding noise of zero flips a ReLU and with it the sign of a few near-zero Adam steps
     # (2*lr = 6e-4 each).  Strict bar when the fixture stayed clear of that, loose bound otherwise.
     assert l2 <= (PARAM_L2_TOL * K if margin >= 5e-7 else 5e-3)
+
+
+def test_host_batch_and_int64_done_match_the_device_path():
+    """update() takes what the reference's own test feeds it (tests/functional/test_rl_algos.py:25-31):
+    CPU tensors, an int64 `done`, next_state aliasing state -- through the pinned zero-copy load."""
+    fx = load_case("ddpg_b8")
+    results = []
+    for on_host in (False, True):
+        orc = oracle_from_fixture(fx)
+        algo = make_algo(fx)
+        load_initial(algo, orc)
+        s, a, r, d, _ = fixture_batch(fx, 0)
+        d = d.to(torch.int64)
+        batch = [s, a, r, d, s] if on_host else [x.cuda() for x in (s, a, r, d, s)]
+        for _ in range(3):
+            algo.update(*batch)
+        torch.cuda.synchronize()
+        results.append({g: ar["theta"].clone() for g, ar in algo.engine.arena.items()})
+    for g in results[0]:
+        assert torch.equal(results[0][g], results[1][g]), g

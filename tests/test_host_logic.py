@@ -212,3 +212,70 @@ def test_config_records_match_reference_defaults():
             d.learner_num_waits, d.warmup_env_steps) == (128, 4, 100, 16, 1000, 10, 1000)
     c = CommonParameters(state_dim=24, action_dim=6, num_steps=100)
     assert (c.eval_every, c.estimate_q_every, c.log_every) == (2500, 5000, 2500)
+
+
+class _FakeEngine:
+    """Records the call order of the python data-parallel wrapper (no GPU, no CUDA library)."""
+
+    def __init__(self):
+        self.calls = []
+        self.fused_comm = False
+        self.arena = {"actor": {"grad": torch.ones(4), "theta": torch.zeros(4), "target": None},
+                      "critic": {"grad": torch.ones(4) * 2, "theta": torch.zeros(4), "target": torch.zeros(4)}}
+
+    def update(self, actor_step=True, segment=-1):
+        self.calls.append(("update", actor_step, segment))
+
+    def set_world_size(self, n):
+        self.calls.append(("world", n))
+
+    def mark_params_dirty(self):
+        pass
+
+
+def _segment_worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oprl_b200.algos.base_algorithm import OffPolicyAlgorithm
+
+    algo = OffPolicyAlgorithm()
+    algo.engine = _FakeEngine()
+    algo.engine.arena["critic"]["theta"] += rank  # replicas start different: rank 0's values must win
+    algo.enable_data_parallel(fused=False)
+    algo._run_update(True)
+    algo._run_update(False)
+    if rank == 0:
+        out.put((algo.engine.calls, algo.engine.arena["critic"]["grad"].tolist(),
+                 algo.engine.arena["actor"]["grad"].tolist(), algo.engine.arena["critic"]["theta"].tolist()))
+    else:
+        out.put(("theta", algo.engine.arena["critic"]["theta"].tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nccl_style_wrapper_orders_segments_and_allreduces_over_gloo():
+    from oprl_b200._lib import SEG_ACTOR_STEP, SEG_CRITIC_GRAD, SEG_CRITIC_STEP_ACTOR_GRAD
+
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_segment_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [out.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    main = next(g for g in got if g[0] != "theta")
+    other = next(g for g in got if g[0] == "theta")
+    calls, cgrad, agrad, theta0 = main
+    assert calls == [("world", 2),
+                     ("update", True, SEG_CRITIC_GRAD), ("update", True, SEG_CRITIC_STEP_ACTOR_GRAD),
+                     ("update", True, SEG_ACTOR_STEP),
+                     ("update", False, SEG_CRITIC_GRAD), ("update", False, SEG_CRITIC_STEP_ACTOR_GRAD)]
+    assert cgrad == [8.0] * 4  # 2 -> all-reduce(sum) over 2 ranks -> 4 -> again in the second update -> 8
+    assert agrad == [2.0] * 4  # only the update with an actor step reduces the actor arena
+    assert other[1] == theta0 == [0.0] * 4  # parameters broadcast from rank 0
