@@ -233,6 +233,35 @@ def run_engine(args):
         barrier()
         api_ms = a0.elapsed_time(a1)
 
+        # ---- independent learners sharing this GPU (the reference's run_training(seeds=N) mode,
+        # runners/train.py:35-49): R engines, one stream each, driven round-robin from this thread.
+        # One update keeps at most ~48 of the 148 SMs busy, so several seeds overlap almost freely.
+        multi = None
+        if args.replicas > 1 and not dp:
+            algos = [algo] + [make_algo(args.algo, S, A, device) for _ in range(args.replicas - 1)]
+            streams = [stream] + [torch.cuda.Stream(device=device) for _ in range(args.replicas - 1)]
+            for a2 in algos[1:]:
+                a2.attach_buffer(buf)
+                a2.engine.set_prefix(buf.ep_lens[:buf.episodes_counter])
+
+            def round_robin(n):
+                for _ in range(n):
+                    for a2, s2 in zip(algos, streams):
+                        with torch.cuda.stream(s2):
+                            a2.learner_step(B)
+
+            round_robin(max(3, args.warmup // 2))
+            barrier()
+            t0 = time.perf_counter()
+            m_steps = max(50, min(args.steps, 1000))
+            round_robin(m_steps)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            multi = {"learners": args.replicas, "value": args.replicas * m_steps / dt, "unit": "updates/s (sum over independent learners on one GPU)",
+                     "what": "R independent seeds, one CUDA stream each, same replay storage; wall clock around the loop + synchronize"}
+            for a2 in algos[1:]:
+                a2.engine.close()
+
         # ---- roofline of the dominant kernel: only the update's GEMM launches, replayed
         gemm_ms, gemm_launches = eng.time_gemm_only(B, iters=200)
         simt_ms = eng.time_simt_only(B, iters=200)
@@ -289,6 +318,8 @@ def run_engine(args):
                             "bytes_per_launch": gather_bytes, "us_per_launch": gather_us},
         "clocks": clocks,
     }
+    if multi:
+        out["multi_learner"] = multi
     if rank == 0:
         if args.cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.algo, B, budget_s=12.0)
@@ -381,6 +412,8 @@ def main():
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--algo", default="ddpg", choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--replicas", type=int, default=1,
+                    help="also time R independent learners (seeds) sharing each GPU; reported separately")
     ap.add_argument("--mode", default="dp", choices=["dp", "replicas"],
                     help="N>1: data-parallel learners with gradient all-reduce (default) or independent replicas")
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
