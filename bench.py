@@ -11,7 +11,8 @@ Printed JSON (one line, rank 0):
   value      whole-job updates/s with everything resident in HBM (device-side index draw),
              CUDA events on the launching stream, max over ranks.
   e2e        the same metric through the public API with HOST minibatch tensors: every step copies
-             the pinned host batch H2D, runs algo.update(), and reads the critic loss back D2H.
+             the pinned host batch H2D, runs algo.update(), and reads the critic loss back D2H
+             (read-back pipelined one step deep; the blocking variant is reported beside it).
   roofline   tensor roofline of the grouped tcgen05 GEMM kernel: algorithmic FLOPs of one update
               / the time of the update's GEMM launches, timed live with CUDA
              events, against MEASURED_PEAKS.json (sustained bf16; the kernels run 3xTF32).
@@ -146,6 +147,9 @@ def fill_buffer(buf, episodes, seed):
     buf.episodes_counter = min(E + 1, buf._max_episodes)
 
 
+D2H_STATE_BYTES = 256  # sizeof(DevState): the block one scalar read-back copies
+
+
 def run_engine(args):
     import torch.distributed as dist
 
@@ -204,20 +208,31 @@ def run_engine(args):
         e2e_steps = max(50, min(args.steps, 1000))
         loss = 0.0
 
-        def e2e_loop(n):
+        def e2e_loop(n, depth):
+            # depth 0: read the loss of update t before launching update t+1 (host stalls every step);
+            # depth 1: the D2H read of update t is enqueued right behind it and consumed after
+            # update t+1 has been launched -- every step still does its H2D and its D2H.
             nonlocal loss
+            pending = []
             for _ in range(n):
                 algo.update(*host)
-                loss = eng.scalars()["critic_loss"]  # D2H read (synchronises)
+                pending.append(eng.scalars_async())
+                if len(pending) > depth:
+                    loss = pending.pop(0).result()["critic_loss"]
+            while pending:
+                loss = pending.pop(0).result()["critic_loss"]
 
-        e2e_loop(max(3, args.warmup // 4))
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        e2e_loop(e2e_steps)
-        e1.record(stream)
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
+        e2e_res = {}
+        for depth in (0, 1):
+            e2e_loop(max(3, args.warmup // 4), depth)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            e2e_loop(e2e_steps, depth)
+            e1.record(stream)
+            barrier()
+            e2e_res[depth] = e0.elapsed_time(e1)
+        e2e_sync_ms, e2e_ms = e2e_res[0], e2e_res[1]
 
         # ---- API loop (GPU-resident buffer, host index draw as the reference): sample(); update()
         np.random.seed(0)
@@ -267,10 +282,10 @@ def run_engine(args):
         simt_ms = eng.time_simt_only(B, iters=200)
         gather_us = eng.time_gather_only(B, iters=200)
 
-    t_ms = torch.tensor([ms, e2e_ms, api_ms], device=device, dtype=torch.float64)
+    t_ms = torch.tensor([ms, e2e_ms, api_ms, e2e_sync_ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, api_ms = [float(x) for x in t_ms.cpu()]
+    ms, e2e_ms, api_ms, e2e_sync_ms = [float(x) for x in t_ms.cpu()]
     launches_per_update = eng.launches(B, True) + 1  # + gather
     if td3:
         launches_per_update = (eng.launches(B, True) + eng.launches(B, False)) / 2 + 1
@@ -299,8 +314,11 @@ def run_engine(args):
                    "l2": "replay storage (128 MB) exceeds L2 and is sampled uniformly; parameters/activations (~3 MB) are L2-resident by construction of the learner loop, as in the reference loop",
                    "index_draw": "device Philox (value) / host numpy (api_loop)"},
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "updates/s",
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32 * 4, "steps": e2e_steps,
-                "last_critic_loss": loss},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": D2H_STATE_BYTES, "steps": e2e_steps,
+                "last_critic_loss": loss,
+                "what": "algo.update(*pinned_host_batch); engine.scalars_async() every step; the read-back of update t "
+                        "is consumed after update t+1 was launched (one step deep)",
+                "blocking_read_every_step": world * e2e_steps / (e2e_sync_ms * 1e-3)},
         "api_loop": {"value": world * api_steps / (api_ms * 1e-3), "unit": "updates/s",
                      "what": "buffer.sample(B) (host index draw, 2 KB H2D) ; algo.update(*batch) -- no per-step sync"},
         "gpu_launches": int(round(launches_per_update * args.steps)),

@@ -127,6 +127,13 @@ int oprl_step(oprl_engine* e, int B, int flags);
  * 0 critic_loss 1 actor_loss 2 alpha_loss 3 mean q 4 mean q_target 5 mean logpi
  * 6 mean (q - q_target) 7 alpha */
 int oprl_get_scalars(oprl_engine* e, float* out_host, int n);
+/* Pipelined form of the same read-back (the reference logs its losses with a blocking `.item()`
+ * per scalar, algos/td3.py:118-131, sac.py:112-150; a learner loop can instead consume the scalars
+ * of update t while update t+1 is already running): _enqueue appends a D2H copy of the scalars of
+ * everything launched so far to the stream and returns a ticket >= 0; _wait blocks on that copy
+ * only.  A ticket stays valid for 8 further enqueues. */
+int oprl_scalars_enqueue(oprl_engine* e);
+int oprl_scalars_wait(oprl_engine* e, int ticket, float* out_host, int n);
 int oprl_get_state(oprl_engine* e, oprl_state* out);
 int oprl_set_state(oprl_engine* e, const oprl_state* in);
 int oprl_sync(oprl_engine* e);

@@ -56,6 +56,8 @@ _SIGNATURES = {
     "oprl_update": (C.c_int, [_P, C.c_int, C.c_int]),
     "oprl_step": (C.c_int, [_P, C.c_int, C.c_int]),
     "oprl_get_scalars": (C.c_int, [_P, _P, C.c_int]),
+    "oprl_scalars_enqueue": (C.c_int, [_P]),
+    "oprl_scalars_wait": (C.c_int, [_P, C.c_int, _P, C.c_int]),
     "oprl_get_state": (C.c_int, [_P, C.POINTER(State)]),
     "oprl_set_state": (C.c_int, [_P, C.POINTER(State)]),
     "oprl_sync": (C.c_int, [_P]),

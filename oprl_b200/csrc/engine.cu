@@ -135,6 +135,11 @@ struct oprl_engine {
   Group grp[2];
   DevState* d_state = nullptr;
   DevState* h_state = nullptr;  // pinned mirror for reads
+  // pipelined scalar read-back (oprl_scalars_enqueue / oprl_scalars_wait)
+  static constexpr int kScalarSlots = 8;
+  DevState* h_ring = nullptr;  // pinned [kScalarSlots]
+  cudaEvent_t ring_done[kScalarSlots] = {};
+  long long ring_next = 0;
   // bump allocator over zero-initialised workspaces
   std::vector<void*> blocks;
   // replay + batch bindings
@@ -370,6 +375,11 @@ struct Builder {
     return o;
   }
   float* counters(int n) { return e->alloc_floats(n); }
+  // OPRL_B200_DW0_GEMM=1 keeps the layer-0 weight gradient as its own GEMM stage (cross-check / A-B)
+  static bool fuse_dw0() {
+    static const bool off = getenv("OPRL_B200_DW0_GEMM") && atoi(getenv("OPRL_B200_DW0_GEMM")) != 0;
+    return !off;
+  }
 
   // ---- forward of one net over input X (tiled [Bp x Kin]).  Hidden layers: bias+ReLU,
   // outputs kept tiled (and transposed when `train`).  The last layer is returned
@@ -423,9 +433,13 @@ struct Builder {
     const int nl = static_cast<int>(net.L.size());
     const int S = e->cfg.state_dim, A = e->cfg.action_dim, A4 = e->A4;
     int s = s0;
+    bool dw0_fused = false;
     for (int l = (l_start < 0 ? nl - 1 : l_start); l >= 0; --l, ++s) {
       const Layer& ly = net.L[l];
-      if (want_dw) {
+      if (want_dw && l == 0 && dw0_fused) {
+        // dW_0 was accumulated in the epilogue of the GEMM that produced dz_0 (GemmOp::dw0_*)
+        if (!dx_epilogue) return s;
+      } else if (want_dw) {
         // dW_l [out x in] = sum_b dzT(o, b) * hprevT(i, b)
         const TM& hprevT = (l == 0) ? XT : pass.hT[l - 1];
         GemmOp o = base_op(dzT, hprevT, pad128(ly.out), ly.Kp, Bp);
@@ -471,6 +485,30 @@ struct Builder {
         o.colsum_n = lp.out;
         o.colsum_out = grad + lp.b_off;
         o.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(lp.Np / kBN));
+        if (l == 1 && fuse_dw0()) {
+          // layer-0 weight gradient dz_0^T . X in this op's epilogue instead of a 2-CTA GEMM stage
+          o.dw0_x = w->X.p;
+          o.dw0_kp = lp.Kp;
+          o.dw0_part = e->alloc_floats(static_cast<size_t>(Bp / kBM) * lp.Np * lp.Kp);
+          o.dw0_out = grad + lp.w_off;
+          o.dw0_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(lp.Np / kBN));
+          o.dw0_ld = lp.in;
+          o.dw0_n = lp.out;
+          o.dw0_cols = lp.Kp;
+          // tiled input columns [action | pad4 | state] -> reference columns [state | action]
+          o.dw0_map_a = is_actor ? 0 : A;
+          o.dw0_map_a4 = A4;
+          o.dw0_map_s = S;
+          // the bias gradient db_0 rides in the same product through a pad column of X read as 1.0
+          o.dw0_ones = (A4 > A) ? A : (lp.Kp > A4 + S ? A4 + S : -1);
+          if (o.dw0_ones >= 0) {
+            o.dw0_bias_out = o.colsum_out;
+            o.colsum = nullptr;
+            o.colsum_out = nullptr;
+            o.colsum_cnt = nullptr;
+          }
+          dw0_fused = true;
+        }
       }
       stage(s).ops.push_back(o);
       dz = ndz;
@@ -1174,6 +1212,10 @@ void oprl_engine_destroy(oprl_engine* e) {
   for (void* p : e->blocks) cudaFree(p);
   if (e->h_state) cudaFreeHost(e->h_state);
   if (e->h_flag) cudaFreeHost(e->h_flag);
+  if (e->h_ring) {
+    cudaFreeHost(e->h_ring);
+    for (int i = 0; i < oprl_engine::kScalarSlots; ++i) cudaEventDestroy(e->ring_done[i]);
+  }
   for (int i = 0; i < oprl_engine::kHostSlots; ++i) {
     if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
     if (e->h_stage_done[i]) cudaEventDestroy(e->h_stage_done[i]);
@@ -1394,6 +1436,40 @@ int oprl_get_scalars(oprl_engine* e, float* out_host, int n) {
   e->h_state->scalars[SC_ALPHA] = e->h_state->alpha;
   memcpy(out_host, e->h_state->scalars, sizeof(float) * n);
   return 0;
+}
+
+int oprl_scalars_enqueue(oprl_engine* e) {
+  if (!e) return fail(-1, "null engine");
+  API_BEGIN
+  if (!e->h_ring) {
+    void* p;
+    CU(cudaMallocHost(&p, sizeof(DevState) * oprl_engine::kScalarSlots));
+    e->h_ring = static_cast<DevState*>(p);
+    for (int i = 0; i < oprl_engine::kScalarSlots; ++i)
+      CU(cudaEventCreateWithFlags(&e->ring_done[i], cudaEventDisableTiming));
+  }
+  const long long ticket = e->ring_next++;
+  const int slot = static_cast<int>(ticket % oprl_engine::kScalarSlots);
+  CU(cudaMemcpyAsync(&e->h_ring[slot], e->d_state, sizeof(DevState), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaEventRecord(e->ring_done[slot], e->stream));
+  return static_cast<int>(ticket & 0x3fffffff);
+  API_END
+}
+
+int oprl_scalars_wait(oprl_engine* e, int ticket, float* out_host, int n) {
+  if (!e || !out_host || n < 0 || n > 32) return fail(-1, "bad scalars call");
+  if (!e->h_ring) return fail(-1, "no scalar read-back was enqueued");
+  const long long newest = e->ring_next - 1;
+  const long long age = ((newest & 0x3fffffff) - ticket) & 0x3fffffff;
+  if (age >= oprl_engine::kScalarSlots) return fail(-1, "scalar ticket %d expired (ring of %d)", ticket, oprl_engine::kScalarSlots);
+  API_BEGIN
+  const int slot = static_cast<int>((newest - age) % oprl_engine::kScalarSlots);
+  CU(cudaEventSynchronize(e->ring_done[slot]));
+  DevState& s = e->h_ring[slot];
+  s.scalars[SC_ALPHA] = s.alpha;
+  memcpy(out_host, s.scalars, sizeof(float) * n);
+  return 0;
+  API_END
 }
 
 int oprl_get_state(oprl_engine* e, oprl_state* out) {

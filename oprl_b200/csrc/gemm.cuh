@@ -105,6 +105,21 @@ struct GemmOp {
   // [action | pad4 | state]):  n < map_a -> map_s + n ; n >= map_a4 -> n - map_a4.
   int map_a, map_a4, map_s;
   int colsum_ld, colsum_n;  // partial row stride; colsum_out gets columns n < colsum_n
+  // Fused layer-0 weight gradient: this op's output D [M x N] is dz_0 (batch x hidden) and
+  //   dW_0[n][k] = sum_m D(m, n) * X(m, k)          (X = the tiled layer-0 input, dw0_kp columns)
+  // is accumulated in the epilogue with fp32 FMAs (per-CTA partial over its 128 rows, fixed-order
+  // sum over the M tiles by the last CTA to arrive) and stored row-major at dw0_out[n * dw0_ld + col],
+  // col = the dw0_map_* column map, rows n < dw0_n.  Replaces a 2-CTA GEMM stage.
+  const float* dw0_x;
+  float* dw0_part;        // [M tiles][N tiles][32][dw0_kp]
+  float* dw0_out;
+  unsigned int* dw0_cnt;  // one arrival counter per N tile (self-resetting)
+  int dw0_kp, dw0_ld, dw0_n, dw0_cols;  // dw0_cols: tiled columns k < dw0_cols are candidates for the store
+  int dw0_map_a, dw0_map_a4, dw0_map_s;  // column map of the dW_0 store (same meaning as map_a/map_a4/map_s)
+  // bias gradient through the same product: tiled column dw0_ones (a pad column of X, < 0 = none) is
+  // read as 1.0, so P[n][dw0_ones] = sum_m D(m, n) = db_0[n]; it is stored to dw0_bias_out[n].
+  int dw0_ones;
+  float* dw0_bias_out;
   int passes;   // 3 = 3xTF32 (fp32-accurate), 1 = single tf32 pass
   int group;    // K chunks per hi*hi accumulator (gemm_finalize)
   int n_big;    // number of hi*hi accumulators, <= 7
@@ -304,16 +319,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // epilogue plan, read from the kernel parameters now (while the first copies are in flight)
     enum : uint32_t { F_BIAS = 1, F_RELU = 2, F_TANH = 4, F_MASK = 8, F_RS = 16, F_ADDM = 32, F_CLAMP = 64,
                       F_ALPHA = 128, F_MVALID = 256, F_NVALID = 512, F_T = 1024, F_TT = 2048, F_RM = 4096,
-                      F_COLSUM = 8192 };
+                      F_COLSUM = 8192, F_DW0 = 16384 };
     uint32_t fl = (o.bias ? F_BIAS : 0u) | (o.act == ACT_RELU ? F_RELU : 0u) | (o.act == ACT_TANH ? F_TANH : 0u) |
                   (o.mask ? F_MASK : 0u) | (o.rs ? F_RS : 0u) | (o.addm ? F_ADDM : 0u) |
                   (o.clamp > 0.f ? F_CLAMP : 0u) | (o.alpha != 1.f ? F_ALPHA : 0u) |
                   (o.m_valid > 0 ? F_MVALID : 0u) | (o.n_valid > 0 ? F_NVALID : 0u) | (o.t ? F_T : 0u) |
-                  (o.tt ? F_TT : 0u) | (o.rm ? F_RM : 0u) | (o.colsum ? F_COLSUM : 0u);
+                  (o.tt ? F_TT : 0u) | (o.rm ? F_RM : 0u) | (o.colsum ? F_COLSUM : 0u) | (o.dw0_out ? F_DW0 : 0u);
     float* out_t = o.t;
     float* out_tt = o.tt;
     int t_rows = o.t_rows, t_c0 = o.t_c0, t_n = o.t_n, tt_rows = o.tt_rows;
     pin(fl); pin_ptr(out_t); pin_ptr(out_tt); pin(t_rows); pin(t_c0); pin(t_n); pin(tt_rows);
+    // fused dW_0: the [128 x 32] tile of the layer-0 input this CTA's rows multiply (one contiguous
+    // 16 KB of the CT32 matrix) is fetched into registers now; its latency hides behind the K loop
+    float4 xr[kAFloats / 4 / 256];
+    if (fl & F_DW0) {
+      const float4* xg = reinterpret_cast<const float4*>(o.dw0_x + static_cast<size_t>(m0 >> 3) * 256);
+#pragma unroll
+      for (int i = 0; i < kAFloats / 4 / 256; ++i) xr[i] = __ldg(xg + (tid - 64) + i * 256);
+    }
     if (!kSimt) {
       // ---- K loop: split every landed fp32 chunk into tf32 hi / lo.  A: this thread's row
       // (32 k) goes registers -> TMEM (the MMA reads A from tensor memory, so shared memory only
@@ -533,7 +556,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       if (warp == 2) {
         const float s = cs_smem[lane] + cs_smem[32 + lane] + cs_smem[64 + lane] + cs_smem[96 + lane];
         o.colsum[static_cast<size_t>(mt) * o.colsum_ld + n0 + lane] = s;
-        if (o.colsum_out) {
+        if (o.colsum_out && !(fl & F_DW0)) {  // (with a fused dW_0 its arrival ticket serves both totals)
           // deterministic cross-CTA total: the last M tile to arrive sums all partials in order
           const int mtiles = o.M / kBM;
           __threadfence();
@@ -550,6 +573,141 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             if (lane == 0) o.colsum_cnt[n0 / kBN] = 0u;
           }
         }
+      }
+    }
+    if (fl & F_DW0) {
+      // ---- fused layer-0 weight gradient (see GemmOp::dw0_*): P[n][k] = sum_m D(m, n) X(m, k) over this
+      // CTA's 128 rows as a register-tiled fp32 product.  Warp w sums rows 16w..16w+15; inside a warp
+      // each lane owns a 4 n x 8 k block (3 LDS.128 per 32 FFMA); the 8 per-warp partials are added
+      // through shared memory, the per-CTA result goes to global, the last M tile adds the tiles up.
+      if (prof && tid == 64) prof[13] = clock64();
+      float* sD = smem + 32 * kTTPitch;     // [128 m][36]: this tile's D, row-major
+      float* Xs = sD + kBM * 36;            // [128 m][36]: the X chunk, row-major
+      float* Ps = Xs + kBM * 36;            // [8 warps][32 n][36]: per-warp partial sums (k halves swizzled)
+      uint32_t* last_flag = reinterpret_cast<uint32_t*>(ctl + 896);
+      const int te = tid - 64, we = te >> 5;
+      const int nq = lane >> 2, ko = lane & 3;
+      const int kp = o.dw0_kp;
+      const int ones = o.dw0_ones;
+      const int nt = n0 >> 5;
+      float* part = o.dw0_part + (static_cast<size_t>(mt) * ntn + nt) * 32 * kp;
+#pragma unroll
+      for (int j4 = 0; j4 < kEN / 4; ++j4)
+        *reinterpret_cast<float4*>(sD + row * 36 + cn0 + 4 * j4) =
+            make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+      for (int kc0 = 0; kc0 < (kp >> 5); ++kc0) {
+        if (kc0 > 0) {
+          const float4* xg = reinterpret_cast<const float4*>(
+              o.dw0_x + (static_cast<size_t>(kc0) * (o.M >> 3) + (m0 >> 3)) * 256);
+#pragma unroll
+          for (int i = 0; i < kAFloats / 4 / 256; ++i) xr[i] = __ldg(xg + te + i * 256);
+        }
+#pragma unroll
+        for (int i = 0; i < kAFloats / 4 / 256; ++i) {
+          const int f = te + i * 256;  // float4 index inside the CT32 chunk: [row group][k core][row]
+          const int m = (f >> 6) * 8 + (f & 7), kc = (f >> 3) & 7;
+          if (ones >= 0 && (ones >> 2) == kc0 * 8 + kc) {
+            xr[i].x = (ones & 3) == 0 ? 1.f : xr[i].x;
+            xr[i].y = (ones & 3) == 1 ? 1.f : xr[i].y;
+            xr[i].z = (ones & 3) == 2 ? 1.f : xr[i].z;
+            xr[i].w = (ones & 3) == 3 ? 1.f : xr[i].w;
+          }
+          *reinterpret_cast<float4*>(Xs + m * 36 + 4 * kc) = xr[i];
+        }
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        float acc[4][8];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+        for (int mm = 0; mm < 16; ++mm) {
+          const int ml = we * 16 + mm;
+          const float4 d4 = *reinterpret_cast<const float4*>(sD + ml * 36 + 4 * nq);
+          const float4 x0 = *reinterpret_cast<const float4*>(Xs + ml * 36 + 8 * ko);
+          const float4 x1 = *reinterpret_cast<const float4*>(Xs + ml * 36 + 8 * ko + 4);
+          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+          const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+        }
+        // float4 stores; the two 4-k halves of odd n-quads are swapped so a quarter warp covers all banks
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            *reinterpret_cast<float4*>(Ps + we * (32 * 36) + (4 * nq + a) * 36 + 8 * ko + 4 * (h ^ (nq & 1))) =
+                make_float4(acc[a][4 * h + 0], acc[a][4 * h + 1], acc[a][4 * h + 2], acc[a][4 * h + 3]);
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < (kBN * kBK) / 256; ++i) {
+          const int oo = te + i * 256;
+          const int n = oo >> 5, k = oo & 31;  // lanes = consecutive k
+          float tot = 0.f;
+          const int ks = k ^ (((n >> 2) & 1) << 2);
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) tot += Ps[w8 * (32 * 36) + n * 36 + ks];
+          part[static_cast<size_t>(n) * kp + kc0 * 32 + k] = tot;
+        }
+        // (the next chunk's Xs stores are ordered behind every warp's reads by the two barriers above)
+      }
+      // deterministic cross-CTA totals (dW_0 and, if present, the bias column sums): the last M tile
+      // to arrive adds the per-tile partials in tile order
+      const int mtiles = o.M / kBM;
+      if (prof && tid == 64) prof[14] = clock64();
+      asm volatile("bar.sync 2, 256;\n" ::: "memory");
+      if (te == 0)
+        *last_flag = (ptx::atom_add_acq_rel_gpu(o.dw0_cnt + nt, 1u) == static_cast<unsigned int>(mtiles - 1)) ? 1u : 0u;
+      asm volatile("bar.sync 2, 256;\n" ::: "memory");
+      if (prof && tid == 64) prof[15] = clock64();
+      if (*last_flag) {
+        const float* p0 = o.dw0_part + static_cast<size_t>(nt) * 32 * kp;
+        const size_t mt_stride = static_cast<size_t>(ntn) * 32 * kp;
+        const int ma = o.dw0_map_a, ma4 = o.dw0_map_a4, ms = o.dw0_map_s, cols = o.dw0_cols, nv = o.dw0_n - n0;
+        float* outp = o.dw0_out + static_cast<size_t>(n0) * o.dw0_ld;
+        float* bias_out = o.dw0_bias_out;
+        const int ld = o.dw0_ld;
+        // 32 x kp outputs, 4 per thread per round; every tile's partial of a round is in flight
+        // together (up to 8 M tiles; more are added in further passes of the same order)
+        for (int base = 0; base < 32 * kp; base += 1024) {
+          float tot[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int i0 = 0; i0 < mtiles; i0 += 8) {
+            float ld4[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                ld4[i][j] = (i0 + i < mtiles) ? __ldcg(p0 + (i0 + i) * mt_stride + base + te + 256 * j) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+              for (int j = 0; j < 4; ++j) tot[j] += ld4[i][j];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int oo = base + te + 256 * j;
+            const int n = oo / kp, kk = oo - n * kp;
+            int col = kk;
+            bool ok = kk < cols && n < nv;
+            if (ma4 > 0) {  // [action | pad4 | state] -> [state | action]
+              if (kk < ma) col = ms + kk;
+              else if (kk >= ma4) col = kk - ma4;
+              else ok = false;
+              ok = ok && (kk < ma4 + ms);
+            }
+            if (ok) outp[static_cast<size_t>(n) * ld + col] = tot[j];
+            if (kk == ones && n < nv) bias_out[n0 + n] = tot[j];
+          }
+        }
+        if ((fl & F_COLSUM) && o.colsum_out && we == 0) {
+          float tot = 0.f;
+          for (int i = 0; i < mtiles; ++i)
+            tot += __ldcg(o.colsum + static_cast<size_t>(i) * o.colsum_ld + n0 + lane);
+          if (n0 + lane < o.colsum_n) o.colsum_out[n0 + lane] = tot;
+        }
+        if (te == 0) o.dw0_cnt[nt] = 0u;
       }
     }
   }

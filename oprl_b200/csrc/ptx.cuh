@@ -197,6 +197,15 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn, int b_
          (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
+// Arrival ticket with release (this CTA's earlier global stores, ordered before it by a CTA
+// barrier) and acquire (the loads of the last arriver) semantics at GPU scope -- one instruction by
+// one thread instead of a __threadfence() in every thread around a relaxed atomic.
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
 // Round-to-nearest (ties away, == cvt.rna.tf32.f32) tf32: low 13 mantissa bits cleared.
 // Done with two integer ops: cvt.rna runs on the quarter-rate conversion unit and made the
 // in-kernel operand split the bottleneck of the GEMM K loop.

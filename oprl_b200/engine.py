@@ -45,6 +45,20 @@ class EngineSpec:
     seed: int = 0
 
 
+class PendingScalars:
+    """Ticket of one pipelined scalar read-back (UpdateEngine.scalars_async)."""
+
+    def __init__(self, engine: "UpdateEngine", ticket: int):
+        self._engine, self._ticket, self._out = engine, ticket, None
+
+    def result(self) -> dict:
+        if self._out is None:
+            buf = (C.c_float * 32)()
+            L.check(self._engine._lib.oprl_scalars_wait(self._engine._h, self._ticket, buf, 32))
+            self._out = {k: float(buf[i]) for i, k in enumerate(L.SCALARS)}
+        return self._out
+
+
 class UpdateEngine:
     """Owns the engine handle and the torch tensors it borrows."""
 
@@ -260,6 +274,12 @@ class UpdateEngine:
     def scalars(self) -> dict:
         L.check(self._lib.oprl_get_scalars(self._h, self._scalars, 32))
         return {k: float(self._scalars[i]) for i, k in enumerate(L.SCALARS)}
+
+    def scalars_async(self) -> "PendingScalars":
+        """Enqueue a D2H read of the scalars of everything launched so far; `.result()` waits for
+        that copy only, so the next update can already be running (valid for 8 further calls)."""
+        self._use_current_stream()
+        return PendingScalars(self, L.check(self._lib.oprl_scalars_enqueue(self._h)))
 
     def state(self) -> L.State:
         st = L.State()

@@ -125,3 +125,37 @@ def test_first_update_obeys_adam_and_polyak_rules_exactly():
         target = 5e-3 * ar[grp]["theta"].cpu() + (1 - 5e-3) * before[grp]["target"].cpu()
         assert torch.equal(ar[grp]["target"].cpu(), target), grp
         assert g.abs().max().item() > 0
+
+
+def test_pipelined_scalar_readback_matches_the_blocking_one():
+    """scalars_async() of update t, consumed after updates t+1.. were launched, returns exactly what a
+    blocking scalars() read right after update t returns (host-batch path, as bench.py's e2e loop)."""
+    from oprl_b200.algos.ddpg import DDPG
+    from oprl_b200.engine import EngineSpec  # noqa: F401
+
+    a, b = make_pair(DDPG)
+    g = torch.Generator().manual_seed(7)
+    batches = []
+    for _ in range(6):
+        batches.append([torch.randn(256, 24, generator=g).pin_memory(), (torch.rand(256, 6, generator=g) * 2 - 1).pin_memory(),
+                        torch.rand(256, 1, generator=g).pin_memory(), torch.zeros(256, 1).pin_memory(),
+                        torch.randn(256, 24, generator=g).pin_memory()])
+    blocking = []
+    for bt in batches:
+        a.update(*bt)
+        blocking.append(a.engine.scalars())
+    pend = []
+    for bt in batches:
+        b.update(*bt)
+        pend.append(b.engine.scalars_async())
+    for want, p in zip(blocking, pend):
+        got = p.result()
+        assert got == want
+    for grp in ("actor", "critic"):
+        assert torch.equal(a.engine.arena[grp]["theta"], b.engine.arena[grp]["theta"])
+    # tickets expire once the ring has wrapped
+    old = b.engine.scalars_async()
+    for _ in range(8):
+        b.engine.scalars_async()
+    with pytest.raises(Exception):
+        old.result()

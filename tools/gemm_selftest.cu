@@ -81,6 +81,28 @@ static double run_case(int M, int N, int K, bool simt, int passes) {
   o.rm = d_rm; o.rm_ld = N; o.rm_m = M; o.rm_n = N;
   o.colsum = d_cs; o.colsum_ld = N;
   o.passes = passes; o.alpha = 1.f;
+  // fused layer-0 weight gradient: dW0[n][k] = sum_m D(m, n) X(m, k), X tiled [M x 64]
+  const int KP0 = 64, A_ = 6, A4_ = 8, S_ = 50;  // columns [action 6 | pad 2 | state 50 | pad 6]
+  HostMat X;
+  X.rows = M; X.cols = KP0;
+  X.v.resize((size_t)M * KP0);
+  for (auto& x : X.v) x = frand();
+  X.upload();
+  float *d_part, *d_dw0, *d_csout;
+  unsigned int* d_cnt;
+  CK(cudaMalloc(&d_part, (size_t)(M / 128) * N * KP0 * 4));
+  CK(cudaMalloc(&d_dw0, (size_t)N * (A_ + S_) * 4));
+  CK(cudaMalloc(&d_csout, (size_t)N * 4));
+  CK(cudaMalloc(&d_cnt, (N / 32) * 4));
+  CK(cudaMemset(d_cnt, 0, (N / 32) * 4));
+  CK(cudaMemset(d_dw0, 0xff, (size_t)N * (A_ + S_) * 4));
+  o.dw0_x = X.d; o.dw0_kp = KP0; o.dw0_part = d_part; o.dw0_out = d_dw0; o.dw0_cnt = d_cnt;
+  o.dw0_ld = A_ + S_; o.dw0_n = N - 3; o.dw0_cols = KP0;
+  o.dw0_map_a = A_; o.dw0_map_a4 = A4_; o.dw0_map_s = S_;
+  o.colsum_out = d_csout; o.colsum_n = N;
+  float* d_bout;
+  CK(cudaMalloc(&d_bout, (size_t)N * 4));
+  o.dw0_ones = A_; o.dw0_bias_out = d_bout;
   if (simt) launch<true>(L); else launch<false>(L);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -121,18 +143,58 @@ static double run_case(int M, int N, int K, bool simt, int passes) {
     double ce = fabs(cs[i] - colref[i]) / (fabs(colref[i]) + 1.0);
     if (!(ce <= max_cerr)) max_cerr = ce;
   }
-  printf("  M=%d N=%d K=%d %s passes=%d: rel_err=%.3e tiled=%.3e ttiled=%.3e colsum=%.3e\n", M, N, K,
-         simt ? "SIMT" : "TC  ", passes, max_err, max_terr, max_tterr, max_cerr);
+  // dW0 and the cross-tile column sums against the device's own D (row-major output)
+  double max_dwerr = 0;
+  {
+    std::vector<float> dw((size_t)N * (A_ + S_)), cso(N);
+    CK(cudaMemcpy(dw.data(), d_dw0, dw.size() * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cso.data(), d_csout, cso.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<float> bo(N);
+    CK(cudaMemcpy(bo.data(), d_bout, bo.size() * 4, cudaMemcpyDeviceToHost));
+    for (int n = 0; n < N - 3; ++n) {  // the ones-column bias gradient against the column sums
+      double ce = fabs(bo[n] - cso[n]) / (fabs(cso[n]) + 1.0);
+      if (!(ce <= max_cerr)) max_cerr = ce;
+    }
+    for (int n = 0; n < N; ++n) {
+      double ctot = 0;
+      for (int m = 0; m < M; ++m) ctot += out[(size_t)m * N + n];
+      double ce = fabs(cso[n] - ctot) / (fabs(ctot) + 1.0);
+      if (!(ce <= max_cerr)) max_cerr = ce;
+      for (int col = 0; col < A_ + S_; ++col) {
+        const int kk = col < S_ ? A4_ + col : col - S_;  // reference column -> tiled column
+        double acc = 0, mag = 0;
+        for (int m = 0; m < M; ++m) {
+          double d = out[(size_t)m * N + n], x = X.v[(size_t)m * KP0 + kk];
+          acc += d * x;
+          mag += fabs(d * x);
+        }
+        const float got = dw[(size_t)n * (A_ + S_) + col];
+        double err;
+        if (n >= N - 3) {
+          uint32_t bits;
+          memcpy(&bits, &got, 4);
+          err = bits == 0xffffffffu ? 0 : 1;  // rows >= dw0_n must stay untouched
+        } else {
+          err = fabs(got - acc) / (mag + 1.0);
+        }
+        if (!(err <= max_dwerr)) max_dwerr = err;
+      }
+    }
+  }
+  printf("  M=%d N=%d K=%d %s passes=%d: rel_err=%.3e tiled=%.3e ttiled=%.3e colsum=%.3e dw0=%.3e\n", M, N, K,
+         simt ? "SIMT" : "TC  ", passes, max_err, max_terr, max_tterr, max_cerr, max_dwerr);
+  cudaFree(X.d); cudaFree(d_part); cudaFree(d_dw0); cudaFree(d_csout); cudaFree(d_cnt);
   cudaFree(A.d); cudaFree(B.d);
   cudaFree(d_bias); cudaFree(d_rm); cudaFree(d_t); cudaFree(d_tt); cudaFree(d_cs);
   double worst = max_err;
   if (!(max_terr < 1e-6)) worst = 1;
   if (!(max_tterr < 1e-6)) worst = 1;
   if (!(max_cerr < 1e-5)) worst = 1;
+  if (!(max_dwerr < 2e-6)) worst = 1;
   return worst;
 }
 
-static GemmLaunch make_bench(int nops, int M, int N, int K, int passes, bool tt) {
+static GemmLaunch make_bench(int nops, int M, int N, int K, int passes, bool tt, bool dw0 = false) {
   GemmLaunch L;
   memset(&L, 0, sizeof(L));
   L.n_ops = nops;
@@ -149,6 +211,21 @@ static GemmLaunch make_bench(int nops, int M, int N, int K, int passes, bool tt)
     o.M = M; o.N = N; o.K = K; o.act = ACT_RELU;
     o.t = t; o.t_rows = M; o.t_n = N; o.passes = passes; o.alpha = 1.f;
     if (tt) { o.tt = ttp; o.tt_rows = N; }
+    if (dw0 && i == 0) {
+      float *x, *part, *out, *cs, *cso;
+      unsigned int* cnt;
+      CK(cudaMalloc(&x, (size_t)M * 32 * 4));
+      CK(cudaMemset(x, 0, (size_t)M * 32 * 4));
+      CK(cudaMalloc(&part, (size_t)(M / 128) * N * 32 * 4));
+      CK(cudaMalloc(&out, (size_t)N * 32 * 4));
+      CK(cudaMalloc(&cs, (size_t)(M / 128) * N * 4));
+      CK(cudaMalloc(&cso, (size_t)N * 4));
+      CK(cudaMalloc(&cnt, (N / 32) * 4));
+      CK(cudaMemset(cnt, 0, (N / 32) * 4));
+      o.dw0_x = x; o.dw0_kp = 32; o.dw0_part = part; o.dw0_out = out; o.dw0_cnt = cnt;
+      o.dw0_ld = 30; o.dw0_n = N; o.dw0_cols = 32; o.dw0_map_a = 6; o.dw0_map_a4 = 8; o.dw0_map_s = 24;
+      o.dw0_ones = 6; o.dw0_bias_out = cso;
+    }
   }
   return L;
 }
@@ -166,8 +243,9 @@ static void spin_warm(const GemmLaunch& L, double ms_target) {
   }
 }
 
-static void bench(int nops, int M, int N, int K, int passes, bool simt, bool tt) {
-  GemmLaunch L = make_bench(nops, M, N, K, passes, tt);
+static void bench(int nops, int M, int N, int K, int passes, bool simt, bool tt, bool dw0 = false) {
+  GemmLaunch L = make_bench(nops, M, N, K, passes, tt, dw0);
+  if (dw0) printf("(next: op 0 carries the fused dW0 + column-sum epilogue)\n");
   if (!simt) spin_warm(L, 300.0);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -214,6 +292,8 @@ static void bench(int nops, int M, int N, int K, int passes, bool simt, bool tt)
   printf("  prof cycles: setup=%lld issue_all=%lld first_full=%lld last_commit=%lld accum=%lld tmem_ld=%lld bar=%lld math=%lld epi_end=%lld exit=%lld | %.0f ns => %.0f MHz\n",
          h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[11] - h[0], h[12] - h[0], h[7] - h[0],
          h[8] - h[0], ns, (h[8] - h[0]) / ns * 1e3);
+  if (dw0)
+    printf("  dW0 epilogue: start=%lld partials_stored=%lld ticket_known=%lld\n", h[13] - h[0], h[14] - h[0], h[15] - h[0]);
 }
 
 int main(int argc, char** argv) {
@@ -240,6 +320,7 @@ int main(int argc, char** argv) {
   bench(1, 256, 256, 256, 3, false, false);
   bench(3, 256, 256, 256, 3, false, false);
   bench(3, 256, 256, 256, 3, false, true);
+  bench(2, 256, 256, 256, 3, false, true, true);
   bench(3, 256, 256, 256, 1, false, false);
   bench(3, 256, 256, 32, 3, false, false);
   bench(5, 256, 512, 512, 3, false, false);
