@@ -57,6 +57,7 @@ static inline int pad4(int x) { return (x + 3) & ~3; }
 // scheduling, parameter fetch, barrier init, TMEM allocation) while its predecessor drains;
 // each kernel executes griddepcontrol.wait before its first global access.
 static bool g_pdl = true;
+static thread_local int g_cluster_x = 1;  // cluster dimension of the next launch_k (split-K GEMM launches)
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                      Args&&... args) {
@@ -66,11 +67,22 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_cluster_x > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = static_cast<unsigned int>(g_cluster_x);
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   CU(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
@@ -132,6 +144,7 @@ struct oprl_engine {
   cudaStream_t stream = nullptr;      // launch stream (caller may redirect it, e.g. torch's current stream)
   cudaStream_t own_stream = nullptr;  // engine-owned: setup work and graph capture
   int A4 = 0, Kin = 0;  // padded action columns / padded input width of layer 0
+  int n_sm = 148;
   Group grp[2];
   DevState* d_state = nullptr;
   DevState* h_state = nullptr;  // pinned mirror for reads
@@ -1003,10 +1016,17 @@ static void launch_gemm_ops(oprl_engine* e, const std::vector<GemmOp>& ops, cuda
       tiles += gemm_tiles(L.op[i]);
       L.tile_end[i] = tiles;
     }
+    // split-K over clusters when the launch leaves most SMs idle (OPRL_B200_KSPLIT=1 turns it off, 2 / 4 cap it)
+    static const int ks_cap = getenv("OPRL_B200_KSPLIT") ? atoi(getenv("OPRL_B200_KSPLIT")) : 4;
+    int ks = gemm_choose_ksplit(L.op, L.n_ops, e->n_sm);
+    while (ks > 1 && ks > ks_cap) ks >>= 1;
+    L.ksplit = ks;
+    g_cluster_x = ks;
     if (e->cfg.gemm_mode == OPRL_GEMM_SIMT)
-      launch_k(gemm_kernel<true>, dim3(tiles), dim3(kGemmThreads), kGemmSmemBytes, st, L);
+      launch_k(gemm_kernel<true>, dim3(tiles * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
     else
-      launch_k(gemm_kernel<false>, dim3(tiles), dim3(kGemmThreads), kGemmSmemBytes, st, L);
+      launch_k(gemm_kernel<false>, dim3(tiles * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
+    g_cluster_x = 1;
   }
 }
 
@@ -1164,6 +1184,7 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   if (prop.major != 10) return fail(-4, "device sm_%d%d is not Blackwell sm_100", prop.major, prop.minor);
   e = new oprl_engine;
   e->cfg = *cfg;
+  e->n_sm = prop.multiProcessorCount;
   if (const char* v = getenv("OPRL_B200_PDL")) g_pdl = atoi(v) != 0;
   if (e->cfg.world_size < 1) e->cfg.world_size = 1;
   CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));

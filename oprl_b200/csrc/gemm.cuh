@@ -130,6 +130,13 @@ struct GemmOp {
 struct GemmLaunch {
   // first cache line of the parameter block: everything the tile -> op lookup needs
   int n_ops;
+  // Split-K over a thread-block cluster: ksplit (1, 2 or 4) CTAs share one output tile, the K
+  // chunks dealt round-robin.  A single SM pulls only ~31-36 B/clk from L2, so the K loop of one
+  // tile (160 KB at K = 256) is ingest-bound; with the chunks spread over ksplit SMs each CTA
+  // streams 1/ksplit of them.  Ranks > 0 push their fp32 partial tile into rank 0's shared memory
+  // (DSMEM stores + a remote mbarrier arrive); rank 0 adds the partials in rank order and runs the
+  // epilogue.  The launch carries cluster dimension (ksplit, 1, 1) and ksplit x the CTAs.
+  int ksplit;
   int tile_end[kMaxOps];  // exclusive prefix sums of gemm_tiles(op[i])
   long long* prof;        // selftest only: per-phase clock64 stamps of CTA 0
   GemmOp op[kMaxOps];
@@ -143,6 +150,23 @@ inline void gemm_finalize(GemmOp& o) {
   const int nchunks = o.K / kBK;
   o.group = (nchunks + 6) / 7 > 2 ? (nchunks + 6) / 7 : 2;
   o.n_big = (nchunks + o.group - 1) / o.group;
+}
+// host: CTAs per tile for one launch -- the largest of {4, 2, 1} that keeps the whole launch in one
+// wave of `n_sm` single-CTA SMs, leaves rank 0 the ring stages the partial tiles land in, and is
+// worth the exchange (an op must have at least 2 chunks per CTA)
+inline int gemm_choose_ksplit(const GemmOp* ops, int n_ops, int n_sm) {
+  int tiles = 0, max_chunks = 0;
+  for (int i = 0; i < n_ops; ++i) {
+    tiles += gemm_tiles(ops[i]);
+    max_chunks = ops[i].K / kBK > max_chunks ? ops[i].K / kBK : max_chunks;
+  }
+  for (int ks = 4; ks >= 2; ks >>= 1) {
+    if (tiles * ks > n_sm) continue;
+    if (max_chunks < 2 * ks) continue;
+    if ((max_chunks + ks - 1) / ks > kStages - (ks - 1)) continue;
+    return ks;
+  }
+  return 1;
 }
 // keep a value in a register from here on (stops ptxas from re-reading kernel parameters,
 // one dependent constant-bank load per use, inside the latency-critical epilogue)
@@ -176,9 +200,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(ctl + 904);  // split-K: partial tiles have landed
+
   ptx::pdl_trigger();
   // ---- which op / tile is this CTA
-  int t = blockIdx.x;
+  const int ks = L.ksplit > 1 ? L.ksplit : 1;
+  const int kr = ks > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
+  int t = ks > 1 ? static_cast<int>(blockIdx.x) / ks : static_cast<int>(blockIdx.x);
   int oi = 0;
   while (oi < L.n_ops && t >= L.tile_end[oi]) ++oi;
   if (oi >= L.n_ops) return;
@@ -200,8 +228,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   const int m0 = mt * kBM;
   const int n0 = (t % ntn) * kBN;
   const int nchunks = o.K / kBK;
+  // this CTA's share of the K chunks: global chunk kr + ks * cl for cl < nloc
+  const int nloc = kr < nchunks ? (nchunks - kr + ks - 1) / ks : 0;
+  const int active = nchunks < ks ? nchunks : ks;  // CTAs of the cluster that hold a partial tile
+  if (nloc == 0) {  // (only with ks > 1) nothing to add: leave after the cluster-wide arrive
+    ptx::cluster_arrive();
+    return;
+  }
   const int passes = o.passes;
   long long* prof = (L.prof && blockIdx.x == 0) ? L.prof : nullptr;
+  long long* prof1 = (L.prof && blockIdx.x == 1 && ks > 1) ? L.prof : nullptr;  // rank 1 of tile 0
+  if (prof1 && tid == 0) prof1[16] = clock64();
   if (prof && tid == 0) {
     prof[0] = clock64();
     unsigned long long gt;
@@ -210,8 +247,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
   // TMEM map: accumulator column block 0 = cross terms, blocks 1..n_big = hi*hi per group of K
   // chunks (at most 7), then kASlots x (A hi | A lo) operand blocks written by the splitter warps.
-  const int group = o.group;
-  const int n_big = o.n_big;
+  int group = o.group;
+  int n_big = o.n_big;
+  if (ks > 1) {  // the accumulator plan of gemm_finalize, for this CTA's chunk count
+    group = (nloc + 6) / 7 > 2 ? (nloc + 6) / 7 : 2;
+    n_big = (nloc + group - 1) / group;
+  }
   const uint32_t a_col0 = static_cast<uint32_t>(32 * (n_big + 1));
   uint32_t tmem_cols = 32;
   while (tmem_cols < a_col0 + kASlots * kATmemCols) tmem_cols <<= 1;
@@ -227,9 +268,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     } else if (lane == kStages) {
       ptx::mbar_init(accum, 1);
       ptx::mbar_init(mask_bar, 1);
+      ptx::mbar_init(xbar, static_cast<uint32_t>(active > 1 ? (active - 1) * 8 : 1));  // one arrival per remote epilogue warp
     }
     ptx::fence_mbar_init();
     __syncwarp();
+    if (ks > 1) ptx::cluster_arrive();  // publishes the barrier init to the cluster
     // the other warps wait on this barrier (after TMEM allocation); the copies start now
     asm volatile("bar.arrive 3, %0;\n" ::"n"(kGemmThreads) : "memory");
     if (prof && lane == 0) prof[1] = clock64();
@@ -237,9 +280,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int a_rb = o.a_rows >> 3;
     const int b_rb = o.b_rows >> 3;
     const uint32_t tx = (kAFloats + kBFloats) * 4u;
-    for (int c = 0; c < nchunks; ++c) {
-      const int s = c % kStages;
-      const uint32_t ph = (c / kStages) & 1;
+    for (int cl = 0; cl < nloc; ++cl) {
+      const int c = kr + cl * ks;
+      const int s = cl % kStages;
+      const uint32_t ph = (cl / kStages) & 1;
       ptx::mbar_wait(&empty[s], ph ^ 1);
       if (ptx::elect_one()) {
         float* st = smem + s * kStageFloats;
@@ -247,7 +291,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         ptx::bulk_g2s(st, o.a + (static_cast<size_t>(c) * a_rb + (m0 >> 3)) * 256, kAFloats * 4, &full[s]);
         ptx::bulk_g2s(st + kAFloats, o.b + (static_cast<size_t>(c) * b_rb + (n0 >> 3)) * 256, kBFloats * 4,
                       &full[s]);
-        if (c == 0 && o.mask) {
+        if (c == 0 && o.mask) {  // (chunk 0 belongs to rank 0, the CTA that runs the epilogue)
           // epilogue ReLU mask: the [128 x 32] tile of the saved activation is one contiguous 16 KB
           ptx::mbar_expect_tx(mask_bar, kMaskBytes);
           ptx::bulk_g2s(mask_smem, o.mask + (static_cast<size_t>(n0 >> 5) * (o.mask_rows >> 3) + (m0 >> 3)) * 256,
@@ -258,6 +302,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     if (prof && lane == 0) prof[2] = clock64();
   } else {
+    if (ks > 1) ptx::cluster_arrive();
     if (!kSimt && warp == 1) ptx::tmem_alloc(tmem_slot, tmem_cols);
     ptx::tc_fence_before();
     asm volatile("bar.sync 3, %0;\n" ::"n"(kGemmThreads) : "memory");
@@ -274,7 +319,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const uint32_t b_lbo = 128u, b_sbo = 1024u;
     int in_group = 0;
     uint32_t big = tmem_d + 32u;
-    for (int c = 0; c < nchunks; ++c) {
+    for (int c = 0; c < nloc; ++c) {  // c: local chunk index
       const int s = c % kStages;
       const uint32_t ph = (c / kStages) & 1;
       ptx::mbar_wait(&conv[s], ph);
@@ -342,7 +387,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // (32 k) goes registers -> TMEM (the MMA reads A from tensor memory, so shared memory only
       // serves the narrow B operand); B: in place (hi) + a second 4 KB buffer (lo).
       const uint32_t ta_lane = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16) + a_col0;
-      for (int c = half; c < nchunks; c += 2) {
+      for (int c = half; c < nloc; c += 2) {  // c: local chunk index
         const int s = c % kStages;
         const uint32_t ph = (c / kStages) & 1;
         ptx::mbar_wait(&full[s], ph);
@@ -409,7 +454,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // FFMA cross-check path: same smem contents, products on CUDA cores in plain fp32.
 #pragma unroll
       for (int j = 0; j < kEN; ++j) v[j] = 0.f;
-      for (int c = 0; c < nchunks; ++c) {
+      for (int c = 0; c < nloc; ++c) {
         const int s = c % kStages;
         const uint32_t ph = (c / kStages) & 1;
         ptx::mbar_wait(&full[s], ph);
@@ -429,6 +474,43 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     // every MMA (or FFMA pass) of this tile is done: the smem ring is free for epilogue staging
     asm volatile("bar.sync 1, 256;\n" ::: "memory");  // also publishes bias_smem
+    if (active > 1) {
+      // ---- split-K: partial tiles travel to rank 0 through distributed shared memory (plain
+      // st.shared::cluster stores; a 16 KB cp.async.bulk shared::cta -> shared::cluster copy measured
+      // slower, ~2 200 vs ~1 800 cycles: one SM pair moves only ~8 B/clk over DSMEM either way).
+      // Slot of rank r = the A part of ring stage kStages - r of rank 0 (the host only splits when
+      // rank 0's own chunks leave those stages unused); element (row, 4 columns j4) of a thread sits
+      // at float4 index (half * 4 + j4) * 128 + row in both CTAs.
+      if (kr > 0) {
+        if (prof1 && tid == 64) prof1[17] = clock64();
+        ptx::cluster_wait();  // rank 0 has initialised xbar (every thread of the cluster arrived at kernel start)
+        if (prof1 && tid == 64) prof1[18] = clock64();
+        const uint32_t slot = ptx::mapa(ptx::smem_u32(smem + (kStages - kr) * kStageFloats), 0);
+#pragma unroll
+        for (int j4 = 0; j4 < kEN / 4; ++j4)
+          ptx::st_cluster_v4(slot + static_cast<uint32_t>(((half * 4 + j4) * 128 + row) * 16), v[4 * j4 + 0],
+                             v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        // one remote arrive per warp (remote arrivals on one mbarrier serialise); the warp barrier
+        // orders the other lanes' stores before lane 0's release
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(xbar), 0));
+        if (prof1 && tid == 64) prof1[19] = clock64();
+        fl = 0;  // rank 0 runs the epilogue
+      } else {
+        ptx::mbar_wait_cluster(xbar, 0);
+        for (int r = 1; r < active; ++r) {
+          const float4* slot = reinterpret_cast<const float4*>(smem + (kStages - r) * kStageFloats);
+#pragma unroll
+          for (int j4 = 0; j4 < kEN / 4; ++j4) {
+            const float4 p4 = slot[(half * 4 + j4) * 128 + row];
+            v[4 * j4 + 0] += p4.x;
+            v[4 * j4 + 1] += p4.y;
+            v[4 * j4 + 2] += p4.z;
+            v[4 * j4 + 3] += p4.w;
+          }
+        }
+      }
+    }
     if (prof && tid == 64) prof[11] = clock64();
 
     const int m = m0 + row;

@@ -63,11 +63,64 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if (++spins > (1u << 26)) {
-      printf("oprl: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      if ((threadIdx.x & 31) == 0) printf("oprl: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
       __trap();
     }
   }
 }
+
+// ------------------------------------------------- thread-block cluster / DSMEM
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t caddr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(caddr), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+// arrive on an mbarrier of another CTA of the cluster; releases this thread's earlier DSMEM stores
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t caddr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(caddr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      if ((threadIdx.x & 31) == 0) printf("oprl: cluster mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+// Bulk copy from this CTA's shared memory into another CTA's (TMA engine, DSMEM); completion is
+// reported as tx bytes on an mbarrier of the destination CTA.  Both addresses are shared::cluster.
+__device__ __forceinline__ void bulk_s2s_cluster(uint32_t dst_caddr, const void* smem_src, uint32_t bytes,
+                                                 uint32_t bar_caddr) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_caddr),
+      "r"(smem_u32(smem_src)), "r"(bytes), "r"(bar_caddr)
+      : "memory");
+}
+// whole-cluster barrier, split in its two halves (every thread of every CTA arrives once)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;\n" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;\n" ::: "memory"); }
 
 // ------------------------------------------------------- bulk async copy (TMA)
 // global -> shared::cta, completion reported as tx bytes on an mbarrier.

@@ -36,6 +36,8 @@ struct HostMat {  // logical [rows x cols] row-major + tiled device copies
 
 static float frand() { return (float)rand() / RAND_MAX * 2.f - 1.f; }
 
+static int g_ksplit = 1;  // CTAs per tile (cluster size) of the launches below; 0 = the engine's automatic choice
+
 template <bool kSimt>
 static void launch(const GemmLaunch& Lin, cudaStream_t st = 0) {
   GemmLaunch L = Lin;
@@ -45,7 +47,22 @@ static void launch(const GemmLaunch& Lin, cudaStream_t st = 0) {
     tiles += gemm_tiles(L.op[i]);
     L.tile_end[i] = tiles;
   }
-  gemm_kernel<kSimt><<<tiles, kGemmThreads, kGemmSmemBytes, st>>>(L);
+  const int ks = g_ksplit > 0 ? g_ksplit : gemm_choose_ksplit(L.op, L.n_ops, 148);
+  L.ksplit = ks;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(tiles * ks);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = kGemmSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ks;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ks > 1 ? 1 : 0;
+  CK(cudaLaunchKernelEx(&cfg, gemm_kernel<kSimt>, L));
 }
 
 static double run_case(int M, int N, int K, bool simt, int passes) {
@@ -280,18 +297,20 @@ static void bench(int nops, int M, int N, int K, int passes, bool simt, bool tt,
   printf("bench graph  TC   (20-node chain): %.2f us/node\n", ms * 1e3 / (200 * 20));
   // phase profile of CTA 0
   long long* d_prof;
-  CK(cudaMalloc(&d_prof, 16 * 8));
-  CK(cudaMemset(d_prof, 0, 16 * 8));
+  CK(cudaMalloc(&d_prof, 24 * 8));
+  CK(cudaMemset(d_prof, 0, 24 * 8));
   GemmLaunch P = L;
   P.prof = d_prof;
   for (int i = 0; i < 3; ++i) launch<false>(P);
   CK(cudaDeviceSynchronize());
-  long long h[16];
+  long long h[24];
   CK(cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost));
   double ns = (double)(h[10] - h[9]);
   printf("  prof cycles: setup=%lld issue_all=%lld first_full=%lld last_commit=%lld accum=%lld tmem_ld=%lld bar=%lld math=%lld epi_end=%lld exit=%lld | %.0f ns => %.0f MHz\n",
          h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[11] - h[0], h[12] - h[0], h[7] - h[0],
          h[8] - h[0], ns, (h[8] - h[0]) / ns * 1e3);
+  if (g_ksplit > 1)
+    printf("  rank 1 (own clock): readout_done=%lld cluster_wait_done=%lld sent=%lld\n", h[17] - h[16], h[18] - h[16], h[19] - h[16]);
   if (dw0)
     printf("  dW0 epilogue: start=%lld partials_stored=%lld ticket_known=%lld\n", h[13] - h[0], h[14] - h[0], h[15] - h[0]);
 }
@@ -314,10 +333,28 @@ int main(int argc, char** argv) {
   if (!(run_case(256, 32, 256, false, 3) < 2e-6)) ++fails;
   if (!(run_case(1024, 512, 96, false, 3) < 2e-6)) ++fails;
   if (!(run_case(256, 512, 512, false, 3) < 2e-6)) ++fails;
+  printf("== split-K over clusters (2 / 4 CTAs per tile)\n");
+  for (int ks = 2; ks <= 4; ks *= 2) {
+    g_ksplit = ks;
+    if (!(run_case(256, 256, 256, true, 3) < 2e-6)) ++fails;
+    if (!(run_case(256, 256, 256, false, 3) < 2e-6)) ++fails;
+    if (!(run_case(128, 32, 32, false, 3) < 2e-6)) ++fails;   // one chunk: ranks > 0 leave at once
+    if (!(run_case(256, 64, 96, false, 3) < 2e-6)) ++fails;   // 3 chunks: uneven shares
+    if (!(run_case(256, 32, 416, false, 3) < 2e-6)) ++fails;  // 13 chunks
+  }
+  g_ksplit = 1;
   printf("fails=%d\n", fails);
 
   if (argc > 1 && atoi(argv[1]) == 0) return fails ? 1 : 0;
   bench(1, 256, 256, 256, 3, false, false);
+  for (int ks = 2; ks <= 4; ks *= 2) {
+    g_ksplit = ks;
+    printf("(next: %d CTAs per tile)\n", ks);
+    bench(1, 256, 256, 256, 3, false, false);
+    if (ks == 2) bench(3, 256, 256, 256, 3, false, true);
+    if (ks == 2) bench(2, 256, 256, 256, 3, false, true, true);
+  }
+  g_ksplit = 1;
   bench(3, 256, 256, 256, 3, false, false);
   bench(3, 256, 256, 256, 3, false, true);
   bench(2, 256, 256, 256, 3, false, true, true);
