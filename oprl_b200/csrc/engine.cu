@@ -352,14 +352,15 @@ static CommArgs make_comm(oprl_engine* e, int group, bool exit_barrier) {
   return cm;
 }
 
-static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, bool exit_barrier = false) {
+static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, bool exit_barrier = false,
+                        LossTail lt = LossTail{nullptr, nullptr, nullptr, 0, 0, 0, 0.f}) {
   // one element per thread: a single load -> compute -> store round trip (which matters most when
   // the gradient loads cross NVLink)
   dim3 grid(g.n_blocks);
   const int group = (&g == &e->grp[OPRL_NET_ACTOR]) ? 0 : 1;
   launch_k(adam_kernel, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs),
            static_cast<const int2*>(g.d_blocks), make_hyper(e->cfg),
-           static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier));
+           static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt);
 }
 
 // --------------------------------------------------------------- program builder
@@ -726,7 +727,35 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     int s_end = b.forward(s, gc.nets[0], gc.theta, false, w->Xp, p_cq, false, simt_head ? nullptr : &lq);
     TM Dm = TM{nullptr, 0, 0};
     int l_start = -1;
-    if (simt_head) {
+    LossTail lt{nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
+    static const bool head_kernel = getenv("OPRL_B200_ACTOR_HEAD") && atoi(getenv("OPRL_B200_ACTOR_HEAD")) != 0;
+    if (simt_head && !head_kernel) {
+      // The seed dL/dq = -1/count of the actor loss is a constant, so dz of the last hidden layer
+      // = seed * w3 (.) relu'(h2) falls out of that layer's forward epilogue and the dX chain starts
+      // right behind it: no head kernel on the critical path.  q itself is only logged
+      // (actor_loss = -mean q): the epilogue leaves per-tile partial dot products h2 . w3 and block 0
+      // of the actor's Adam launch adds them up.   (OPRL_B200_ACTOR_HEAD=1: separate head kernel.)
+      const Net& net = gc.nets[0];
+      const Layer& last = net.L.back();
+      const int hl = static_cast<int>(net.L.size()) - 2;
+      GemmOp& op = b.stage(s_end - 1).ops.back();  // critic layer `hl` over Xp, emitted by forward() above
+      const int ntn = net.L[hl].Np / kBN;
+      Dm = e->alloc_tm(Bp, net.L[hl].Np);
+      op.aux_vec = gc.theta + last.w_off;
+      op.aux_t = Dm.p;
+      op.aux_alpha = -inv_count;
+      op.aux_m = B;
+      op.tail_out = e->alloc_floats(static_cast<size_t>(2 * ntn) * Bp);
+      lt.part = op.tail_out;
+      lt.b3 = gc.theta + last.b_off;
+      lt.out = &e->d_state->scalars[SC_ACTOR_LOSS];
+      lt.nparts = 2 * ntn;
+      lt.ld = Bp;
+      lt.B = B;
+      lt.scale = -inv_count;
+      s = s_end;
+      l_start = hl;
+    } else if (simt_head) {
       TM dz2[2], dz2T[2];
       add_critic_head(e, b, s_end, 1, 1, &p_cq, nullptr, nullptr, nullptr, nullptr, false, false, dz2, dz2T);
       Dm = dz2[0];
@@ -768,7 +797,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     s = b.backward(s, ga.nets[0], ga.grad, p_a, dza, dzaT, w->XT, true, true, nullptr);
     // actor Adam + Polyak + re-tiling   (ddpg.py:107,79-84 ; td3.py:141,83-84)
     b.seg = 2;
-    b.stage(s).add_simt([e, &ga](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm); });
+    b.stage(s).add_simt([e, &ga, lt](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt); });
     ++s;
   }
 }

@@ -67,7 +67,7 @@ constexpr int kATmemCols = 2 * kBK;            // per stage: A hi (32 columns) |
 constexpr int kGemmThreads = 320;  // warp 0 copies, warp 1 MMA, warps 2-9 split + epilogue
 constexpr int kEN = kBN / 2;        // epilogue columns per thread (two warps per TMEM lane quarter)
 constexpr int kMaskBytes = kBM * kBN * 4;  // ReLU-mask tile of the epilogue, prefetched
-constexpr int kGemmSmemBytes = kStages * kStageBytes + kMaskBytes + 1024;
+constexpr int kGemmSmemBytes = kStages * kStageBytes + kMaskBytes + 1280;
 constexpr int kTTPitch = kBM + 4;  // smem pitch of the transposed staging tile (conflict-free)
 constexpr int kMaxOps = 12;
 
@@ -105,6 +105,18 @@ struct GemmOp {
   // [action | pad4 | state]):  n < map_a -> map_s + n ; n >= map_a4 -> n - map_a4.
   int map_a, map_a4, map_s;
   int colsum_ld, colsum_n;  // partial row stride; colsum_out gets columns n < colsum_n
+  // Scalar head riding on the last hidden layer (critic.Q1(s, pi(s)) of the DDPG / TD3 actor step,
+  // ddpg.py:104, td3.py:135-137): with D = h (post-ReLU) and aux_vec = the head weights w3,
+  //   tail_out[(2 * ntile + half) * M + m] = sum_{n in this thread's 16 columns} D(m, n) w3[n]
+  // (the consumer adds the 2 * N/32 partials per row: q[m] - b3), and
+  //   aux_t(m, n) = D(m, n) > 0 && m < aux_m ? aux_alpha * w3[n] : 0            (tiled [M x N])
+  // is dz of this layer for the constant seed dL/dq = aux_alpha -- the backward chain starts from it
+  // without a separate head kernel on the critical path.
+  const float* aux_vec;
+  float* aux_t;
+  float* tail_out;
+  float aux_alpha;
+  int aux_m;
   // Fused layer-0 weight gradient: this op's output D [M x N] is dz_0 (batch x hidden) and
   //   dW_0[n][k] = sum_m D(m, n) * X(m, k)          (X = the tiled layer-0 input, dw0_kp columns)
   // is accumulated in the epilogue with fp32 FMAs (per-CTA partial over its 128 rows, fixed-order
@@ -195,6 +207,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 1);
   float* cs_smem = reinterpret_cast<float*>(ctl + 256);    // [4][32]
   float* bias_smem = reinterpret_cast<float*>(ctl + 768);  // [32]
+  float* aux_smem = reinterpret_cast<float*>(ctl + 1024);  // [32]: this tile's slice of GemmOp::aux_vec
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -361,15 +374,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int ct = (tid - 64) & 127;   // 0..127 inside the group
     ptx::pdl_wait();  // bias / mask / outputs alias buffers the previous kernel may still use
     if (tid - 64 < kBN) bias_smem[tid - 64] = (o.bias && n0 + tid - 64 < o.bias_n) ? __ldg(o.bias + n0 + tid - 64) : 0.f;
+    if (tid - 64 >= kBN && tid - 64 < 2 * kBN) aux_smem[tid - 64 - kBN] = o.aux_vec ? __ldg(o.aux_vec + n0 + tid - 64 - kBN) : 0.f;
     // epilogue plan, read from the kernel parameters now (while the first copies are in flight)
     enum : uint32_t { F_BIAS = 1, F_RELU = 2, F_TANH = 4, F_MASK = 8, F_RS = 16, F_ADDM = 32, F_CLAMP = 64,
                       F_ALPHA = 128, F_MVALID = 256, F_NVALID = 512, F_T = 1024, F_TT = 2048, F_RM = 4096,
-                      F_COLSUM = 8192, F_DW0 = 16384 };
+                      F_COLSUM = 8192, F_DW0 = 16384, F_AUX = 32768 };
     uint32_t fl = (o.bias ? F_BIAS : 0u) | (o.act == ACT_RELU ? F_RELU : 0u) | (o.act == ACT_TANH ? F_TANH : 0u) |
                   (o.mask ? F_MASK : 0u) | (o.rs ? F_RS : 0u) | (o.addm ? F_ADDM : 0u) |
                   (o.clamp > 0.f ? F_CLAMP : 0u) | (o.alpha != 1.f ? F_ALPHA : 0u) |
                   (o.m_valid > 0 ? F_MVALID : 0u) | (o.n_valid > 0 ? F_NVALID : 0u) | (o.t ? F_T : 0u) |
-                  (o.tt ? F_TT : 0u) | (o.rm ? F_RM : 0u) | (o.colsum ? F_COLSUM : 0u) | (o.dw0_out ? F_DW0 : 0u);
+                  (o.tt ? F_TT : 0u) | (o.rm ? F_RM : 0u) | (o.colsum ? F_COLSUM : 0u) | (o.dw0_out ? F_DW0 : 0u) |
+                  (o.aux_vec ? F_AUX : 0u);
     float* out_t = o.t;
     float* out_tt = o.tt;
     int t_rows = o.t_rows, t_c0 = o.t_c0, t_n = o.t_n, tt_rows = o.tt_rows;
@@ -570,6 +585,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     if (prof && tid == 64) prof[12] = clock64();
     // ---- outputs
+    if (fl & F_AUX) {
+      float dot = 0.f;
+#pragma unroll
+      for (int j = 0; j < kEN; ++j) dot = fmaf(v[j], aux_smem[cn0 + j], dot);
+      o.tail_out[static_cast<size_t>(2 * (n0 >> 5) + half) * o.M + m] = dot;
+      const float aa = m < o.aux_m ? o.aux_alpha : 0.f;
+#pragma unroll
+      for (int j4 = 0; j4 < kEN / 4; ++j4)
+        *reinterpret_cast<float4*>(o.aux_t + ct_index(t_rows, m, nb + 4 * j4)) =
+            make_float4(v[4 * j4 + 0] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 0] : 0.f,
+                        v[4 * j4 + 1] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 1] : 0.f,
+                        v[4 * j4 + 2] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 2] : 0.f,
+                        v[4 * j4 + 3] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 3] : 0.f);
+    }
     if (fl & F_T) {
 #pragma unroll
       for (int j4 = 0; j4 < kEN / 4; ++j4) {

@@ -402,10 +402,21 @@ struct AdamHyper {  // python doubles of torch.optim.Adam, rounded to fp32 where
   float tau, one_minus_tau;  // (float)tau, (float)(1 - tau)
 };
 constexpr int kAdamThreads = 256;
+// Optional duty of block 0 of an Adam launch: the actor loss of the DDPG / TD3 actor step,
+//   out = scale * sum_{m < B} (b3 + sum_{p < nparts} part[p * ld + m])        (= -mean q(s, pi(s)))
+// from the per-tile partial head dot products the critic forward GEMM left behind (GemmOp::tail_out).
+// A logging scalar only -- nothing on the gradient path waits for it.
+struct LossTail {
+  const float* part;  // nullptr = no duty
+  const float* b3;
+  float* out;
+  int nparts, ld, B;
+  float scale;
+};
 // mode: bit0 = Adam step, bit1 = Polyak, bit2 = (re)tile online weights, bit3 = tile targets
 __global__ void __launch_bounds__(kAdamThreads)
     adam_kernel(const AdamSeg* segs, const int2* blocks, AdamHyper hp, const DevState* st, int mode,
-                const __grid_constant__ CommArgs cm) {
+                const __grid_constant__ CommArgs cm, const LossTail lt) {
   ptx::pdl_trigger();
   // block -> (tensor, first element): one block per 256 consecutive elements of one tensor, so the
   // grid holds no idle blocks (a [6] bias does not get the grid width of a [256 x 256] weight)
@@ -465,6 +476,25 @@ __global__ void __launch_bounds__(kAdamThreads)
       }
       if (sg.tw && (mode & 8)) sg.tw[ct_index(sg.w_rows, r, c)] = tp;
     }
+    }
+  }
+  if (lt.part && blockIdx.x == 0) {
+    __shared__ float lt_sh[kAdamThreads / 32];
+    float acc = 0.f;
+    const float b3 = lt.b3[0];
+    for (int m = threadIdx.x; m < lt.B; m += kAdamThreads) {
+      float q = b3;
+      for (int p = 0; p < lt.nparts; ++p) q += __ldcg(lt.part + static_cast<size_t>(p) * lt.ld + m);
+      acc += q;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) lt_sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < kAdamThreads / 32; ++w) tot += lt_sh[w];
+      *lt.out = lt.scale * tot;
     }
   }
   if (reduce && cm.exit_barrier) {
