@@ -1060,10 +1060,11 @@ static void launch_gemm_ops(oprl_engine* e, const std::vector<GemmOp>& ops, cuda
 }
 
 static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, bool gemm_only = false,
-                      bool simt_only = false) {
+                      bool simt_only = false, int max_stages = 1 << 30) {
   int n = 0;
   for (auto& sg : p->stages) {
     if (segment >= 0 && sg.segment != segment) continue;
+    if (max_stages-- <= 0) break;
     if (!sg.ops.empty() && !simt_only) {
       launch_gemm_ops(e, sg.ops, st);
       n += static_cast<int>((sg.ops.size() + kMaxOps - 1) / kMaxOps);
@@ -1690,7 +1691,31 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));
   CU(cudaEventCreate(&e1));
+  // what >= 100: the first (what - 100) stages of the update as their own graph -- the difference
+  // between consecutive prefixes is the in-situ cost of one stage (tools/stage_profile.py)
+  cudaGraphExec_t prefix = nullptr;
+  if (what >= 100) {
+    cudaGraph_t g = nullptr;
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
+    int n = 0;
+    try {
+      n = run_stages(e, p, -1, e->own_stream, false, false, what - 100);
+    } catch (...) {
+      cudaStreamEndCapture(e->own_stream, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CU(cudaStreamEndCapture(e->own_stream, &g));
+    if (n > 0) CU(cudaGraphInstantiate(&prefix, g, 0));
+    CU(cudaGraphDestroy(g));
+    if (launches_per_iter) *launches_per_iter = n;
+  }
   auto body = [&]() -> int {
+    if (what >= 100) {
+      if (prefix) CU(cudaGraphLaunch(prefix, e->stream));
+      return 0;
+    }
     if (what == 0 || what == 2) {
       cudaGraphExec_t ge = p->graph[what == 0 ? 4 : 5];
       if (ge) CU(cudaGraphLaunch(ge, e->stream));
@@ -1708,7 +1733,8 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
   CU(cudaEventElapsedTime(ms_total, e0, e1));
   CU(cudaEventDestroy(e0));
   CU(cudaEventDestroy(e1));
-  if (launches_per_iter) *launches_per_iter = what == 0 ? p->n_gemm_launches : 1;
+  if (prefix) CU(cudaGraphExecDestroy(prefix));
+  if (launches_per_iter && what < 100) *launches_per_iter = what == 0 ? p->n_gemm_launches : 1;
   return 0;
   API_END
 }

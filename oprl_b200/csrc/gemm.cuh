@@ -389,6 +389,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     float* out_tt = o.tt;
     int t_rows = o.t_rows, t_c0 = o.t_c0, t_n = o.t_n, tt_rows = o.tt_rows;
     pin(fl); pin_ptr(out_t); pin_ptr(out_tt); pin(t_rows); pin(t_c0); pin(t_n); pin(tt_rows);
+    // tanh' factors of the epilogue (rs), fetched now: their latency hides behind the K loop
+    float rsv[kEN];
+#pragma unroll
+    for (int j = 0; j < kEN; ++j) rsv[j] = 0.f;
+    if (fl & F_RS) {
+#pragma unroll
+      for (int j = 0; j < kEN; ++j)
+        if (n0 + cn0 + j < o.rs_n) rsv[j] = __ldg(o.rs + static_cast<size_t>(m0 + row) * o.rs_ld + n0 + cn0 + j);
+    }
     // fused dW_0: the [128 x 32] tile of the layer-0 input this CTA's rows multiply (one contiguous
     // 16 KB of the CT32 matrix) is fetched into registers now; its latency hides behind the K loop
     float4 xr[kAFloats / 4 / 256];
@@ -555,11 +564,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     if (fl & F_RS) {
 #pragma unroll
-      for (int j = 0; j < kEN; ++j)
-        if (nb + j < o.rs_n) {
-          const float a = o.rs[static_cast<size_t>(m) * o.rs_ld + nb + j];
-          v[j] *= (1.f - a * a);
-        }
+      for (int j = 0; j < kEN; ++j) v[j] *= (1.f - rsv[j] * rsv[j]);  // rsv = 0 beyond rs_n
     }
     if (fl & F_ADDM) {
 #pragma unroll
@@ -669,17 +674,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         o.colsum[static_cast<size_t>(mt) * o.colsum_ld + n0 + lane] = s;
         if (o.colsum_out && !(fl & F_DW0)) {  // (with a fused dW_0 its arrival ticket serves both totals)
           // deterministic cross-CTA total: the last M tile to arrive sums all partials in order
+          // (release/acquire ticket by lane 0; the warp barrier orders the other lanes' stores before it)
           const int mtiles = o.M / kBM;
-          __threadfence();
           __syncwarp();
           unsigned int ticket = 0;
-          if (lane == 0) ticket = atomicAdd(o.colsum_cnt + (n0 / kBN), 1u);
+          if (lane == 0) ticket = ptx::atom_add_acq_rel_gpu(o.colsum_cnt + (n0 / kBN), 1u);
           ticket = __shfl_sync(0xffffffffu, ticket, 0);
           if (ticket == static_cast<unsigned int>(mtiles - 1)) {
-            __threadfence();
             float tot = 0.f;
-            for (int i = 0; i < mtiles; ++i)
-              tot += __ldcg(o.colsum + static_cast<size_t>(i) * o.colsum_ld + n0 + lane);
+            for (int i0 = 0; i0 < mtiles; i0 += 8) {  // up to 8 tiles in flight
+              float ld8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                ld8[i] = (i0 + i < mtiles) ? __ldcg(o.colsum + static_cast<size_t>(i0 + i) * o.colsum_ld + n0 + lane) : 0.f;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) tot += ld8[i];
+            }
             if (n0 + lane < o.colsum_n) o.colsum_out[n0 + lane] = tot;
             if (lane == 0) o.colsum_cnt[n0 / kBN] = 0u;
           }

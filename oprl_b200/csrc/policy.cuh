@@ -499,14 +499,26 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
     tail[0] = loss; tail[1] = qsum; tail[2] = ysum; tail[3] = esum;
     tail[4] = dsum[0]; tail[5] = dsum[1]; tail[6] = lpsum;
   }
-  // ---- last block: fixed-order reduction over blocks
-  __threadfence();
+  // ---- last block: fixed-order reduction over blocks.  One release/acquire ticket by one thread
+  // (the block barrier orders every thread's partial stores before it) instead of a __threadfence()
+  // in every thread on both sides of a relaxed atomic.
   __syncthreads();
   __shared__ unsigned int ticket;
-  if (n == 0) ticket = atomicAdd(a.counter, 1u);
+  if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
   __syncthreads();
   if (ticket != gridDim.x - 1) return;
-  __threadfence();
+  // every load of the reduction is issued before the first add: the per-block scalar tails (warp 0:
+  // lane = block, 7 values each) and, in the critic step, the head-weight / bias-gradient partials
+  // of this thread's hidden unit (batches of sixteen blocks, two critics)
+  float tl[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const unsigned int nb32 = (gridDim.x + 31) / 32;
+  if (warp == 0 && nb32 == 1) {
+    if (static_cast<unsigned int>(lane) < gridDim.x) {
+      const float* tp = a.part + static_cast<size_t>(lane) * W + a.nq * 2 * a.H;
+#pragma unroll
+      for (int k = 0; k < 7; ++k) tl[k] = __ldcg(tp + k);
+    }
+  }
   if (a.mode == 0 && live) {
     for (int i = 0; i < a.nq; ++i) {
       // loads batched sixteen blocks at a time (independent L2 round trips), adds in block order
@@ -530,15 +542,29 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
       a.gb2[i][n] = gb;
     }
   }
-  // per-block scalar tails: gathered by (block, k) threads in parallel, summed in block order
-  __syncthreads();
-  for (unsigned int idx = n; idx < gridDim.x * 8; idx += blockDim.x)
-    sh[idx] = __ldcg(a.part + static_cast<size_t>(idx >> 3) * W + a.nq * 2 * a.H + (idx & 7));
-  __syncthreads();
+  float t[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (nb32 == 1) {
+    // <= 32 blocks: a fixed xor tree over the lanes of warp 0 (deterministic)
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) {
+        float x = tl[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        t[k] = x;
+      }
+    }
+  } else {
+    // more blocks (batch > 256): gathered by (block, k) threads in parallel, summed in block order
+    __syncthreads();
+    for (unsigned int idx = n; idx < gridDim.x * 8; idx += blockDim.x)
+      sh[idx] = __ldcg(a.part + static_cast<size_t>(idx >> 3) * W + a.nq * 2 * a.H + (idx & 7));
+    __syncthreads();
+    if (n == 0)
+      for (unsigned int b = 0; b < gridDim.x; ++b)
+        for (int k = 0; k < 7; ++k) t[k] += sh[b * 8 + k];
+  }
   if (n == 0) {
-    float t[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (unsigned int b = 0; b < gridDim.x; ++b)
-      for (int k = 0; k < 7; ++k) t[k] += sh[b * 8 + k];
     if (a.mode == 0) {
       st->scalars[SC_CRITIC_LOSS] = t[0] * a.inv_count;
       st->scalars[SC_Q_MEAN] = t[1] * a.inv_count;
