@@ -308,9 +308,9 @@ def run_engine(args):
         "data": "synthetic",
         "config": {"workload": wl["name"], "algo": args.algo, "batch": B,
                    "parallelism": "1 learner" if world == 1 else (
-                       f"dp{world}: replicated buffer + parameters, {B} rows/GPU (global minibatch {B * world}), NCCL all-reduce of the "
-                       f"critic and actor gradient arenas before each Adam step; value counts {B}-row minibatch updates job-wide "
-                       f"(optimizer steps/s = value / {world})" if dp else f"{world} independent learner replicas (one seed per GPU, no collective)"),
+                       f"dp{world}: replicated buffer + parameters, {B} rows/GPU (global minibatch {B * world}), gradient arenas "
+                       f"all-reduced inside the Adam kernels over NVLink peer memory (OPRL_B200_DP_NCCL=1: NCCL all-reduce between graph "
+                       f"segments); value counts {B}-row minibatch updates job-wide (optimizer steps/s = value / {world})" if dp else f"{world} independent learner replicas (one seed per GPU, no collective)"),
                    "l2": "replay storage (128 MB) exceeds L2 and is sampled uniformly; parameters/activations (~3 MB) are L2-resident by construction of the learner loop, as in the reference loop",
                    "index_draw": "device Philox (value) / host numpy (api_loop)"},
         "e2e": {"value": world * e2e_steps / (e2e_ms * 1e-3), "unit": "updates/s",

@@ -1462,6 +1462,12 @@ int oprl_update(oprl_engine* e, int flags, int segment) {
   API_BEGIN
   oprl_engine::Work* w = get_work(e, e->cur_B);
   Program* p = get_program(e, w, flags);
+  // OPRL_B200_NOGRAPH=1: the same launches issued one by one into the stream (A/B against the graph)
+  static const bool no_graph = getenv("OPRL_B200_NOGRAPH") && atoi(getenv("OPRL_B200_NOGRAPH")) != 0;
+  if (no_graph) {
+    run_stages(e, p, segment < 0 ? -1 : segment, e->stream);
+    return 0;
+  }
   cudaGraphExec_t g = p->graph[segment < 0 ? 3 : segment];
   if (g) CU(cudaGraphLaunch(g, e->stream));
   return 0;

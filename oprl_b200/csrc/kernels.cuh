@@ -375,22 +375,21 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
   return v;
 }
 // phase 0: "gradients of step `epoch` are complete here"; phase 1: "I have read everybody's".
-__device__ __forceinline__ void comm_signal(const CommArgs& cm, int phase, unsigned int epoch) {
+// Both are called by the first `world` threads of a block, thread r handling rank r, so the remote
+// flag stores and the polls of the local flag block run side by side instead of one after another.
+__device__ __forceinline__ void comm_signal(const CommArgs& cm, int phase, unsigned int epoch, int r) {
   __threadfence_system();
-  for (int r = 0; r < cm.world; ++r)
-    st_release_sys(cm.peer_flags[r] + (cm.group * 2 + phase) * kMaxRanks + cm.rank, epoch);
+  st_release_sys(cm.peer_flags[r] + (cm.group * 2 + phase) * kMaxRanks + cm.rank, epoch);
 }
-__device__ __forceinline__ void comm_wait(const CommArgs& cm, int phase, unsigned int epoch) {
+__device__ __forceinline__ void comm_wait(const CommArgs& cm, int phase, unsigned int epoch, int r) {
   const unsigned int* mine = cm.peer_flags[cm.rank] + (cm.group * 2 + phase) * kMaxRanks;
-  for (int r = 0; r < cm.world; ++r) {
-    unsigned int spins = 0;
-    // steps only grow: ">=" tolerates a peer that is already one handshake ahead
-    while (static_cast<int>(ld_acquire_sys(mine + r) - epoch) < 0) {
-      if (++spins > (1u << 28)) {
-        printf("oprl: rank %d timed out waiting for rank %d (group %d phase %d epoch %u)\n", cm.rank, r, cm.group,
-               phase, epoch);
-        __trap();
-      }
+  unsigned int spins = 0;
+  // steps only grow: ">=" tolerates a peer that is already one handshake ahead
+  while (static_cast<int>(ld_acquire_sys(mine + r) - epoch) < 0) {
+    if (++spins > (1u << 28)) {
+      printf("oprl: rank %d timed out waiting for rank %d (group %d phase %d epoch %u)\n", cm.rank, r, cm.group,
+             phase, epoch);
+      __trap();
     }
   }
 }
@@ -426,9 +425,9 @@ __global__ void __launch_bounds__(kAdamThreads)
   const bool reduce = cm.world > 1 && (mode & 1);
   const unsigned int epoch = static_cast<unsigned int>(st->step[sg.opt]);
   if (reduce) {
-    if (threadIdx.x == 0) {
-      if (blockIdx.x == 0) comm_signal(cm, 0, epoch);
-      comm_wait(cm, 0, epoch);
+    if (static_cast<int>(threadIdx.x) < cm.world) {
+      if (blockIdx.x == 0) comm_signal(cm, 0, epoch, threadIdx.x);
+      comm_wait(cm, 0, epoch, threadIdx.x);
     }
     __syncthreads();
   }
@@ -443,8 +442,15 @@ __global__ void __launch_bounds__(kAdamThreads)
     if (mode & 1) {
       float g;
       if (reduce) {
+        // every rank's copy of this element is requested before the first add: one NVLink round
+        // trip instead of world - 1 dependent ones; the sum itself stays in rank order
+        float gr[kMaxRanks];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r) gr[r] = r < cm.world ? cm.peer_grad[r][sg.goff + i] : 0.f;
         g = 0.f;
-        for (int r = 0; r < cm.world; ++r) g += cm.peer_grad[r][sg.goff + i];
+#pragma unroll
+        for (int r = 0; r < kMaxRanks; ++r)
+          if (r < cm.world) g += gr[r];
       } else {
         g = sg.grad[i];
       }
@@ -505,8 +511,8 @@ __global__ void __launch_bounds__(kAdamThreads)
       __threadfence();
       if (atomicAdd(cm.done_counter, 1u) == gridDim.x - 1) {
         *cm.done_counter = 0u;
-        comm_signal(cm, 1, epoch);
-        comm_wait(cm, 1, epoch);
+        for (int r = 0; r < cm.world; ++r) comm_signal(cm, 1, epoch, r);
+        for (int r = 0; r < cm.world; ++r) comm_wait(cm, 1, epoch, r);
       }
     }
   }
