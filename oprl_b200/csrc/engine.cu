@@ -173,7 +173,9 @@ struct oprl_engine {
   static constexpr int kHostSlots = 4;
   float* h_stage[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t h_stage_done[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
-  float* d_stage = nullptr;
+  float* d_stage[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};  // device mirrors of the pinned slots
+  cudaEvent_t h2d_done[kHostSlots] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;  // H2D of the next step's batch runs beside the current update
   size_t stage_floats = 0;
   int stage_next = 0;
   int ext_mask = 0;
@@ -1270,7 +1272,10 @@ void oprl_engine_destroy(oprl_engine* e) {
   for (int i = 0; i < oprl_engine::kHostSlots; ++i) {
     if (e->h_stage[i]) cudaFreeHost(e->h_stage[i]);
     if (e->h_stage_done[i]) cudaEventDestroy(e->h_stage_done[i]);
+    if (e->d_stage[i]) cudaFree(e->d_stage[i]);
+    if (e->h2d_done[i]) cudaEventDestroy(e->h2d_done[i]);
   }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   if (e->d_prefix) cudaFree(e->d_prefix);
   cudaStreamDestroy(e->own_stream);
   delete e;
@@ -1419,7 +1424,12 @@ int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const f
       CU(cudaMallocHost(&p, n * sizeof(float)));
       e->h_stage[i] = static_cast<float*>(p);
       if (!e->h_stage_done[i]) CU(cudaEventCreateWithFlags(&e->h_stage_done[i], cudaEventDisableTiming));
+      if (!e->h2d_done[i]) CU(cudaEventCreateWithFlags(&e->h2d_done[i], cudaEventDisableTiming));
+      if (e->d_stage[i]) CU(cudaFree(e->d_stage[i]));
+      CU(cudaMalloc(&p, n * sizeof(float)));
+      e->d_stage[i] = static_cast<float*>(p);
     }
+    if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     e->stage_floats = n;
   }
   // one pinned slot per in-flight step: pack the five host arrays, one H2D copy
@@ -1433,9 +1443,19 @@ int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const f
   memcpy(h + ns + na, r, static_cast<size_t>(B) * 4);
   memcpy(h + ns + na + B, d, static_cast<size_t>(B) * 4);
   memcpy(h + ns + na + 2 * B, s2, ns * 4);
-  // zero-copy: the dense-load kernel reads the pinned slot straight over PCIe (57 KB: ~3 us) -- one
-  // launch instead of a DMA + a launch; the slot is reusable once that kernel has run
-  const int rc = oprl_load_batch(e, h, h + ns, h + ns + na, h + ns + na + B, h + ns + na + 2 * B, B);
+  // The packed slot goes to its device mirror on the copy stream -- beside whatever update is still
+  // running on the launch stream -- and the dense-load kernel reads HBM.  (OPRL_B200_ZEROCOPY=1: the
+  // kernel reads the pinned slot straight over PCIe instead: one launch less, but ~10 us of PCIe read
+  // latency inside every step's chain.)  Slot and mirror are reusable once that kernel has run.
+  static const bool zero_copy = getenv("OPRL_B200_ZEROCOPY") && atoi(getenv("OPRL_B200_ZEROCOPY")) != 0;
+  const float* src = h;
+  if (!zero_copy) {
+    CU(cudaMemcpyAsync(e->d_stage[slot], h, n * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    CU(cudaEventRecord(e->h2d_done[slot], e->copy_stream));
+    CU(cudaStreamWaitEvent(e->stream, e->h2d_done[slot], 0));
+    src = e->d_stage[slot];
+  }
+  const int rc = oprl_load_batch(e, src, src + ns, src + ns + na, src + ns + na + B, src + ns + na + 2 * B, B);
   CU(cudaEventRecord(e->h_stage_done[slot], e->stream));
   return rc;
   API_END

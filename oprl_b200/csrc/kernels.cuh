@@ -419,9 +419,11 @@ __global__ void __launch_bounds__(kAdamThreads)
   ptx::pdl_trigger();
   // block -> (tensor, first element): one block per 256 consecutive elements of one tensor, so the
   // grid holds no idle blocks (a [6] bias does not get the grid width of a [256 x 256] weight)
+  // both tables are written by the host when the program is built, never by a kernel: read them
+  // (two dependent L2 round trips) before waiting for the previous launch, not after
   const int2 bt = blocks[blockIdx.x];
-  ptx::pdl_wait();
   const AdamSeg sg = segs[bt.x];
+  ptx::pdl_wait();
   const bool reduce = cm.world > 1 && (mode & 1);
   const unsigned int epoch = static_cast<unsigned int>(st->step[sg.opt]);
   if (reduce) {

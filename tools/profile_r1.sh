@@ -2,7 +2,7 @@
 # Profiling pass (run under gpurun from the repo root; ONE GPU):
 #   1. launch list of one short bench run (cold-cache, serialised -> compare SHARES, not absolutes),
 #   2. the same with caches left warm (--cache-control none),
-#   3. one --set full capture of the 11 grouped-GEMM launches of one DDPG update and of the SIMT kernels,
+#   3. one --set full capture of the 12 grouped-GEMM launches of one DDPG update and of the SIMT kernels,
 #   4. the in-situ stage costs (tools/stage_profile.py, not under ncu).
 # Summaries are cut here (ncu is on the box) so only small CSVs travel back.
 set -x
@@ -14,7 +14,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 320 -c 160 --csv \
     --log-file gpurun_out/${TAG}_launches_ddpg_b256.csv $B > gpurun_out/bench_under_ncu.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 320 -c 160 --csv \
     --log-file gpurun_out/${TAG}_launches_ddpg_b256_warm.csv $B > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 110 -c 11 \
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 120 -c 12 \
     -o gpurun_out/gemm_${TAG} -f $B > gpurun_out/ncu_gemm.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"gather_kernel|critic_head_kernel|adam_kernel" -s 40 -c 4 \
     -o gpurun_out/simt_${TAG} -f $B > gpurun_out/ncu_simt.log 2>&1
