@@ -193,7 +193,9 @@ def run_engine(args):
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(stream)
+        t_host0 = time.perf_counter()
         learner_steps(args.steps)
+        host_enqueue_us = (time.perf_counter() - t_host0) / args.steps * 1e6  # host time to ENQUEUE one step
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -321,6 +323,7 @@ def run_engine(args):
                 "blocking_read_every_step": world * e2e_steps / (e2e_sync_ms * 1e-3)},
         "api_loop": {"value": world * api_steps / (api_ms * 1e-3), "unit": "updates/s",
                      "what": "buffer.sample(B) (host index draw, 2 KB H2D) ; algo.update(*batch) -- no per-step sync"},
+        "host_enqueue_us_per_step": host_enqueue_us,
         "gpu_launches": int(round(launches_per_update * args.steps)),
         "launches_per_update": launches_per_update,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",

@@ -141,8 +141,14 @@ class OffPolicyAlgorithm:
         ``batch = buffer.sample(B); algo.update(*batch)``, distrib/policy_update_worker.py:66-68,
         without the host round trip): uniform index draw on the GPU from the attached buffer,
         gather, update.  Needs ``attach_buffer`` + ``engine.set_prefix``."""
-        self.engine.sample(batch_size, None)
-        self._run_update(self._wants_actor_step())
+        eng = self.engine
+        if getattr(self, "_dp_group", None) is None or eng.fused_comm:
+            # one C call: in a steady loop the gather of the NEXT step already ran as a parallel branch
+            # of this step's update graph (oprl_step), so nothing sits between two update graphs
+            eng.step(batch_size, self._wants_actor_step())
+        else:
+            eng.sample(batch_size, None)
+            self._run_update(self._wants_actor_step())
         self._after_update()
 
     def _after_update(self) -> None:

@@ -120,6 +120,7 @@ struct Stage {
   std::vector<std::function<void(cudaStream_t)>> simt;
   std::vector<int> simt_launches;  // kernels each SIMT entry launches
   int segment = 0;
+  bool bumps_tick = false;  // holds the loss kernel that advances DevState::tick
   void add_simt(std::function<void(cudaStream_t)> f, int n_launches = 1) {
     simt.push_back(std::move(f));
     simt_launches.push_back(n_launches);
@@ -130,7 +131,8 @@ struct Program {
   int B = 0, Bp = 0;
   int flags = 0;
   std::vector<Stage> stages;
-  cudaGraphExec_t graph[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] segments, [3] all, [4] GEMM launches only, [5] SIMT launches only (profiling)
+  cudaGraphExec_t graph[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] segments, [3] all, [4] GEMM launches only, [5] SIMT launches only (profiling), [6] all + the next step's gather as a parallel branch (oprl_step)
+  unsigned long long step_key = 0;  // replay binding the gather of graph[6] was captured with
   int n_gemm_launches = 0;
   int n_launches = 0;
 };
@@ -180,6 +182,23 @@ struct oprl_engine {
   int stage_next = 0;
   int ext_mask = 0;
   int cur_B = 0;
+  // Double-buffered working sets: every batch load (sample / load_batch*) goes into the working set
+  // of the other parity than the one the last update consumed.  Loads that touch nothing the caller
+  // can see (device-side sampling in oprl_step, host batches) run on `copy_stream`, beside the update
+  // that is still executing on the launch stream; Work::ev_free / ev_ready order the two streams.
+  int cur_par = 0;
+  bool rb_dirty = true;   // replay storage / prefix changed since the last gather: order the next one behind it
+  bool overlap = true;    // OPRL_B200_PREFETCH=0 turns the side-stream loads off
+  unsigned long long host_tick = 0;  // updates launched so far (== DevState::tick once they have run)
+  // oprl_step in a steady loop: the NEXT step's gather is a parallel branch of the update graph (behind
+  // the loss kernel that advances the tick), so no gather launch and no cross-stream event sits
+  // between two consecutive update graphs
+  cudaStream_t cap_side = nullptr;
+  cudaEvent_t cap_fork = nullptr, cap_join = nullptr;
+  bool prefetch_valid = false;  // the other working set holds the batch of the next oprl_step
+  int prefetched_B = 0;
+  int stable_steps = 0;               // consecutive oprl_step calls with an unchanged replay binding
+  unsigned long long rb_epoch = 1;    // bumped by oprl_buffer_bind / oprl_buffer_set_prefix
   // fused NVLink gradient all-reduce (oprl_comm_*)
   struct Comm {
     int world = 1, rank = 0;
@@ -212,6 +231,9 @@ struct oprl_engine {
 struct oprl_engine::Work {
   int B, Bp;
   TM X, XT, Xn, Xp;
+  float *r = nullptr, *d = nullptr;  // rewards / dones of the loaded batch (read by the loss kernels)
+  cudaEvent_t ev_ready = nullptr;    // the load into this working set has finished (side stream)
+  cudaEvent_t ev_free = nullptr;     // the last launch-stream work that touches this working set
   int* d_idx = nullptr;      // [B][2]
   float* noise_raw[2] = {nullptr, nullptr};
   float* noise_out[2] = {nullptr, nullptr};
@@ -586,7 +608,7 @@ static void add_critic_head(oprl_engine* e, Builder& b, int stage, int mode, int
       dz2T[i] = TM{nullptr, 0, 0};
     }
   }
-  a.r = e->br; a.d = e->bd; a.logp2 = logp2; a.logp = logp;
+  a.r = b.w->r; a.d = b.w->d; a.logp2 = logp2; a.logp = logp;
   const int blocks = (B + kHeadRows - 1) / kHeadRows;
   a.part = e->alloc_floats(static_cast<size_t>(blocks) * (nq * 2 * H + 8));
   a.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
@@ -598,6 +620,7 @@ static void add_critic_head(oprl_engine* e, Builder& b, int stage, int mode, int
   b.stage(stage).add_simt([a, st, blocks, threads, smem](cudaStream_t sm) {
     launch_k(critic_head_kernel, dim3(blocks), dim3(threads), smem, sm, a, st);
   });
+  if (mode == 0) b.stage(stage).bumps_tick = true;
 }
 
 static void fill_constant_seed(oprl_engine* e, const TM& D, int B, int ncols, float value) {
@@ -689,7 +712,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   // TD target + MSE seeds                        (ddpg.py:95-98, td3.py:105-112)
   TdArgs td;
   memset(&td, 0, sizeof(td));
-  td.qn = qn; td.q = q; td.r = e->br; td.d = e->bd;
+  td.qn = qn; td.q = q; td.r = w->r; td.d = w->d;
   td.gamma = static_cast<float>(c.gamma);
   td.inv_count = inv_count;
   td.B = B; td.nq = nq;
@@ -702,6 +725,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   {
     DevState* st = e->d_state;
     b.stage(s).add_simt([td, st](cudaStream_t sm) { launch_k(td_kernel, dim3(1), dim3(kTdThreads), 0, sm, td, st); });
+    b.stage(s).bumps_tick = true;
     ++s;
   }
   // critic backward
@@ -897,7 +921,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   } else if (!tqc) {
     TdArgs td;
     memset(&td, 0, sizeof(td));
-    td.qn = zn; td.q = z; td.r = e->br; td.d = e->bd; td.logpi_next = logp2;
+    td.qn = zn; td.q = z; td.r = w->r; td.d = w->d; td.logpi_next = logp2;
     td.gamma = static_cast<float>(c.gamma);
     td.inv_count = inv_count;
     td.B = B; td.nq = nc;
@@ -908,10 +932,11 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
       td.db3[i] = gc.grad + gc.nets[i].L.back().b_off;
     }
     b.stage(s).add_simt([td, st](cudaStream_t sm) { launch_k(td_kernel, dim3(1), dim3(kTdThreads), 0, sm, td, st); });
+    b.stage(s).bumps_tick = true;
   } else {
     TqcArgs t;
     memset(&t, 0, sizeof(t));
-    t.zn = zn; t.z = z; t.r = e->br; t.d = e->bd; t.logp2 = logp2;
+    t.zn = zn; t.z = z; t.r = w->r; t.d = w->d; t.logp2 = logp2;
     t.gamma = static_cast<float>(c.gamma);
     t.keep = NT - c.top_quantiles_to_drop;
     t.inv_total = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size * NT * t.keep));
@@ -926,6 +951,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     t.loss_part = e->alloc_floats(Bp);
     t.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
     b.stage(s).add_simt([t, st, B](cudaStream_t sm) { launch_k(tqc_loss_kernel, dim3(B), dim3(kTqcThreads), 0, sm, t, st); });
+    b.stage(s).bumps_tick = true;
   }
   ++s;
   {
@@ -1062,8 +1088,10 @@ static void launch_gemm_ops(oprl_engine* e, const std::vector<GemmOp>& ops, cuda
 }
 
 static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, bool gemm_only = false,
-                      bool simt_only = false, int max_stages = 1 << 30) {
+                      bool simt_only = false, int max_stages = 1 << 30,
+                      const std::function<void()>& after_tick_bump = nullptr) {
   int n = 0;
+  bool forked = false;
   for (auto& sg : p->stages) {
     if (segment >= 0 && sg.segment != segment) continue;
     if (max_stages-- <= 0) break;
@@ -1076,6 +1104,10 @@ static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, 
         sg.simt[i](st);
         n += sg.simt_launches[i];
       }
+    if (sg.bumps_tick && after_tick_bump && !forked) {
+      after_tick_bump();
+      forked = true;
+    }
   }
   return n;
 }
@@ -1118,8 +1150,9 @@ static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
   return raw;
 }
 
-static oprl_engine::Work* get_work(oprl_engine* e, int B) {
-  auto it = e->work.find(B);
+static oprl_engine::Work* get_work(oprl_engine* e, int B, int par = -1) {
+  if (par < 0) par = e->cur_par;
+  auto it = e->work.find(2 * B + par);
   if (it != e->work.end()) return it->second.get();
   const oprl_cfg& c = e->cfg;
   std::unique_ptr<oprl_engine::Work> w(new oprl_engine::Work);
@@ -1131,6 +1164,10 @@ static oprl_engine::Work* get_work(oprl_engine* e, int B) {
   w->Xp = e->alloc_tm(Bp, e->Kin);
   w->XT = e->alloc_tm(e->Kin, Bp);
   w->d_idx = reinterpret_cast<int*>(e->alloc_floats(static_cast<size_t>(Bp) * 2));
+  w->r = e->alloc_floats(Bp);
+  w->d = e->alloc_floats(Bp);
+  CU(cudaEventCreateWithFlags(&w->ev_ready, cudaEventDisableTiming));
+  CU(cudaEventCreateWithFlags(&w->ev_free, cudaEventDisableTiming));
   const size_t nz = static_cast<size_t>(Bp) * c.action_dim;
   for (int k = 0; k < 2; ++k) {
     w->noise_raw[k] = e->alloc_floats(nz);
@@ -1144,7 +1181,6 @@ static oprl_engine::Work* get_work(oprl_engine* e, int B) {
     e->bd = e->alloc_floats(Bp);
     e->bs2 = e->alloc_floats(static_cast<size_t>(Bp) * c.state_dim);
     e->batch_cap = Bp;
-    for (auto& kv : e->work) kv.second->prog.clear();  // programs bake br / bd pointers
   }
   GatherArgs& g = w->gather;
   memset(&g, 0, sizeof(g));
@@ -1163,17 +1199,57 @@ static oprl_engine::Work* get_work(oprl_engine* e, int B) {
     g.noise[k].scale = (c.algo == OPRL_ALGO_TD3) ? static_cast<float>(c.policy_noise) : 1.f;
     g.noise[k].clip = (c.algo == OPRL_ALGO_TD3) ? static_cast<float>(c.noise_clip) : 0.f;
   }
+  g.wr = w->r;
+  g.wd = w->d;
+  // the zero-fills above were queued on the launch stream; the first load into this working set may
+  // run on the copy stream -- it must not be overtaken by them (once per working set)
+  CU(cudaStreamSynchronize(e->stream));
   oprl_engine::Work* raw = w.get();
-  e->work[B] = std::move(w);
+  e->work[2 * B + par] = std::move(w);
   return raw;
 }
 
-static void launch_gather(oprl_engine* e, oprl_engine::Work* w, GatherArgs g) {
-  g.bs = e->bs; g.ba = e->ba; g.br = e->br; g.bd = e->bd; g.bs2 = e->bs2;
+// Begin a batch load: picks the working set of the other parity and the stream the load runs on.
+// side = true: on the copy stream, ordered only behind the last launch-stream work that touched that
+// working set (so it overlaps the update in flight); side = false: on the launch stream.
+static oprl_engine::Work* begin_load(oprl_engine* e, int B, bool side, cudaStream_t* st) {
+  const int par = e->cur_par ^ 1;
+  oprl_engine::Work* w = get_work(e, B, par);
+  e->prefetch_valid = false;  // this load overwrites whatever was prefetched into that working set
+  if (side) {
+    if (!e->copy_stream) CU(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    CU(cudaStreamWaitEvent(e->copy_stream, w->ev_free, 0));
+    *st = e->copy_stream;
+  } else {
+    *st = e->stream;
+  }
+  return w;
+}
+static void end_load(oprl_engine* e, oprl_engine::Work* w, int B, bool side) {
+  if (side) {
+    CU(cudaEventRecord(w->ev_ready, e->copy_stream));
+    CU(cudaStreamWaitEvent(e->stream, w->ev_ready, 0));  // whatever the caller launches next sees the batch
+  } else {
+    CU(cudaEventRecord(w->ev_free, e->stream));
+  }
+  e->cur_par ^= 1;
+  e->cur_B = B;
+  e->ext_mask = 0;
+}
+
+static void launch_gather(oprl_engine* e, oprl_engine::Work* w, GatherArgs g, cudaStream_t st, bool arena,
+                          bool in_graph = false) {
+  if (arena) { g.bs = e->bs; g.ba = e->ba; g.br = e->br; g.bd = e->bd; g.bs2 = e->bs2; }
+  g.tick = e->host_tick;
+  g.ext = e->ext_mask;
+  if (in_graph) {  // replayed every step: the tick comes from the device counter, never injected noise
+    g.dev_tick = 1;
+    g.ext = 0;
+  }
   const int total = g.noise[0].n + g.noise[1].n;
   const int nblocks = total ? std::min((total + kGatherBlock * 4 - 1) / (kGatherBlock * 4), 64) : 0;
   const int row_blocks = (g.B + kGatherRows - 1) / kGatherRows;
-  gather_kernel<<<row_blocks + nblocks, kGatherBlock, 0, e->stream>>>(g, e->d_state);
+  gather_kernel<<<row_blocks + nblocks, kGatherBlock, 0, st>>>(g, e->d_state);
   CU(cudaGetLastError());
 }
 
@@ -1218,6 +1294,7 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   e->cfg = *cfg;
   e->n_sm = prop.multiProcessorCount;
   if (const char* v = getenv("OPRL_B200_PDL")) g_pdl = atoi(v) != 0;
+  if (const char* v = getenv("OPRL_B200_PREFETCH")) e->overlap = atoi(v) != 0;
   if (e->cfg.world_size < 1) e->cfg.world_size = 1;
   CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   e->stream = e->own_stream;
@@ -1257,9 +1334,14 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
 void oprl_engine_destroy(oprl_engine* e) {
   if (!e) return;
   cudaStreamSynchronize(e->stream);
+  if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+  for (auto& kv : e->work) {
+    if (kv.second->ev_ready) cudaEventDestroy(kv.second->ev_ready);
+    if (kv.second->ev_free) cudaEventDestroy(kv.second->ev_free);
+  }
   for (auto& kv : e->work)
     for (auto& pv : kv.second->prog)
-      for (int k = 0; k < 6; ++k)
+      for (int k = 0; k < 7; ++k)
         if (pv.second->graph[k]) cudaGraphExecDestroy(pv.second->graph[k]);
   for (void* p : e->comm.opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->blocks) cudaFree(p);
@@ -1276,6 +1358,11 @@ void oprl_engine_destroy(oprl_engine* e) {
     if (e->h2d_done[i]) cudaEventDestroy(e->h2d_done[i]);
   }
   if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+  if (e->cap_side) {
+    cudaStreamDestroy(e->cap_side);
+    cudaEventDestroy(e->cap_fork);
+    cudaEventDestroy(e->cap_join);
+  }
   if (e->d_prefix) cudaFree(e->d_prefix);
   cudaStreamDestroy(e->own_stream);
   delete e;
@@ -1319,6 +1406,8 @@ int oprl_buffer_bind(oprl_engine* e, const float* states, const float* actions, 
   e->rb_states = states; e->rb_actions = actions; e->rb_rewards = rewards; e->rb_dones = dones;
   e->rb_E = E; e->rb_L = L;
   for (auto& kv : e->work) kv.second->gather.L = L;
+  e->rb_dirty = true;
+  e->rb_epoch += 1;
   return 0;
 }
 
@@ -1328,6 +1417,7 @@ int oprl_buffer_set_prefix(oprl_engine* e, const int* prefix_host, int n_eps) {
   if (n_eps + 1 > e->prefix_cap) {
     if (e->d_prefix) {
       CU(cudaStreamSynchronize(e->stream));
+      if (e->copy_stream) CU(cudaStreamSynchronize(e->copy_stream));  // a prefetching gather may still read it
       CU(cudaFree(e->d_prefix));
     }
     e->prefix_cap = std::max(1024, 2 * (n_eps + 1));
@@ -1338,6 +1428,8 @@ int oprl_buffer_set_prefix(oprl_engine* e, const int* prefix_host, int n_eps) {
   CU(cudaMemcpyAsync(e->d_prefix, prefix_host, sizeof(int) * (n_eps + 1), cudaMemcpyHostToDevice, e->stream));
   e->n_eps = n_eps;
   e->n_trans = prefix_host[n_eps];
+  e->rb_dirty = true;
+  e->rb_epoch += 1;
   return 0;
   API_END
 }
@@ -1350,64 +1442,78 @@ int oprl_batch_bind(oprl_engine* e, float* s, float* a, float* r, float* d, floa
   return 0;
 }
 
-static int push_ext_mask(oprl_engine* e) {
-  API_BEGIN
-  if (e->ext_mask) {
-    *e->h_flag = e->ext_mask;
-    CU(cudaMemcpyAsync(&e->d_state->ext_noise, e->h_flag, sizeof(int), cudaMemcpyHostToDevice, e->stream));
-    e->ext_mask = 0;
-  }
-  return 0;
-  API_END
-}
 
-int oprl_sample(oprl_engine* e, const int* ep_step_host, int B) {
+// side: run the gather on the copy stream, beside the update in flight (device-side draw only, and
+// nothing written that the caller can see)
+static int sample_impl(oprl_engine* e, const int* ep_step_host, int B, bool side) {
   if (!e || B <= 0) return fail(-1, "bad sample call");
   if (!e->rb_states) return fail(-1, "no replay storage bound");
   if (e->batch_cap && B > e->batch_cap) return fail(-1, "B=%d exceeds the bound batch arena (%d)", B, e->batch_cap);
   API_BEGIN
-  oprl_engine::Work* w = get_work(e, B);
-  if (int rc = push_ext_mask(e)) return rc;
-  GatherArgs g = w->gather;
-  g.states = e->rb_states; g.actions = e->rb_actions; g.rewards = e->rb_rewards; g.dones = e->rb_dones;
-  g.L = e->rb_L;
-  g.dense = 0;
   if (ep_step_host) {
     for (int i = 0; i < B; ++i) {
       const int ep = ep_step_host[2 * i], st = ep_step_host[2 * i + 1];
       if (ep < 0 || ep >= e->rb_E || st < 0 || st >= e->rb_L)
         return fail(-1, "index %d out of range: episode %d step %d", i, ep, st);
     }
-    CU(cudaMemcpyAsync(w->d_idx, ep_step_host, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, e->stream));
+  } else if (!e->d_prefix || e->n_trans <= 0) {
+    return fail(-1, "device sampling needs oprl_buffer_set_prefix");
+  }
+  // replay rows / prefix sums written since the last gather, or injected noise copied on the launch
+  // stream: this gather must be ordered behind them
+  side = side && e->overlap && !ep_step_host && !e->rb_dirty && !e->ext_mask;
+  cudaStream_t st;
+  oprl_engine::Work* w = begin_load(e, B, side, &st);
+  GatherArgs g = w->gather;
+  g.states = e->rb_states; g.actions = e->rb_actions; g.rewards = e->rb_rewards; g.dones = e->rb_dones;
+  g.L = e->rb_L;
+  g.dense = 0;
+  if (ep_step_host) {
+    CU(cudaMemcpyAsync(w->d_idx, ep_step_host, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, st));
     g.ep_step = w->d_idx;
   } else {
-    if (!e->d_prefix || e->n_trans <= 0) return fail(-1, "device sampling needs oprl_buffer_set_prefix");
     g.ep_step = nullptr;
     g.prefix = e->d_prefix;
     g.n_eps = e->n_eps;
     g.n_trans = e->n_trans;
     g.out_ep_step = w->d_idx;
   }
-  launch_gather(e, w, g);
-  e->cur_B = B;
+  launch_gather(e, w, g, st, !side);
+  end_load(e, w, B, side);
+  e->rb_dirty = false;
+  return 0;
+  API_END
+}
+
+int oprl_sample(oprl_engine* e, const int* ep_step_host, int B) { return sample_impl(e, ep_step_host, B, false); }
+
+// side: the sources are engine-owned device mirrors already ordered on the copy stream
+static int load_batch_impl(oprl_engine* e, const float* s, const float* a, const float* r, const float* d,
+                           const float* s2, int B, bool side) {
+  if (!e || !s || !a || !r || !d || !s2 || B <= 0) return fail(-1, "bad batch");
+  API_BEGIN
+  if (e->batch_cap && B > e->batch_cap) return fail(-1, "B=%d exceeds the bound batch arena (%d)", B, e->batch_cap);
+  side = side && e->overlap && !e->ext_mask;
+  cudaStream_t st;
+  oprl_engine::Work* w = begin_load(e, B, side, &st);
+  if (!side && e->copy_stream) {
+    // sources staged on the copy stream (host batches with the side path switched off for this call)
+    cudaEvent_t ev = w->ev_ready;
+    CU(cudaEventRecord(ev, e->copy_stream));
+    CU(cudaStreamWaitEvent(e->stream, ev, 0));
+  }
+  GatherArgs g = w->gather;
+  g.states = s; g.actions = a; g.rewards = r; g.dones = d; g.next_states = s2;
+  g.dense = 1;
+  launch_gather(e, w, g, st, !side);
+  end_load(e, w, B, side);
   return 0;
   API_END
 }
 
 int oprl_load_batch(oprl_engine* e, const float* s, const float* a, const float* r, const float* d,
                     const float* s2, int B) {
-  if (!e || !s || !a || !r || !d || !s2 || B <= 0) return fail(-1, "bad batch");
-  API_BEGIN
-  oprl_engine::Work* w = get_work(e, B);
-  if (B > e->batch_cap) return fail(-1, "B=%d exceeds the bound batch arena (%d)", B, e->batch_cap);
-  if (int rc = push_ext_mask(e)) return rc;
-  GatherArgs g = w->gather;
-  g.states = s; g.actions = a; g.rewards = r; g.dones = d; g.next_states = s2;
-  g.dense = 1;
-  launch_gather(e, w, g);
-  e->cur_B = B;
-  return 0;
-  API_END
+  return load_batch_impl(e, s, a, r, d, s2, B, false);
 }
 
 int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const float* r, const float* d,
@@ -1418,6 +1524,7 @@ int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const f
   const size_t n = static_cast<size_t>(B) * (2 * S + A + 2);
   if (n > e->stage_floats) {
     CU(cudaStreamSynchronize(e->stream));
+    if (e->copy_stream) CU(cudaStreamSynchronize(e->copy_stream));
     for (int i = 0; i < oprl_engine::kHostSlots; ++i) {
       if (e->h_stage[i]) CU(cudaFreeHost(e->h_stage[i]));
       void* p;
@@ -1443,20 +1550,20 @@ int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const f
   memcpy(h + ns + na, r, static_cast<size_t>(B) * 4);
   memcpy(h + ns + na + B, d, static_cast<size_t>(B) * 4);
   memcpy(h + ns + na + 2 * B, s2, ns * 4);
-  // The packed slot goes to its device mirror on the copy stream -- beside whatever update is still
-  // running on the launch stream -- and the dense-load kernel reads HBM.  (OPRL_B200_ZEROCOPY=1: the
-  // kernel reads the pinned slot straight over PCIe instead: one launch less, but ~10 us of PCIe read
-  // latency inside every step's chain.)  Slot and mirror are reusable once that kernel has run.
+  // The packed slot goes to its device mirror on the copy stream and the dense-load kernel follows it
+  // there -- both beside whatever update is still running on the launch stream (the working sets are
+  // double-buffered).  OPRL_B200_ZEROCOPY=1: the load kernel reads the pinned slot straight over PCIe
+  // on the launch stream instead (one operation less, ~10 us of PCIe read latency inside every step).
   static const bool zero_copy = getenv("OPRL_B200_ZEROCOPY") && atoi(getenv("OPRL_B200_ZEROCOPY")) != 0;
   const float* src = h;
   if (!zero_copy) {
     CU(cudaMemcpyAsync(e->d_stage[slot], h, n * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
-    CU(cudaEventRecord(e->h2d_done[slot], e->copy_stream));
-    CU(cudaStreamWaitEvent(e->stream, e->h2d_done[slot], 0));
     src = e->d_stage[slot];
   }
-  const int rc = oprl_load_batch(e, src, src + ns, src + ns + na, src + ns + na + B, src + ns + na + 2 * B, B);
-  CU(cudaEventRecord(e->h_stage_done[slot], e->stream));
+  const bool side = !zero_copy && e->overlap && !e->ext_mask;
+  const int rc = load_batch_impl(e, src, src + ns, src + ns + na, src + ns + na + B, src + ns + na + 2 * B, B, !zero_copy);
+  // slot and mirror are reusable once the load kernel has run
+  CU(cudaEventRecord(e->h_stage_done[slot], side ? e->copy_stream : e->stream));
   return rc;
   API_END
 }
@@ -1466,7 +1573,7 @@ int oprl_set_noise(oprl_engine* e, int which, const float* noise_dev, int n) {
   const int A = e->cfg.action_dim;
   if (n <= 0 || n % A) return fail(-1, "noise length %d is not a multiple of action_dim", n);
   API_BEGIN
-  oprl_engine::Work* w = get_work(e, n / A);
+  oprl_engine::Work* w = get_work(e, n / A, e->cur_par ^ 1);  // the working set the next load fills
   CU(cudaMemcpyAsync(w->noise_raw[which], noise_dev, sizeof(float) * n, cudaMemcpyDeviceToDevice, e->stream));
   e->ext_mask |= 1 << which;
   return 0;
@@ -1486,16 +1593,96 @@ int oprl_update(oprl_engine* e, int flags, int segment) {
   static const bool no_graph = getenv("OPRL_B200_NOGRAPH") && atoi(getenv("OPRL_B200_NOGRAPH")) != 0;
   if (no_graph) {
     run_stages(e, p, segment < 0 ? -1 : segment, e->stream);
-    return 0;
+  } else {
+    cudaGraphExec_t g = p->graph[segment < 0 ? 3 : segment];
+    if (g) CU(cudaGraphLaunch(g, e->stream));
   }
-  cudaGraphExec_t g = p->graph[segment < 0 ? 3 : segment];
-  if (g) CU(cudaGraphLaunch(g, e->stream));
+  CU(cudaEventRecord(w->ev_free, e->stream));
+  if (segment <= 0) e->host_tick += 1;  // the loss kernel of segment 0 advances DevState::tick
   return 0;
   API_END
 }
 
+// The update graph of working set `w` with the gather of the next step (device-side draw into `wn`)
+// as a parallel branch forked behind the loss kernel.  Re-captured when the replay binding changed.
+static cudaGraphExec_t get_step_graph(oprl_engine* e, oprl_engine::Work* w, oprl_engine::Work* wn, Program* p) {
+  if (p->graph[6] && p->step_key == e->rb_epoch) return p->graph[6];
+  if (p->graph[6]) {
+    CU(cudaStreamSynchronize(e->stream));
+    CU(cudaGraphExecDestroy(p->graph[6]));
+    p->graph[6] = nullptr;
+  }
+  if (!e->cap_side) {
+    CU(cudaStreamCreateWithFlags(&e->cap_side, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&e->cap_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&e->cap_join, cudaEventDisableTiming));
+  }
+  GatherArgs g = wn->gather;
+  g.states = e->rb_states; g.actions = e->rb_actions; g.rewards = e->rb_rewards; g.dones = e->rb_dones;
+  g.L = e->rb_L;
+  g.dense = 0;
+  g.ep_step = nullptr;
+  g.prefix = e->d_prefix;
+  g.n_eps = e->n_eps;
+  g.n_trans = e->n_trans;
+  g.out_ep_step = wn->d_idx;
+  CU(cudaStreamSynchronize(e->stream));  // workspace memsets of a freshly created working set
+  cudaGraph_t graph = nullptr;
+  bool forked = false;
+  CU(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
+  try {
+    run_stages(e, p, -1, e->own_stream, false, false, 1 << 30, [&]() {
+      CU(cudaEventRecord(e->cap_fork, e->own_stream));
+      CU(cudaStreamWaitEvent(e->cap_side, e->cap_fork, 0));
+      launch_gather(e, wn, g, e->cap_side, false, true);
+      CU(cudaEventRecord(e->cap_join, e->cap_side));
+      forked = true;
+    });
+    if (forked) CU(cudaStreamWaitEvent(e->own_stream, e->cap_join, 0));
+  } catch (...) {
+    cudaStreamEndCapture(e->own_stream, &graph);
+    if (graph) cudaGraphDestroy(graph);
+    throw;
+  }
+  CU(cudaStreamEndCapture(e->own_stream, &graph));
+  if (forked) CU(cudaGraphInstantiate(&p->graph[6], graph, 0));
+  CU(cudaGraphDestroy(graph));
+  p->step_key = e->rb_epoch;
+  return p->graph[6];
+}
+
 int oprl_step(oprl_engine* e, int B, int flags) {
-  if (int rc = oprl_sample(e, nullptr, B)) return rc;
+  if (!e || B <= 0) return fail(-1, "bad step call");
+  static const bool no_graph = getenv("OPRL_B200_NOGRAPH") && atoi(getenv("OPRL_B200_NOGRAPH")) != 0;
+  // steady loop = nothing happened since the last step that the next gather would have to be ordered
+  // behind (replay writes announced by oprl_buffer_set_prefix / _bind, injected noise)
+  const bool stable = e->overlap && !no_graph && !e->rb_dirty && !e->ext_mask && e->d_prefix && e->n_trans > 0;
+  if (e->prefetch_valid && e->prefetched_B == B && stable) {
+    e->cur_par ^= 1;  // the batch was gathered inside the previous step's graph
+    e->cur_B = B;
+  } else {
+    if (int rc = sample_impl(e, nullptr, B, true)) return rc;
+  }
+  e->prefetch_valid = false;
+  e->stable_steps = stable ? e->stable_steps + 1 : 0;
+  if (stable && e->stable_steps >= 4) {
+    for (int k = 0; k < 2; ++k)
+      if (!e->grp[k].theta) return fail(-1, "arena %d not bound", k);
+    API_BEGIN
+    oprl_engine::Work* w = get_work(e, B, e->cur_par);
+    oprl_engine::Work* wn = get_work(e, B, e->cur_par ^ 1);
+    Program* p = get_program(e, w, flags);
+    if (cudaGraphExec_t g = get_step_graph(e, w, wn, p)) {
+      CU(cudaGraphLaunch(g, e->stream));
+      CU(cudaEventRecord(w->ev_free, e->stream));
+      CU(cudaEventRecord(wn->ev_free, e->stream));
+      e->host_tick += 1;
+      e->prefetch_valid = true;
+      e->prefetched_B = B;
+      return 0;
+    }
+    API_END
+  }
   return oprl_update(e, flags, OPRL_SEG_ALL);
 }
 
@@ -1570,6 +1757,7 @@ int oprl_set_state(oprl_engine* e, const oprl_state* in) {
   API_BEGIN
   DevState& s = *e->h_state;
   s.tick = in->tick;
+  e->host_tick = in->tick;
   s.step[0] = in->step_actor;
   s.step[1] = in->step_critic;
   s.step[2] = in->step_alpha;
@@ -1760,6 +1948,11 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
   CU(cudaEventDestroy(e0));
   CU(cudaEventDestroy(e1));
   if (prefix) CU(cudaGraphExecDestroy(prefix));
+  if (what == 2 || what >= 100) {
+    // those replays ran the loss kernel (which advances DevState::tick) without oprl_update
+    if (int rc = read_state(e)) return rc;
+    e->host_tick = e->h_state->tick;
+  }
   if (launches_per_iter && what < 100) *launches_per_iter = what == 0 ? p->n_gemm_launches : 1;
   return 0;
   API_END

@@ -93,7 +93,15 @@ struct GatherArgs {
   int dense;
   unsigned long long seed;
   // outputs
-  float *bs, *ba, *br, *bd, *bs2;  // row-major batch arena (nullable when dense)
+  float *bs, *ba, *br, *bd, *bs2;  // row-major batch arena the caller sees (every pointer nullable)
+  float *wr, *wd;                   // rewards / dones of this batch as the update's kernels read them
+  // RNG stream offset = number of updates completed, and the injected-noise mask: passed by the
+  // host (which counts the updates it has launched) so that a gather running ahead of the previous
+  // update -- on another stream, into the other working set -- does not race with the device counters
+  unsigned long long tick;
+  int ext;
+  int dev_tick;  // 1: read DevState::tick instead (prefetching gather inside the update graph, placed
+                 // behind the loss kernel that advances the counter -- nobody writes it after that)
   int* out_ep_step;                 // [B][2] what was sampled (device sampling), nullable
   TM X, XT, Xn, Xp;
   NoiseSpec noise[2];  // blocks >= B draw the update's normals (n == 0: none)
@@ -109,8 +117,8 @@ __global__ void __launch_bounds__(kGatherBlock)
   if (static_cast<int>(blockIdx.x) >= row_blocks) {
     // ---- noise blocks: 4 normals per thread, one Philox subsequence per quad
     const int total = g.noise[0].n + g.noise[1].n;
-    const unsigned long long tick = st->tick;
-    const int ext = st->ext_noise;
+    const unsigned long long tick = g.dev_tick ? st->tick : g.tick;
+    const int ext = g.ext;
     const int nb = gridDim.x - row_blocks;
     for (int base = ((blockIdx.x - row_blocks) * kGatherBlock + threadIdx.x) * 4; base < total;
          base += nb * kGatherBlock * 4) {
@@ -157,7 +165,7 @@ __global__ void __launch_bounds__(kGatherBlock)
     } else {
       if (lane == 0) {
         curandStatePhilox4_32_10_t rng;
-        curand_init(g.seed ^ 0x9E3779B97F4A7C15ull, static_cast<unsigned long long>(b), st->tick * 4ull, &rng);
+        curand_init(g.seed ^ 0x9E3779B97F4A7C15ull, static_cast<unsigned long long>(b), (g.dev_tick ? st->tick : g.tick) * 4ull, &rng);
         const unsigned int u = curand(&rng);
         const int t = static_cast<int>((static_cast<unsigned long long>(u) * g.n_trans) >> 32);
         const int* pre = cached ? s_prefix : g.prefix;
@@ -218,8 +226,10 @@ __global__ void __launch_bounds__(kGatherBlock)
     }
   }
   if (lane == 0) {
-    g.br[b] = r;
-    g.bd[b] = d;
+    if (g.br) g.br[b] = r;
+    if (g.bd) g.bd[b] = d;
+    g.wr[b] = r;
+    g.wd[b] = d;
   }
 }
 

@@ -123,7 +123,7 @@ class UpdateEngine:
     def _use_current_stream(self):
         # 0 is torch's legacy default stream: name it explicitly (cudaStreamLegacy == 0x1), NULL
         # would mean "engine-owned stream" to the C ABI.
-        s = torch.cuda.current_stream(self.device).cuda_stream or 1
+        s = torch._C._cuda_getCurrentRawStream(self.device.index) or 1
         if s != self._stream_id:
             L.check(self._lib.oprl_engine_set_stream(self._h, C.c_void_p(s)))
             self._stream_id = s

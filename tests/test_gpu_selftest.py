@@ -1,0 +1,26 @@
+"""GPU: the grouped GEMM kernel on its own (tools/gemm_selftest.cu, correctness half): every product
+against a float64 host reference, tiled / transposed-tiled / row-major stores, column sums, the fused
+layer-0 weight + bias gradient epilogue (two 32-column chunks, column map, untouched pad rows), and the
+same cases with 2 and 4 CTAs per tile (split-K over clusters: even, uneven and empty chunk shares)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_gemm_selftest_passes():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    g.build()  # (re)builds build/gemm_selftest when a source is newer
+    exe = os.path.join(ROOT, "build", "gemm_selftest")
+    out = subprocess.run([exe, "0"], capture_output=True, text=True, timeout=300)
+    sys.stdout.write(out.stdout[-3000:])
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "fails=0" in out.stdout
+    assert out.stdout.count("dw0=") >= 18  # every case carried the fused epilogue
