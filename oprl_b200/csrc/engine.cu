@@ -121,6 +121,8 @@ struct Stage {
   std::vector<int> simt_launches;  // kernels each SIMT entry launches
   int segment = 0;
   bool bumps_tick = false;  // holds the loss kernel that advances DevState::tick
+  std::vector<GemmLaunch> launches;  // prepare_stage_tables: one per <= kMaxOps ops, descriptors on the device
+  std::vector<int> launch_tiles;
   void add_simt(std::function<void(cudaStream_t)> f, int n_launches = 1) {
     simt.push_back(std::move(f));
     simt_launches.push_back(n_launches);
@@ -1061,28 +1063,47 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
 // ================================================================== program execution
 namespace oprl {
 
-static void launch_gemm_ops(oprl_engine* e, const std::vector<GemmOp>& ops, cudaStream_t st) {
-  for (size_t i0 = 0; i0 < ops.size(); i0 += kMaxOps) {
-    GemmLaunch L;
-    memset(&L, 0, sizeof(L));
-    int tiles = 0;
-    L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, ops.size() - i0));
-    for (int i = 0; i < L.n_ops; ++i) {
-      L.op[i] = ops[i0 + i];
-      gemm_finalize(L.op[i]);
-      tiles += gemm_tiles(L.op[i]);
-      L.tile_end[i] = tiles;
+// Once per program, before any capture: finalize every stage's ops, pick the split-K factor of each
+// launch and upload the op descriptors to device memory (the kernels get a pointer, not 4.4 KB of
+// by-value parameters per launch).
+static void prepare_stage_tables(oprl_engine* e, Program* p) {
+  // split-K over clusters when the launch leaves most SMs idle (OPRL_B200_KSPLIT=1 turns it off, 2 / 4 cap it)
+  static const int ks_cap = getenv("OPRL_B200_KSPLIT") ? atoi(getenv("OPRL_B200_KSPLIT")) : 4;
+  for (auto& sg : p->stages) {
+    sg.launches.clear();
+    sg.launch_tiles.clear();
+    for (size_t i0 = 0; i0 < sg.ops.size(); i0 += kMaxOps) {
+      GemmLaunch L;
+      memset(&L, 0, sizeof(L));
+      int tiles = 0;
+      L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, sg.ops.size() - i0));
+      for (int i = 0; i < L.n_ops; ++i) {
+        gemm_finalize(sg.ops[i0 + i]);
+        tiles += gemm_tiles(sg.ops[i0 + i]);
+        L.tile_end[i] = tiles;
+      }
+      int ks = gemm_choose_ksplit(&sg.ops[i0], L.n_ops, e->n_sm);
+      while (ks > 1 && ks > ks_cap) ks >>= 1;
+      L.ksplit = ks;
+      GemmOp* d = reinterpret_cast<GemmOp*>(e->alloc_floats((sizeof(GemmOp) * L.n_ops + 3) / 4));
+      CU(cudaMemcpyAsync(d, &sg.ops[i0], sizeof(GemmOp) * L.n_ops, cudaMemcpyHostToDevice, e->stream));
+      L.ops = d;
+      sg.launches.push_back(L);
+      sg.launch_tiles.push_back(tiles);
     }
-    // split-K over clusters when the launch leaves most SMs idle (OPRL_B200_KSPLIT=1 turns it off, 2 / 4 cap it)
-    static const int ks_cap = getenv("OPRL_B200_KSPLIT") ? atoi(getenv("OPRL_B200_KSPLIT")) : 4;
-    int ks = gemm_choose_ksplit(L.op, L.n_ops, e->n_sm);
-    while (ks > 1 && ks > ks_cap) ks >>= 1;
-    L.ksplit = ks;
+  }
+  CU(cudaStreamSynchronize(e->stream));
+}
+
+static void launch_gemm_ops(oprl_engine* e, const Stage& sg, cudaStream_t st) {
+  for (size_t i = 0; i < sg.launches.size(); ++i) {
+    const GemmLaunch& L = sg.launches[i];
+    const int ks = L.ksplit;
     g_cluster_x = ks;
     if (e->cfg.gemm_mode == OPRL_GEMM_SIMT)
-      launch_k(gemm_kernel<true>, dim3(tiles * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
+      launch_k(gemm_kernel<true>, dim3(sg.launch_tiles[i] * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
     else
-      launch_k(gemm_kernel<false>, dim3(tiles * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
+      launch_k(gemm_kernel<false>, dim3(sg.launch_tiles[i] * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
     g_cluster_x = 1;
   }
 }
@@ -1096,7 +1117,7 @@ static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, 
     if (segment >= 0 && sg.segment != segment) continue;
     if (max_stages-- <= 0) break;
     if (!sg.ops.empty() && !simt_only) {
-      launch_gemm_ops(e, sg.ops, st);
+      launch_gemm_ops(e, sg, st);
       n += static_cast<int>((sg.ops.size() + kMaxOps - 1) / kMaxOps);
     }
     if (!gemm_only)
@@ -1123,6 +1144,7 @@ static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
   p->flags = flags;
   if (e->cfg.algo == OPRL_ALGO_DDPG || e->cfg.algo == OPRL_ALGO_TD3) build_ddpg_td3(e, w, p.get());
   else build_sac_tqc(e, w, p.get());
+  prepare_stage_tables(e, p.get());
   CU(cudaStreamSynchronize(e->stream));  // workspace memsets / constant uploads done
   // capture: one graph per segment + one for the whole update
   for (int k = 0; k < 6; ++k) {

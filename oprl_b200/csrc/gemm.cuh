@@ -151,7 +151,11 @@ struct GemmLaunch {
   int ksplit;
   int tile_end[kMaxOps];  // exclusive prefix sums of gemm_tiles(op[i])
   long long* prof;        // selftest only: per-phase clock64 stamps of CTA 0
-  GemmOp op[kMaxOps];
+  // The op descriptors (~400 B each) live in device memory, written once when the program is built:
+  // passing them by value made every GEMM node of the update graph carry 4.4 KB of kernel parameters
+  // (54 KB per graph launch to patch on the host).  Each CTA copies its descriptor into shared
+  // memory at kernel start -- before the programmatic-dependent-launch wait, the table is static.
+  const GemmOp* ops;
 };
 
 __host__ __device__ __forceinline__ int gemm_tiles(const GemmOp& o) {
@@ -224,18 +228,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   while (oi < L.n_ops && t >= L.tile_end[oi]) ++oi;
   if (oi >= L.n_ops) return;
   if (oi > 0) t -= L.tile_end[oi - 1];
-  const GemmOp& o = L.op[oi];
+  __shared__ __align__(16) GemmOp so;
   {
-    // Kernel parameters live in a constant bank that is cold at every launch: touch every
-    // 64-byte line of this op's descriptor now, all misses in flight together, instead of
-    // paying them one by one (control-dependent) in the epilogue.
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&o);
-    uint32_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < static_cast<int>(sizeof(GemmOp) / 4); i += 16) acc ^= w[i];
-    acc ^= w[sizeof(GemmOp) / 4 - 1];
-    asm volatile("" ::"r"(acc));
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(L.ops + oi);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&so);
+    for (int i = tid; i < static_cast<int>(sizeof(GemmOp) / 4); i += kGemmThreads) dst[i] = __ldg(src + i);
+    __syncthreads();
   }
+  const GemmOp& o = so;
   const int ntn = o.N / kBN;
   const int mt = t / ntn;
   const int m0 = mt * kBM;
