@@ -44,9 +44,9 @@ WORKLOADS = {
 # algorithmic MFLOP per update and gathered bytes per update
 ALGO_MFLOP = {"ddpg": 365.4, "td3": 413.5, "sac": 2738.4, "tqc": 8564.8}
 # dram__bytes_read.sum + dram__bytes_write.sum per gemm_kernel launch from the committed
-# `ncu --set full` capture (profiles/r1_ncu_gemm_kernel_summary.csv: 9.42 MB over the 14 launches of one
+# `ncu --set full` capture (profiles/r1b_ncu_gemm_kernel_summary.csv: 8.92 MB over the 12 launches of one
 # DDPG update, cold L2 as ncu replays it; in the live loop the operands are L2-resident)
-GEMM_DRAM_BYTES_PER_LAUNCH = {"ddpg": 673_207}
+GEMM_DRAM_BYTES_PER_LAUNCH = {"ddpg": 743_147}
 L_EP = 1000
 
 
