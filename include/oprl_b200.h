@@ -97,7 +97,11 @@ int oprl_engine_sync_params(oprl_engine* e);
  * states [E, L+1, S], actions [E, L, A], rewards [E, L, 1], dones [E, L, 1]. */
 int oprl_buffer_bind(oprl_engine* e, const float* states, const float* actions,
                      const float* rewards, const float* dones, int E, int L);
-/* Host prefix sums of episode lengths (n_eps + 1 ints) for on-device index sampling. */
+/* Host prefix sums of episode lengths (n_eps + 1 ints) for on-device index sampling.
+ * Also the ordering point for replay writes: transitions written to the bound storage become
+ * visible to oprl_step's device-side sampling through this call (or oprl_buffer_bind) -- the first
+ * gather after it is ordered behind everything enqueued on the launch stream so far, later gathers
+ * may run ahead of the update in flight (see oprl_step). */
 int oprl_buffer_set_prefix(oprl_engine* e, const int* prefix_host, int n_eps);
 /* Row-major batch arrays the gather writes (what sample() returns): device pointers
  * s [cap,S], a [cap,A], r [cap], d [cap], s2 [cap,S]. */
@@ -109,8 +113,10 @@ int oprl_sample(oprl_engine* e, const int* ep_step_host, int B);
 /* Generic path: load a caller-provided dense device batch instead of gathering. */
 int oprl_load_batch(oprl_engine* e, const float* s, const float* a, const float* r,
                     const float* d, const float* s2, int B);
-/* Same with HOST arrays (fp32, contiguous): packed into a pinned staging ring and moved with a
- * single asynchronous H2D copy -- the path a CPU-resident replay buffer / trainer would use. */
+/* Same with HOST arrays (fp32, contiguous): packed into a pinned staging ring (the arrays may be
+ * reused as soon as the call returns), copied H2D and loaded into the engine's other working set on
+ * a copy stream, beside the update still running on the launch stream -- the path a CPU-resident
+ * replay buffer / trainer would use. */
 int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const float* r,
                          const float* d, const float* s2, int B);
 /* Inject the standard-normal draws of the next update (parity tests).  which = 0:
@@ -118,9 +124,15 @@ int oprl_load_batch_host(oprl_engine* e, const float* s, const float* a, const f
  * 1: second draw (SAC-TQC actor-step noise).  noise: device pointer [B, A]. */
 int oprl_set_noise(oprl_engine* e, int which, const float* noise_dev, int n);
 
-/* update(): one gradient update on the batch last sampled / loaded. */
+/* update(): one gradient update on the batch last sampled / loaded (calling it again repeats the
+ * update on the same batch). */
 int oprl_update(oprl_engine* e, int flags, int segment);
-/* Fused device-resident learner step: on-device sampling + update in one graph. */
+/* Device-resident learner step = oprl_sample(e, NULL, B) + oprl_update(e, flags, OPRL_SEG_ALL), the
+ * loop body of distrib/policy_update_worker.py:66-68 without the host round trip.  In a steady loop
+ * (same B, no oprl_buffer_set_prefix / _bind / oprl_set_noise in between) the batch of step t+1 is
+ * gathered as a parallel branch of step t's update graph; the uniform draws are the ones the
+ * in-order sequence would have made (the RNG offset is the update count, not the launch order).
+ * The row-major batch arrays of oprl_batch_bind are NOT written on this path. */
 int oprl_step(oprl_engine* e, int B, int flags);
 
 /* Logging scalars (synchronises the stream):
