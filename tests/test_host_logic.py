@@ -279,3 +279,19 @@ def test_nccl_style_wrapper_orders_segments_and_allreduces_over_gloo():
     assert cgrad == [8.0] * 4  # 2 -> all-reduce(sum) over 2 ranks -> 4 -> again in the second update -> 8
     assert agrad == [2.0] * 4  # only the update with an actor step reduces the actor arena
     assert other[1] == theta0 == [0.0] * 4  # parameters broadcast from rank 0
+
+
+def test_gemm_planning_code_on_the_host():
+    """tools/host_logic_test.cu: CT32 index map, TMEM accumulator plan, split-K choice and the
+    shared-memory budget of the GEMM kernel, compiled with nvcc and run on the CPU."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import __graft_entry__ as g
+
+    g.build()
+    out = subprocess.run([os.path.join(root, "build", "host_logic_test")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "PASS" in out.stdout
