@@ -159,3 +159,38 @@ def test_pipelined_scalar_readback_matches_the_blocking_one():
         b.engine.scalars_async()
     with pytest.raises(Exception):
         old.result()
+
+
+@pytest.mark.parametrize("name", ["ddpg", "td3", "sac"])
+def test_prefetching_learner_step_equals_the_in_order_sequence(name):
+    """learner_step() (oprl_step: after four steady steps the NEXT batch is gathered as a parallel branch
+    of the running update graph, into the other working set) must produce bit-for-bit what the in-order
+    API sequence sample(device draw) ; update() produces: same draws, same batches, same parameters --
+    including across a replay change announced by set_prefix in the middle."""
+    from oprl_b200.algos.ddpg import DDPG
+    from oprl_b200.algos.sac import SAC
+    from oprl_b200.algos.td3 import TD3
+
+    cls, kw = dict(ddpg=(DDPG, {}), td3=(TD3, {}), sac=(SAC, dict(tune_alpha=True)))[name]
+    a, b = make_pair(cls, **kw)
+    buf = full_buffer(24, 6, episodes=100)
+    for algo in (a, b):
+        algo.attach_buffer(buf)
+        algo.engine.set_prefix(buf.ep_lens[:buf.episodes_counter])
+    B = 256
+    for k in range(14):
+        if k == 9:  # the replay binding changes: both must re-order behind it and sample from 60 episodes
+            for algo in (a, b):
+                algo.engine.set_prefix(buf.ep_lens[:60])
+        a.learner_step(B)
+        b.engine.sample(B, None)
+        b._run_update(b._wants_actor_step())
+        b._after_update()
+    torch.cuda.synchronize()
+    assert a.engine.state().tick == b.engine.state().tick == 14
+    for grp in ("actor", "critic"):
+        for key in ("theta", "m", "v", "target"):
+            x, y = a.engine.arena[grp][key], b.engine.arena[grp][key]
+            if x is not None:
+                assert torch.equal(x, y), (grp, key)
+    assert a.engine.state().log_alpha == b.engine.state().log_alpha
