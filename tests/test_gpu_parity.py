@@ -105,7 +105,8 @@ def test_fixture_parity(name):
 
 def test_host_batch_and_int64_done_match_the_device_path():
     """update() takes what the reference's own test feeds it (tests/functional/test_rl_algos.py:25-31):
-    CPU tensors, an int64 `done`, next_state aliasing state -- through the pinned zero-copy load."""
+    CPU tensors, an int64 `done`, next_state aliasing state -- through the pinned staging ring and the
+    copy-stream load into the other working set."""
     fx = load_case("ddpg_b8")
     results = []
     for on_host in (False, True):
