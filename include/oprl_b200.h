@@ -143,7 +143,10 @@ int oprl_get_scalars(oprl_engine* e, float* out_host, int n);
  * per scalar, algos/td3.py:118-131, sac.py:112-150; a learner loop can instead consume the scalars
  * of update t while update t+1 is already running): _enqueue appends a D2H copy of the scalars of
  * everything launched so far to the stream and returns a ticket >= 0; _wait blocks on that copy
- * only.  A ticket stays valid for 8 further enqueues. */
+ * only.  A ticket stays valid for 8 further enqueues / updates.  In a loop that reads every update the
+ * engine switches to a program variant whose last kernel publishes the scalars into a pinned,
+ * device-mapped ring itself: _enqueue then costs no GPU work and _wait polls host memory
+ * (single-learner engines; OPRL_B200_HOST_SCALARS=0 keeps the D2H copy). */
 int oprl_scalars_enqueue(oprl_engine* e);
 int oprl_scalars_wait(oprl_engine* e, int ticket, float* out_host, int n);
 int oprl_get_state(oprl_engine* e, oprl_state* out);

@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cmath>
 #include <stdexcept>
 #include <cstdarg>
@@ -143,6 +145,8 @@ struct Program {
 
 using namespace oprl;
 
+constexpr int kFlagPublish = 0x100;  // internal program flag (not part of the ABI's OPRL_UPDATE_* bits)
+
 struct oprl_engine {
   oprl_cfg cfg;
   cudaStream_t stream = nullptr;      // launch stream (caller may redirect it, e.g. torch's current stream)
@@ -157,6 +161,18 @@ struct oprl_engine {
   DevState* h_ring = nullptr;  // pinned [kScalarSlots]
   cudaEvent_t ring_done[kScalarSlots] = {};
   long long ring_next = 0;
+  // The last kernel of an update can publish the state block into this pinned, device-mapped ring
+  // itself (kernels.cuh publish_state); scalars_enqueue then costs no GPU work.  OPRL_B200_HOST_SCALARS=0:
+  // always the D2H copy + event.
+  bool host_scalars = true;
+  DevState* h_pub = nullptr;  // pinned [kHostRing]
+  // single-learner engines only: the data-parallel programs keep the validated D2H read-back
+  bool publishes() const { return host_scalars && h_pub && cfg.world_size == 1; }
+  // Publishing costs the update's last kernel a system-scope fence (~3 us on the chain), so it is a
+  // program VARIANT (internal flag kFlagPublish) used only while somebody reads the scalars of every
+  // update: scalars_enqueue arms it for the next update; loops that never read run the plain variant.
+  bool want_pub = false;        // a read-back was requested since the last update
+  bool last_published = false;  // the last update launched was the publishing variant
   // bump allocator over zero-initialised workspaces
   std::vector<void*> blocks;
   // replay + batch bindings
@@ -379,7 +395,7 @@ static CommArgs make_comm(oprl_engine* e, int group, bool exit_barrier) {
 }
 
 static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, bool exit_barrier = false,
-                        LossTail lt = LossTail{nullptr, nullptr, nullptr, 0, 0, 0, 0.f}) {
+                        LossTail lt = LossTail{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f}) {
   // one element per thread: a single load -> compute -> store round trip (which matters most when
   // the gradient loads cross NVLink)
   dim3 grid(g.n_blocks);
@@ -744,7 +760,9 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     const bool polyak = td3 ? do_actor : true;  // td3.py:81-84 ; ddpg.py:72-77
     const int mode = 1 | 4 | (polyak ? (2 | 8) : 0);
     const bool exit_barrier = !do_actor;  // no actor handshake follows to fence the critic gradients
-    b.stage(s).add_simt([e, &gc, mode, exit_barrier](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier); });
+    LossTail ltc{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
+    if (!do_actor && (p->flags & kFlagPublish)) ltc.pub = e->h_pub;  // TD3 critic-only update: this is its last kernel
+    b.stage(s).add_simt([e, &gc, mode, exit_barrier, ltc](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc); });
     ++s;
   }
   if (do_actor) {
@@ -755,7 +773,8 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     int s_end = b.forward(s, gc.nets[0], gc.theta, false, w->Xp, p_cq, false, simt_head ? nullptr : &lq);
     TM Dm = TM{nullptr, 0, 0};
     int l_start = -1;
-    LossTail lt{nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
+    LossTail lt{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
+    lt.pub = (p->flags & kFlagPublish) ? e->h_pub : nullptr;  // the actor's Adam is the last kernel of this update
     static const bool head_kernel = getenv("OPRL_B200_ACTOR_HEAD") && atoi(getenv("OPRL_B200_ACTOR_HEAD")) != 0;
     if (simt_head && !head_kernel) {
       // The seed dL/dq = -1/count of the actor loss is a constant, so dz of the last hidden layer
@@ -1051,6 +1070,7 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   al.add = tqc ? 0.f : static_cast<float>(c.target_entropy);
   al.world = e->comm.connected ? e->comm.world : 1;
   for (int r = 0; r < al.world && e->comm.connected; ++r) al.peer_x[r] = e->comm.peer_grad[0][r] + ga.floats;
+  al.pub = (p->flags & kFlagPublish) ? e->h_pub : nullptr;  // alpha_step_kernel is the last kernel of a SAC / TQC update
   b.stage(s).add_simt([e, &ga, al, st](cudaStream_t sm) {
     launch_adam(e, ga, 1 | 4, sm);
     launch_k(alpha_step_kernel, dim3(1), dim3(32), 0, sm, st, al);
@@ -1317,6 +1337,13 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   e->n_sm = prop.multiProcessorCount;
   if (const char* v = getenv("OPRL_B200_PDL")) g_pdl = atoi(v) != 0;
   if (const char* v = getenv("OPRL_B200_PREFETCH")) e->overlap = atoi(v) != 0;
+  if (const char* v = getenv("OPRL_B200_HOST_SCALARS")) e->host_scalars = atoi(v) != 0;
+  if (e->host_scalars) {
+    void* hp;
+    CU(cudaHostAlloc(&hp, sizeof(DevState) * kHostRing, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(hp, 0, sizeof(DevState) * kHostRing);
+    e->h_pub = static_cast<DevState*>(hp);
+  }
   if (e->cfg.world_size < 1) e->cfg.world_size = 1;
   CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   e->stream = e->own_stream;
@@ -1369,6 +1396,7 @@ void oprl_engine_destroy(oprl_engine* e) {
   for (void* p : e->blocks) cudaFree(p);
   if (e->h_state) cudaFreeHost(e->h_state);
   if (e->h_flag) cudaFreeHost(e->h_flag);
+  if (e->h_pub) cudaFreeHost(e->h_pub);
   if (e->h_ring) {
     cudaFreeHost(e->h_ring);
     for (int i = 0; i < oprl_engine::kScalarSlots; ++i) cudaEventDestroy(e->ring_done[i]);
@@ -1610,6 +1638,11 @@ int oprl_update(oprl_engine* e, int flags, int segment) {
     if (!e->grp[k].theta) return fail(-1, "arena %d not bound", k);
   API_BEGIN
   oprl_engine::Work* w = get_work(e, e->cur_B);
+  if (segment <= 0) {  // decided once per update (segment 0 / whole update), kept for its later segments
+    e->last_published = e->publishes() && e->want_pub;
+    e->want_pub = false;
+  }
+  flags = (flags & ~kFlagPublish) | (e->last_published ? kFlagPublish : 0);
   Program* p = get_program(e, w, flags);
   // OPRL_B200_NOGRAPH=1: the same launches issued one by one into the stream (A/B against the graph)
   static const bool no_graph = getenv("OPRL_B200_NOGRAPH") && atoi(getenv("OPRL_B200_NOGRAPH")) != 0;
@@ -1693,8 +1726,11 @@ int oprl_step(oprl_engine* e, int B, int flags) {
     API_BEGIN
     oprl_engine::Work* w = get_work(e, B, e->cur_par);
     oprl_engine::Work* wn = get_work(e, B, e->cur_par ^ 1);
-    Program* p = get_program(e, w, flags);
+    const bool pub = e->publishes() && e->want_pub;
+    Program* p = get_program(e, w, (flags & ~kFlagPublish) | (pub ? kFlagPublish : 0));
     if (cudaGraphExec_t g = get_step_graph(e, w, wn, p)) {
+      e->last_published = pub;
+      e->want_pub = false;
       CU(cudaGraphLaunch(g, e->stream));
       CU(cudaEventRecord(w->ev_free, e->stream));
       CU(cudaEventRecord(wn->ev_free, e->stream));
@@ -1726,6 +1762,9 @@ int oprl_get_scalars(oprl_engine* e, float* out_host, int n) {
 
 int oprl_scalars_enqueue(oprl_engine* e) {
   if (!e) return fail(-1, "null engine");
+  e->want_pub = true;  // the next update publishes its scalars itself
+  if (e->publishes() && e->last_published && e->host_tick > 0)  // the last update did: its index is the ticket
+    return static_cast<int>(((e->host_tick - 1) & 0x1fffffff) | 0x20000000);
   API_BEGIN
   if (!e->h_ring) {
     void* p;
@@ -1744,6 +1783,32 @@ int oprl_scalars_enqueue(oprl_engine* e) {
 
 int oprl_scalars_wait(oprl_engine* e, int ticket, float* out_host, int n) {
   if (!e || !out_host || n < 0 || n > 32) return fail(-1, "bad scalars call");
+  if (ticket & 0x20000000) {
+    if (!e->h_pub || e->host_tick == 0) return fail(-1, "no update has published its scalars");
+    const unsigned long long newest = e->host_tick - 1;
+    const unsigned long long age = ((newest & 0x1fffffff) - static_cast<unsigned long long>(ticket & 0x1fffffff)) & 0x1fffffff;
+    if (age >= static_cast<unsigned long long>(kHostRing))
+      return fail(-1, "scalar ticket expired (%d updates later; ring of %d)", static_cast<int>(age), kHostRing);
+    const unsigned long long idx = newest - age;  // index of the update whose scalars are wanted
+    const volatile DevState* slot = e->h_pub + (idx % kHostRing);
+    unsigned long long spins = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    while (slot->tick < idx + 1) {
+      if ((++spins & 4095) == 0) {
+        const cudaError_t q = cudaStreamQuery(e->stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(-2, "CUDA error %s while waiting for scalars", cudaGetErrorString(q));
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30))
+          return fail(-1, "timed out waiting for update %llu to publish its scalars", idx);
+      }
+    }
+    if (slot->tick != idx + 1) return fail(-1, "scalar ticket overwritten by a later update");
+    std::atomic_thread_fence(std::memory_order_acquire);
+    float tmp[32];
+    for (int i = 0; i < 32; ++i) tmp[i] = slot->scalars[i];
+    tmp[SC_ALPHA] = slot->alpha;
+    memcpy(out_host, tmp, sizeof(float) * n);
+    return 0;
+  }
   if (!e->h_ring) return fail(-1, "no scalar read-back was enqueued");
   const long long newest = e->ring_next - 1;
   const long long age = ((newest & 0x3fffffff) - ticket) & 0x3fffffff;

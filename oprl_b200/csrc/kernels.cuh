@@ -33,6 +33,24 @@ struct DevState {
 
 constexpr double kBeta1 = 0.9, kBeta2 = 0.999;
 
+// Host-visible copy of the state block: the last kernel of an update writes DevState into slot
+// (tick - 1) % kHostRing of a pinned, device-mapped ring -- every word but the tick first, a system
+// fence, then the tick as the sequence number the host polls.  Replaces a D2H copy + event per step
+// in loops that read the losses of every update (OPRL_B200_HOST_SCALARS=1).
+// Call with all threads of one block, after a barrier that orders the block's own writes to *st.
+constexpr int kHostRing = 8;
+__device__ __forceinline__ void publish_state(const DevState* st, DevState* ring, int tid, int nthreads) {
+  if (!ring) return;
+  const unsigned long long tick = *reinterpret_cast<const volatile unsigned long long*>(&st->tick);
+  DevState* slot = ring + ((tick - 1ull) % kHostRing);
+  const volatile unsigned int* src = reinterpret_cast<const volatile unsigned int*>(st);
+  volatile unsigned int* dst = reinterpret_cast<volatile unsigned int*>(slot);
+  for (int i = 2 + tid; i < static_cast<int>(sizeof(DevState) / 4); i += nthreads) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(slot) = tick;
+}
+
 // Advance the per-update counters (one thread, at the end of the loss kernel): everything that
 // consumed the old tick (sampling, noise) ran in earlier launches; the Adam launches that need
 // the new step counts run later.
@@ -416,6 +434,7 @@ constexpr int kAdamThreads = 256;
 // from the per-tile partial head dot products the critic forward GEMM left behind (GemmOp::tail_out).
 // A logging scalar only -- nothing on the gradient path waits for it.
 struct LossTail {
+  DevState* pub;      // non-null: this launch is the update's last kernel -- publish_state() to this ring
   const float* part;  // nullptr = no duty
   const float* b3;
   float* out;
@@ -514,6 +533,10 @@ __global__ void __launch_bounds__(kAdamThreads)
       for (int w = 0; w < kAdamThreads / 32; ++w) tot += lt_sh[w];
       *lt.out = lt.scale * tot;
     }
+  }
+  if (lt.pub && blockIdx.x == 0) {
+    __syncthreads();  // actor_loss above is part of what gets published
+    publish_state(st, lt.pub, threadIdx.x, kAdamThreads);
   }
   if (reduce && cm.exit_barrier) {
     // nobody overwrites gradients another rank may still be reading: the last block of this launch

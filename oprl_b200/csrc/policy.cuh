@@ -188,6 +188,7 @@ struct AlphaStep {
   float add;  // SAC: target_entropy ; TQC: 0
   int world;  // data-parallel learners: sum the per-rank shares (runs after the actor Adam's handshake)
   const float* peer_x[kMaxRanks];
+  DevState* pub;  // non-null: publish_state() to this host ring (this is the update's last kernel)
 };
 __device__ __forceinline__ void alpha_step(DevState* st, const AlphaStep& as) {
   float share = 0.f;
@@ -214,6 +215,10 @@ __global__ void alpha_step_kernel(DevState* st, AlphaStep as) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
   if (threadIdx.x == 0 && blockIdx.x == 0 && as.enabled) alpha_step(st, as);
+  if (as.pub && blockIdx.x == 0) {
+    __syncthreads();
+    publish_state(st, as.pub, threadIdx.x, blockDim.x);
+  }
 }
 
 // --------------------------------------------------------------- TQC critic loss + seeds

@@ -153,9 +153,10 @@ def test_pipelined_scalar_readback_matches_the_blocking_one():
         assert got == want
     for grp in ("actor", "critic"):
         assert torch.equal(a.engine.arena[grp]["theta"], b.engine.arena[grp]["theta"])
-    # tickets expire once the ring has wrapped
+    # tickets expire once the ring has wrapped (8 further updates, each with its read-back)
     old = b.engine.scalars_async()
     for _ in range(8):
+        b.update(*batches[0])
         b.engine.scalars_async()
     with pytest.raises(Exception):
         old.result()
