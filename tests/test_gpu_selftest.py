@@ -14,11 +14,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_gemm_selftest_passes():
-    sys.path.insert(0, ROOT)
-    import __graft_entry__ as g
-
-    g.build()  # (re)builds build/gemm_selftest when a source is newer
     exe = os.path.join(ROOT, "build", "gemm_selftest")
+    if not os.path.exists(exe):
+        # normally built by __graft_entry__.build() and shipped with the tree; compile only the tool here
+        # (never the shared library: this process may already have it mapped)
+        os.makedirs(os.path.dirname(exe), exist_ok=True)
+        subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                               os.path.join(ROOT, "tools", "gemm_selftest.cu"), "-o", exe], cwd=ROOT)
     out = subprocess.run([exe, "0"], capture_output=True, text=True, timeout=300)
     sys.stdout.write(out.stdout[-3000:])
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
