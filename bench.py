@@ -375,17 +375,25 @@ def oracle_learner(algo, B, episodes=20):
 
 
 def cpu_baseline(algo, B, budget_s):
-    torch.set_num_threads(os.cpu_count() or 1)
+    """All host threads (the headline figure) and, beside it, one thread (SURVEY.md section 8d asks for both)."""
     step = oracle_learner(algo, B)
-    for _ in range(5):
-        step()
-    n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < budget_s:
-        step()
-        n += 1
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} updates of the same workload (20x1000-step replay, batch {B}) in {dt:.1f} s, torch {torch.__version__} CPU"}
+    out = {}
+    for threads, budget in ((os.cpu_count() or 1, budget_s), (1, budget_s / 3)):
+        torch.set_num_threads(threads)
+        for _ in range(5):
+            step()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < budget:
+            step()
+            n += 1
+        dt = time.perf_counter() - t0
+        if not out:
+            out = {"value": n / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{n} updates of the same workload (20x1000-step replay, batch {B}) in {dt:.1f} s, torch {torch.__version__} CPU"}
+        else:
+            out["value_1_thread"] = n / dt
+    torch.set_num_threads(os.cpu_count() or 1)
+    return out
 
 
 def run_reference(args):
