@@ -184,10 +184,14 @@ int oprl_gather_rows(const float* states, const float* actions, const float* rew
 int oprl_update_launches(oprl_engine* e, int B, int flags);
 
 /* Measurement hook for bench.py's roofline: what = 0 replays only the tcgen05 GEMM launches of
- * one update `iters` times, what = 2 only its SIMT launches, what = 1 the gather (device index draw); total milliseconds by CUDA
+ * one update `iters` times, what = 2 only its SIMT launches, what = 3 only its batch-slice chain launches
+ * (csrc/chain.cuh), what = 1 the gather (device index draw); total milliseconds by CUDA
  * events on the launch stream.  Leaves activations / batch in an unspecified state. */
 int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* ms_total,
                  int* launches_per_iter);
+/* Debug hook (OPRL_B200_CHAIN_PROF=1): 64 clock64 stamps of CTA 0 of the critic-step (which = 0) or
+ * actor-step (1) chain launch of the last update; no reference counterpart. */
+int oprl_chain_prof(oprl_engine* e, int B, int flags, int which, long long* out64);
 
 #ifdef __cplusplus
 }

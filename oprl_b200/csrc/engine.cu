@@ -28,6 +28,7 @@
 #include "../../include/oprl_b200.h"
 #include "kernels.cuh"
 #include "policy.cuh"
+#include "chain.cuh"
 
 namespace oprl {
 
@@ -121,13 +122,15 @@ struct Stage {
   std::vector<GemmOp> ops;
   std::vector<std::function<void(cudaStream_t)>> simt;
   std::vector<int> simt_launches;  // kernels each SIMT entry launches
+  std::vector<char> simt_is_chain;  // the entry is a batch-slice chain launch (chain.cuh), timed as its own class
   int segment = 0;
   bool bumps_tick = false;  // holds the loss kernel that advances DevState::tick
   std::vector<GemmLaunch> launches;  // prepare_stage_tables: one per <= kMaxOps ops, descriptors on the device
   std::vector<int> launch_tiles;
-  void add_simt(std::function<void(cudaStream_t)> f, int n_launches = 1) {
+  void add_simt(std::function<void(cudaStream_t)> f, int n_launches = 1, bool is_chain = false) {
     simt.push_back(std::move(f));
     simt_launches.push_back(n_launches);
+    simt_is_chain.push_back(is_chain ? 1 : 0);
   }
 };
 
@@ -135,10 +138,12 @@ struct Program {
   int B = 0, Bp = 0;
   int flags = 0;
   std::vector<Stage> stages;
-  cudaGraphExec_t graph[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] segments, [3] all, [4] GEMM launches only, [5] SIMT launches only (profiling), [6] all + the next step's gather as a parallel branch (oprl_step)
+  cudaGraphExec_t graph[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [0..2] segments, [3] all, [4] GEMM launches only, [5] SIMT launches only (profiling), [6] all + the next step's gather as a parallel branch (oprl_step), [7] chain launches only (profiling)
   unsigned long long step_key = 0;  // replay binding the gather of graph[6] was captured with
   int n_gemm_launches = 0;
+  int n_chain_launches = 0;
   int n_launches = 0;
+  long long* chain_prof[2] = {nullptr, nullptr};  // OPRL_B200_CHAIN_PROF=1: clock64 stamps of CTA 0 of the critic / actor chain
 };
 
 }  // namespace oprl
@@ -650,9 +655,363 @@ static void fill_constant_seed(oprl_engine* e, const TM& D, int B, int ncols, fl
   CU(cudaStreamSynchronize(e->stream));
 }
 
+// ---------------------------------------------------------------- DDPG / TD3 on the chain kernel
+// One update = chain(critic step) -> grouped dW GEMM -> Adam(critic) -> chain(actor step) -> grouped dW
+// GEMM -> Adam(actor): 6 launches instead of 15 (chain.cuh).  OPRL_B200_CHAIN=0 keeps the stage path.
+static bool use_chain(const oprl_engine* e) {
+  static const bool off = getenv("OPRL_B200_CHAIN") && atoi(getenv("OPRL_B200_CHAIN")) == 0;
+  const oprl_cfg& c = e->cfg;
+  auto ok_h = [](int h) { return h == 128 || h == 256; };
+  return !off && (c.algo == OPRL_ALGO_DDPG || c.algo == OPRL_ALGO_TD3) && c.gemm_mode == OPRL_GEMM_TC_3XTF32 &&
+         c.actor_layers == 2 && c.critic_layers == 2 && ok_h(c.actor_hidden) && ok_h(c.critic_hidden) &&
+         c.action_dim <= kCMaxJ && e->Kin <= 256;
+}
+
+struct ChainBuf {  // one operand buffer in the chain kernel's shared memory (+ its "written" barrier)
+  int hi = 0, lo = 0, sbo = 0, bar = -1;
+  int prod = 0;  // productions so far: the consumer of production k waits for barrier phase k
+};
+
+struct ChainBuilder {
+  oprl_engine* e;
+  int top = kChainCtlBytes;
+  int n_bars = 0;
+  std::vector<ChainOp> ops;
+  ChainLaunch L;
+  explicit ChainBuilder(oprl_engine* e_) : e(e_) { memset(&L, 0, sizeof(L)); }
+  ChainBuf buf(int K) {
+    ChainBuf b;
+    b.sbo = chain_buf_sbo(K);
+    b.hi = top;
+    b.lo = top + chain_buf_bytes(K);
+    top = (top + 2 * chain_buf_bytes(K) + 127) & ~127;
+    b.bar = n_bars++;
+    if (n_bars > kCMaxBufs) throw std::runtime_error("chain: too many operand buffers");
+    if (top > kChainSmemMax) throw std::runtime_error("chain: operand buffers exceed shared memory");
+    return b;
+  }
+  void input(const TM& src, ChainBuf& b) {
+    if (L.n_in >= 3) throw std::runtime_error("chain: too many input matrices");
+    ChainInput& in = L.in[L.n_in++];
+    in.src = src.p; in.rows = src.rows; in.kchunks = src.cols / 32;
+    in.hi = b.hi; in.lo = b.lo; in.sbo = b.sbo; in.bar = b.bar;
+    b.prod += 1;
+  }
+  // D^T[M x 16] = W[M x K] . in^T : M output features, K = width of the input buffer
+  ChainOp op(const TM& wt, int M, int K, const ChainBuf& in) {
+    ChainOp o;
+    memset(&o, 0, sizeof(o));
+    o.w = wt.p; o.w_rows = wt.rows;
+    o.mtiles = pad128(M) / 128; o.kchunks = K / 32;
+    if (o.mtiles > 2 || o.kchunks > 8 || wt.rows < o.mtiles * 128) throw std::runtime_error("chain: layer too wide");
+    o.in_hi = in.hi; o.in_lo = in.lo; o.in_sbo = in.sbo; o.in_bar = in.bar; o.in_phase = in.prod - 1;
+    if (in.prod < 1) throw std::runtime_error("chain: operand consumed before it is produced");
+    o.out_bar = -1; o.x_bar = -1; o.vec_slot = -1; o.vec2_slot = -1;
+    return o;
+  }
+  void out(ChainOp& o, ChainBuf& b) {
+    o.flags |= CF_OUT_SMEM;
+    o.out_hi = b.hi; o.out_lo = b.lo; o.out_sbo = b.sbo; o.out_bar = b.bar;
+    b.prod += 1;
+  }
+  void gout(ChainOp& o, const TM& t) {
+    o.flags |= CF_OUT_GLOBAL;
+    o.gout = t.p; o.gout_rows = t.rows;
+  }
+  int vec(float* dst, int n) {
+    if (L.n_vec >= kCMaxVec) throw std::runtime_error("chain: too many partial vectors");
+    L.vec_dst[L.n_vec] = dst;
+    L.vec_n[L.n_vec] = n;
+    return L.n_vec++;
+  }
+  // upload the op table, size the partial block; returns the launch closure
+  std::function<void(cudaStream_t)> finish(int B, int Bp, long long* prof) {
+    if (ops.size() > static_cast<size_t>(kCMaxOps)) throw std::runtime_error("chain: too many ops");
+    int chunks = 0;
+    for (auto& o : ops) chunks += o.mtiles * o.kchunks;
+    if (chunks > kCMaxChunks) throw std::runtime_error("chain: too many weight chunks");
+    L.n_ops = static_cast<int>(ops.size());
+    L.B = B; L.Bp = Bp;
+    L.n_cta = (B + kNB - 1) / kNB;
+    L.part_stride = L.n_vec * kCFeat + 32;
+    L.part = e->alloc_floats(static_cast<size_t>(L.n_cta) * L.part_stride);
+    L.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+    L.st = e->d_state;
+    L.prof = prof;
+    ChainOp* d = reinterpret_cast<ChainOp*>(e->alloc_floats((sizeof(ChainOp) * ops.size() + 3) / 4));
+    CU(cudaMemcpyAsync(d, ops.data(), sizeof(ChainOp) * ops.size(), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    L.ops = d;
+    const ChainLaunch LL = L;
+    const int smem = top;
+    return [LL, smem](cudaStream_t sm) {
+      launch_k(chain_kernel, dim3(LL.n_cta), dim3(kChainThreads), static_cast<size_t>(smem), sm, LL);
+    };
+  }
+};
+
+static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
+  const oprl_cfg& c = e->cfg;
+  const bool td3 = c.algo == OPRL_ALGO_TD3;
+  const bool do_actor = (p->flags & OPRL_UPDATE_ACTOR) != 0;
+  const int B = w->B, Bp = w->Bp, A = c.action_dim, S = c.state_dim, A4 = e->A4, nq = c.n_critics;
+  const int Kin = e->Kin, Ha = c.actor_hidden, Hc = c.critic_hidden;
+  Builder b{e, w, p, 3};
+  Group& ga = e->grp[OPRL_NET_ACTOR];
+  Group& gc = e->grp[OPRL_NET_CRITIC];
+  const Net& an = ga.nets[0];
+  const float inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
+  const int n_cta = (B + kNB - 1) / kNB;
+  static const bool want_prof = getenv("OPRL_B200_CHAIN_PROF") && atoi(getenv("OPRL_B200_CHAIN_PROF")) != 0;
+  if (want_prof)
+    for (int k = 0; k < 2; ++k) p->chain_prof[k] = reinterpret_cast<long long*>(e->alloc_floats(2 * 64));
+
+  // what the chain launches leave behind for the weight-gradient GEMMs (transposed-tiled [feature x batch])
+  TM c_h0T[2], c_dz1T[2], c_dz0T[2];
+  for (int i = 0; i < nq; ++i) {
+    c_h0T[i] = e->alloc_tm(pad128(Hc), Bp);
+    c_dz1T[i] = e->alloc_tm(pad128(Hc), Bp);
+    c_dz0T[i] = e->alloc_tm(pad128(Hc), Bp);
+  }
+  TM a_h0T{nullptr, 0, 0}, a_h1T{nullptr, 0, 0}, a_dz1T{nullptr, 0, 0}, a_dz0T{nullptr, 0, 0}, dzaT{nullptr, 0, 0};
+  float* a_rm = nullptr;
+  unsigned int *a_mask0 = nullptr, *a_mask1 = nullptr;
+  if (do_actor) {
+    a_h0T = e->alloc_tm(pad128(Ha), Bp);
+    a_h1T = e->alloc_tm(pad128(Ha), Bp);
+    a_dz1T = e->alloc_tm(pad128(Ha), Bp);
+    a_dz0T = e->alloc_tm(pad128(Ha), Bp);
+    dzaT = e->alloc_tm(128, Bp);
+    a_rm = e->alloc_floats(static_cast<size_t>(Bp) * A);
+    a_mask0 = reinterpret_cast<unsigned int*>(e->alloc_floats(static_cast<size_t>(n_cta) * kCFeat));
+    a_mask1 = reinterpret_cast<unsigned int*>(e->alloc_floats(static_cast<size_t>(n_cta) * kCFeat));
+  }
+
+  // ---- chain A: targets, critic forward, TD loss, critic dX chain, and pi(s) for the actor step
+  {
+    ChainBuilder cb(e);
+    ChainBuf bX = cb.buf(Kin), bXn = cb.buf(Kin), bXp;
+    cb.input(w->X, bX);
+    cb.input(w->Xn, bXn);
+    if (do_actor) {
+      bXp = cb.buf(Kin);
+      cb.input(w->Xp, bXp);
+    }
+    ChainBuf bigA = cb.buf(Ha), bigC[2], bigP;
+    for (int i = 0; i < nq; ++i) bigC[i] = cb.buf(Hc);
+    if (do_actor || nq == 2) bigP = cb.buf(std::max(Ha, Hc));
+    if (std::max(Ha, Hc) != std::min(Ha, Hc)) throw std::runtime_error("chain: actor and critic hidden widths differ");
+    // 0: actor_target layer 0 over s'                                        (ddpg.py:94, td3.py:102)
+    {
+      ChainOp o = cb.op(an.L[0].TW, Ha, Kin, bXn);
+      o.bias = ga.target + an.L[0].b_off; o.flags |= CF_BIAS_RELU;
+      cb.out(o, bigA);
+      cb.ops.push_back(o);
+    }
+    // critics layer 0 over (s, a)                                            (ddpg.py:96, td3.py:95)
+    for (int i = 0; i < nq; ++i) {
+      const Net& cn = gc.nets[i];
+      ChainOp o = cb.op(cn.L[0].W, Hc, Kin, bX);
+      o.bias = gc.theta + cn.L[0].b_off; o.flags |= CF_BIAS_RELU | CF_SAVE_MASK;
+      o.mask_slot = i;
+      cb.out(o, bigC[i]);
+      cb.gout(o, c_h0T[i]);
+      cb.ops.push_back(o);
+    }
+    if (do_actor) {  // actor layer 0 over s (actor step forward: independent of the critic update)
+      ChainOp o = cb.op(an.L[0].W, Ha, Kin, bXp);
+      o.bias = ga.theta + an.L[0].b_off; o.flags |= CF_BIAS_RELU | CF_MASK_GLOBAL;
+      o.gmask = a_mask0;
+      cb.out(o, bigP);
+      cb.gout(o, a_h0T);
+      cb.ops.push_back(o);
+    }
+    // actor_target layer 1 + tanh head -> a' into the action columns of the (s', a') operand
+    {
+      ChainOp o = cb.op(an.L[1].TW, Ha, Ha, bigA);
+      o.bias = ga.target + an.L[1].b_off; o.flags |= CF_BIAS_RELU;
+      o.head = CH_ACTION; o.J = A;
+      o.hw = ga.target + an.L[2].w_off; o.hw_ld = Ha; o.hb = ga.target + an.L[2].b_off;
+      if (td3) {  // target policy smoothing (td3.py:98-103)
+        o.aux = w->noise_out[0];
+        o.clamp = static_cast<float>(c.max_action);
+      }
+      o.x_hi = bXn.hi; o.x_lo = bXn.lo; o.x_sbo = bXn.sbo; o.x_bar = bXn.bar;
+      bXn.prod += 1;
+      cb.ops.push_back(o);
+    }
+    if (do_actor) {  // actor layer 1 + tanh head -> pi(s): row-major (tanh') and into the tiled (s, pi(s)) matrix
+      ChainOp o = cb.op(an.L[1].W, Ha, Ha, bigP);
+      o.bias = ga.theta + an.L[1].b_off; o.flags |= CF_BIAS_RELU | CF_MASK_GLOBAL;
+      o.gmask = a_mask1;
+      cb.gout(o, a_h1T);
+      o.head = CH_ACTION; o.J = A;
+      o.hw = ga.theta + an.L[2].w_off; o.hw_ld = Ha; o.hb = ga.theta + an.L[2].b_off;
+      o.hout = a_rm; o.hout2 = w->Xp.p;
+      cb.ops.push_back(o);
+    }
+    // critic_target over (s', a')
+    ChainBuf* bigT[2] = {&bigA, &bigP};
+    for (int i = 0; i < nq; ++i) {
+      const Net& cn = gc.nets[i];
+      ChainOp o = cb.op(cn.L[0].TW, Hc, Kin, bXn);
+      o.bias = gc.target + cn.L[0].b_off; o.flags |= CF_BIAS_RELU;
+      cb.out(o, *bigT[i]);
+      cb.ops.push_back(o);
+    }
+    for (int i = 0; i < nq; ++i) {
+      const Net& cn = gc.nets[i];
+      ChainOp o = cb.op(cn.L[1].TW, Hc, Hc, *bigT[i]);
+      o.bias = gc.target + cn.L[1].b_off; o.flags |= CF_BIAS_RELU;
+      o.head = CH_QTARGET; o.crit = i;
+      o.hw = gc.target + cn.L[2].w_off; o.hb = gc.target + cn.L[2].b_off;
+      cb.ops.push_back(o);
+    }
+    // online critics layer 1 + head + TD loss + dz1                           (ddpg.py:95-98, td3.py:105-112)
+    for (int i = 0; i < nq; ++i) {
+      const Net& cn = gc.nets[i];
+      ChainOp o = cb.op(cn.L[1].W, Hc, Hc, bigC[i]);
+      o.bias = gc.theta + cn.L[1].b_off; o.flags |= CF_BIAS_RELU;
+      o.head = CH_QLOSS; o.crit = i;
+      o.hw = gc.theta + cn.L[2].w_off; o.hb = gc.theta + cn.L[2].b_off;
+      o.vec_slot = cb.vec(gc.grad + cn.L[2].w_off, Hc);
+      o.vec2_slot = cb.vec(gc.grad + cn.L[1].b_off, Hc);
+      cb.out(o, *bigT[i]);  // dz1 reuses the target net's buffer (its last reader ran two ops earlier)
+      o.flags &= ~CF_OUT_SMEM;  // (written by the head code, not by the generic layer epilogue)
+      o.gout = c_dz1T[i].p; o.gout_rows = c_dz1T[i].rows;
+      cb.ops.push_back(o);
+    }
+    // dz0 = (dz1 . W1) (.) relu'(h0)
+    for (int i = 0; i < nq; ++i) {
+      const Net& cn = gc.nets[i];
+      ChainOp o = cb.op(cn.L[1].WT, Hc, Hc, *bigT[i]);
+      o.flags |= CF_APPLY_MASK | CF_COLSUM;
+      o.mask_slot = i;
+      o.vec_slot = cb.vec(gc.grad + cn.L[0].b_off, Hc);
+      cb.gout(o, c_dz0T[i]);
+      cb.ops.push_back(o);
+    }
+    cb.L.kind = 0; cb.L.nq = nq;
+    cb.L.gamma = static_cast<float>(c.gamma);
+    cb.L.inv_count = inv_count;
+    cb.L.r = w->r; cb.L.d = w->d;
+    for (int i = 0; i < nq; ++i) cb.L.gb3[i] = gc.grad + gc.nets[i].L[2].b_off;
+    cb.L.bump = 1; cb.L.bump_actor = do_actor ? 1 : 0;
+    b.stage(0).add_simt(cb.finish(B, Bp, p->chain_prof[0]), 1, true);
+    b.stage(0).bumps_tick = true;
+  }
+  // ---- critic weight gradients: dW1 = dz1^T . h0^T, dW0 = dz0^T . X^T (K = batch), one grouped launch
+  for (int i = 0; i < nq; ++i) {
+    const Net& cn = gc.nets[i];
+    {
+      GemmOp o = b.base_op(c_dz1T[i], c_h0T[i], pad128(Hc), cn.L[1].Kp, Bp);
+      o.rm = gc.grad + cn.L[1].w_off; o.rm_ld = cn.L[1].in; o.rm_m = cn.L[1].out; o.rm_n = cn.L[1].in;
+      b.stage(1).ops.push_back(o);
+    }
+    {
+      GemmOp o = b.base_op(c_dz0T[i], w->XT, pad128(Hc), cn.L[0].Kp, Bp);
+      o.rm = gc.grad + cn.L[0].w_off; o.rm_ld = cn.L[0].in; o.rm_m = cn.L[0].out; o.rm_n = cn.L[0].Kp;
+      o.map_a = A; o.map_a4 = A4; o.map_s = S;  // tiled [action | pad4 | state] -> reference [state | action]
+      b.stage(1).ops.push_back(o);
+    }
+  }
+  b.seg = 1;
+  {
+    const bool polyak = td3 ? do_actor : true;  // td3.py:81-84 ; ddpg.py:72-77
+    const int mode = 1 | 4 | (polyak ? (2 | 8) : 0);
+    const bool exit_barrier = !do_actor;
+    LossTail ltc{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
+    if (!do_actor && (p->flags & kFlagPublish)) ltc.pub = e->h_pub;
+    b.stage(2).add_simt([e, &gc, mode, exit_barrier, ltc](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc); });
+  }
+  if (!do_actor) return;
+  // ---- chain C: critic.Q1(s, pi(s)) with the updated critic, dX down to the action, policy backward
+  {
+    const Net& cn = gc.nets[0];
+    ChainBuilder cb(e);
+    ChainBuf bXp = cb.buf(Kin);
+    cb.input(w->Xp, bXp);
+    ChainBuf big0 = cb.buf(Hc), big1 = cb.buf(Hc), big2 = cb.buf(Ha);
+    {
+      ChainOp o = cb.op(cn.L[0].W, Hc, Kin, bXp);
+      o.bias = gc.theta + cn.L[0].b_off; o.flags |= CF_BIAS_RELU | CF_SAVE_MASK;
+      o.mask_slot = 0;
+      cb.out(o, big0);
+      cb.ops.push_back(o);
+    }
+    {
+      ChainOp o = cb.op(cn.L[1].W, Hc, Hc, big0);
+      o.bias = gc.theta + cn.L[1].b_off; o.flags |= CF_BIAS_RELU;
+      o.head = CH_QACTOR;
+      o.hw = gc.theta + cn.L[2].w_off; o.hb = gc.theta + cn.L[2].b_off;
+      cb.out(o, big1);
+      o.flags &= ~CF_OUT_SMEM;
+      cb.ops.push_back(o);
+    }
+    {
+      ChainOp o = cb.op(cn.L[1].WT, Hc, Hc, big1);
+      o.flags |= CF_APPLY_MASK;
+      o.mask_slot = 0;
+      o.head = CH_DXA; o.J = A;
+      o.hw = gc.theta + cn.L[0].w_off + S; o.hw_ld = cn.L[0].in;  // W0[f][S + j]: the action columns
+      o.aux = a_rm;
+      o.w2 = ga.theta + an.L[2].w_off; o.Ha = Ha;
+      o.mask2_slot = 1;
+      o.hout = dzaT.p;
+      o.vec_slot = cb.vec(ga.grad + an.L[1].b_off, Ha);
+      cb.out(o, big2);
+      o.flags &= ~CF_OUT_SMEM;
+      o.gout = a_dz1T.p; o.gout_rows = a_dz1T.rows;
+      cb.ops.push_back(o);
+    }
+    {
+      ChainOp o = cb.op(an.L[1].WT, Ha, Ha, big2);
+      o.flags |= CF_APPLY_MASK | CF_COLSUM;
+      o.mask_slot = 2;
+      o.vec_slot = cb.vec(ga.grad + an.L[0].b_off, Ha);
+      cb.gout(o, a_dz0T);
+      cb.ops.push_back(o);
+    }
+    cb.L.kind = 1; cb.L.nq = 1;
+    cb.L.inv_count = inv_count;
+    cb.L.gb_head = ga.grad + an.L[2].b_off; cb.L.J = A;
+    cb.L.n_gm = 2;
+    cb.L.gm_src[0] = a_mask1; cb.L.gm_slot[0] = 1;
+    cb.L.gm_src[1] = a_mask0; cb.L.gm_slot[1] = 2;
+    b.stage(3).add_simt(cb.finish(B, Bp, p->chain_prof[1]), 1, true);
+  }
+  // ---- actor weight gradients
+  {
+    GemmOp o = b.base_op(dzaT, a_h1T, 128, an.L[2].Kp, Bp);
+    o.rm = ga.grad + an.L[2].w_off; o.rm_ld = an.L[2].in; o.rm_m = an.L[2].out; o.rm_n = an.L[2].in;
+    b.stage(4).ops.push_back(o);
+  }
+  {
+    GemmOp o = b.base_op(a_dz1T, a_h0T, pad128(Ha), an.L[1].Kp, Bp);
+    o.rm = ga.grad + an.L[1].w_off; o.rm_ld = an.L[1].in; o.rm_m = an.L[1].out; o.rm_n = an.L[1].in;
+    b.stage(4).ops.push_back(o);
+  }
+  {
+    GemmOp o = b.base_op(a_dz0T, w->XT, pad128(Ha), an.L[0].Kp, Bp);
+    o.rm = ga.grad + an.L[0].w_off; o.rm_ld = an.L[0].in; o.rm_m = an.L[0].out; o.rm_n = an.L[0].Kp;
+    o.map_a = 0; o.map_a4 = A4; o.map_s = S;
+    b.stage(4).ops.push_back(o);
+  }
+  b.seg = 2;
+  {
+    LossTail lt{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
+    lt.pub = (p->flags & kFlagPublish) ? e->h_pub : nullptr;
+    b.stage(5).add_simt([e, &ga, lt](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt); });
+  }
+}
+
 static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   const oprl_cfg& c = e->cfg;
   const bool td3 = c.algo == OPRL_ALGO_TD3;
+  if (use_chain(e)) {
+    build_chain_ddpg_td3(e, w, p);
+    return;
+  }
   const bool do_actor = (p->flags & OPRL_UPDATE_ACTOR) != 0;
   const int B = w->B, Bp = w->Bp, A = c.action_dim, nq = c.n_critics;
   Builder b{e, w, p, c.gemm_mode == OPRL_GEMM_TC_TF32 ? 1 : 3};
@@ -1128,20 +1487,22 @@ static void launch_gemm_ops(oprl_engine* e, const Stage& sg, cudaStream_t st) {
   }
 }
 
-static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, bool gemm_only = false,
-                      bool simt_only = false, int max_stages = 1 << 30,
-                      const std::function<void()>& after_tick_bump = nullptr) {
+// what: 0 = every launch, 1 = GEMM launches only, 2 = SIMT launches only (no chain launches), 3 = chain launches only
+static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, int what = 0,
+                      int max_stages = 1 << 30, const std::function<void()>& after_tick_bump = nullptr) {
   int n = 0;
   bool forked = false;
   for (auto& sg : p->stages) {
     if (segment >= 0 && sg.segment != segment) continue;
     if (max_stages-- <= 0) break;
-    if (!sg.ops.empty() && !simt_only) {
+    if (!sg.ops.empty() && (what == 0 || what == 1)) {
       launch_gemm_ops(e, sg, st);
       n += static_cast<int>((sg.ops.size() + kMaxOps - 1) / kMaxOps);
     }
-    if (!gemm_only)
+    if (what != 1)
       for (size_t i = 0; i < sg.simt.size(); ++i) {
+        if (what == 2 && sg.simt_is_chain[i]) continue;
+        if (what == 3 && !sg.simt_is_chain[i]) continue;
         sg.simt[i](st);
         n += sg.simt_launches[i];
       }
@@ -1167,13 +1528,14 @@ static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
   prepare_stage_tables(e, p.get());
   CU(cudaStreamSynchronize(e->stream));  // workspace memsets / constant uploads done
   // capture: one graph per segment + one for the whole update
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < 8; ++k) {
+    if (k == 6) continue;  // the step graph (update + next gather) is captured by get_step_graph
     const int segment = (k >= 3) ? -1 : k;
     cudaGraph_t g = nullptr;
     CU(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
     int n = 0;
     try {
-      n = run_stages(e, p.get(), segment, e->own_stream, k == 4, k == 5);
+      n = run_stages(e, p.get(), segment, e->own_stream, k == 4 ? 1 : (k == 5 ? 2 : (k == 7 ? 3 : 0)));
     } catch (...) {
       cudaStreamEndCapture(e->own_stream, &g);
       if (g) cudaGraphDestroy(g);
@@ -1182,6 +1544,7 @@ static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
     CU(cudaStreamEndCapture(e->own_stream, &g));
     if (k == 3) p->n_launches = n;
     if (k == 4) p->n_gemm_launches = n;
+    if (k == 7) p->n_chain_launches = n;
     if (n > 0) {
       CU(cudaGraphInstantiate(&p->graph[k], g, 0));
     }
@@ -1349,6 +1712,7 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   e->stream = e->own_stream;
   CU(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   CU(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  CU(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
   e->A4 = pad4(cfg->action_dim);
   e->Kin = pad32(e->A4 + cfg->state_dim);
   const bool stochastic = cfg->algo == OPRL_ALGO_SAC || cfg->algo == OPRL_ALGO_TQC;
@@ -1390,7 +1754,7 @@ void oprl_engine_destroy(oprl_engine* e) {
   }
   for (auto& kv : e->work)
     for (auto& pv : kv.second->prog)
-      for (int k = 0; k < 7; ++k)
+      for (int k = 0; k < 8; ++k)
         if (pv.second->graph[k]) cudaGraphExecDestroy(pv.second->graph[k]);
   for (void* p : e->comm.opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->blocks) cudaFree(p);
@@ -1686,7 +2050,7 @@ static cudaGraphExec_t get_step_graph(oprl_engine* e, oprl_engine::Work* w, oprl
   bool forked = false;
   CU(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
   try {
-    run_stages(e, p, -1, e->own_stream, false, false, 1 << 30, [&]() {
+    run_stages(e, p, -1, e->own_stream, 0, 1 << 30, [&]() {
       CU(cudaEventRecord(e->cap_fork, e->own_stream));
       CU(cudaStreamWaitEvent(e->cap_side, e->cap_fork, 0));
       launch_gather(e, wn, g, e->cap_side, false, true);
@@ -1982,8 +2346,23 @@ int oprl_update_launches(oprl_engine* e, int B, int flags) {
   API_END
 }
 
+/* OPRL_B200_CHAIN_PROF=1: clock64 stamps of CTA 0 of the critic (which = 0) / actor (1) chain launch of
+ * the last update: [0] entry, [1] inputs staged, [2] last op done, [3] exit, [16 + i] MMA warp starts
+ * op i, [32 + i] accumulators of op i complete. */
+int oprl_chain_prof(oprl_engine* e, int B, int flags, int which, long long* out64) {
+  if (!e || B <= 0 || which < 0 || which > 1 || !out64) return fail(-1, "bad argument");
+  API_BEGIN
+  oprl_engine::Work* w = get_work(e, B);
+  Program* p = get_program(e, w, flags);
+  if (!p->chain_prof[which]) return fail(-1, "no chain profile (OPRL_B200_CHAIN_PROF=1 and a chain program)");
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaMemcpy(out64, p->chain_prof[which], 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+  API_END
+}
+
 /* what = 0: replay only the GEMM launches of one update `iters` times; what = 2: only its SIMT
- * launches; what = 1: the gather (device-side index draw) `iters` times.  Timed with CUDA events on the launch stream. */
+ * launches; what = 3: only its batch-slice chain launches (chain.cuh); what = 1: the gather (device-side index draw) `iters` times.  Timed with CUDA events on the launch stream. */
 int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* ms_total, int* launches_per_iter) {
   if (!e || B <= 0 || iters <= 0 || !ms_total) return fail(-1, "bad argument");
   API_BEGIN
@@ -2001,7 +2380,7 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
     CU(cudaStreamBeginCapture(e->own_stream, cudaStreamCaptureModeThreadLocal));
     int n = 0;
     try {
-      n = run_stages(e, p, -1, e->own_stream, false, false, what - 100);
+      n = run_stages(e, p, -1, e->own_stream, 0, what - 100);
     } catch (...) {
       cudaStreamEndCapture(e->own_stream, &g);
       if (g) cudaGraphDestroy(g);
@@ -2017,8 +2396,8 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
       if (prefix) CU(cudaGraphLaunch(prefix, e->stream));
       return 0;
     }
-    if (what == 0 || what == 2) {
-      cudaGraphExec_t ge = p->graph[what == 0 ? 4 : 5];
+    if (what == 0 || what == 2 || what == 3) {
+      cudaGraphExec_t ge = p->graph[what == 0 ? 4 : (what == 2 ? 5 : 7)];
       if (ge) CU(cudaGraphLaunch(ge, e->stream));
       return 0;
     }
@@ -2035,12 +2414,12 @@ int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* m
   CU(cudaEventDestroy(e0));
   CU(cudaEventDestroy(e1));
   if (prefix) CU(cudaGraphExecDestroy(prefix));
-  if (what == 2 || what >= 100) {
+  if (what == 2 || what == 3 || what >= 100) {
     // those replays ran the loss kernel (which advances DevState::tick) without oprl_update
     if (int rc = read_state(e)) return rc;
     e->host_tick = e->h_state->tick;
   }
-  if (launches_per_iter && what < 100) *launches_per_iter = what == 0 ? p->n_gemm_launches : 1;
+  if (launches_per_iter && what < 100) *launches_per_iter = what == 0 ? p->n_gemm_launches : (what == 3 ? p->n_chain_launches : 1);
   return 0;
   API_END
 }
