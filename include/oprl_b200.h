@@ -180,6 +180,14 @@ int oprl_gather_rows(const float* states, const float* actions, const float* rew
                      const float* dones, int E, int L, int S, int A, const int* ep_step_host,
                      int* ep_step_dev, int B, float* s, float* a, float* r, float* d, float* s2,
                      void* stream);
+/* Ingest edge -- EpisodicReplayBuffer.add_transition / add_episode (src/oprl/buffers/episodic_buffer.py:81-112).
+ * `staged_dev` holds n transitions already copied to the device, one row of S + A + 4 floats each:
+ * [state | action | reward | done | episode index (int32 bits) | step index (int32 bits)]; one launch writes them
+ * into the replay storage (states [E, L+1, S], actions [E, L, A], rewards / dones [E, L, 1]).  The caller
+ * guarantees 0 <= episode < E and 0 <= step < L (the Python buffer stages them from its own ring bookkeeping). */
+int oprl_scatter_transitions(float* states, float* actions, float* rewards, float* dones, int E, int L, int S, int A,
+                             const float* staged_dev, int n, void* stream);
+
 /* number of kernel launches one oprl_update(flags, OPRL_SEG_ALL) enqueues at batch B */
 int oprl_update_launches(oprl_engine* e, int B, int flags);
 
@@ -189,7 +197,7 @@ int oprl_update_launches(oprl_engine* e, int B, int flags);
  * events on the launch stream.  Leaves activations / batch in an unspecified state. */
 int oprl_profile(oprl_engine* e, int B, int flags, int what, int iters, float* ms_total,
                  int* launches_per_iter);
-/* Debug hook (OPRL_B200_CHAIN_PROF=1): 64 clock64 stamps of CTA 0 of the critic-step (which = 0) or
+/* Debug hook (OPRL_B200_CHAIN_PROF=1): 256 clock64 stamps of CTA 0 of the critic-step (which = 0) or
  * actor-step (1) chain launch of the last update; no reference counterpart. */
 int oprl_chain_prof(oprl_engine* e, int B, int flags, int which, long long* out64);
 

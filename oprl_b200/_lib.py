@@ -68,6 +68,8 @@ _SIGNATURES = {
     "oprl_comm_connect": (C.c_int, [_P, _P, _P]),
     "oprl_update_launches": (C.c_int, [_P, C.c_int, C.c_int]),
     "oprl_profile": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "oprl_scatter_transitions": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "oprl_chain_prof": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P]),
     "oprl_gather_rows": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P,
                                    C.c_int, _P, _P, _P, _P, _P, _P]),
 }

@@ -16,6 +16,29 @@ from .nn_functions import disable_gradient
 from .nn_models import adopt_parameters
 
 
+class _DetachedHook:
+    """What an ``_EngineDirtyHook`` unpickles to: a policy loaded from ``torch.save(algo.actor)`` has no engine."""
+
+    def __call__(self, *_) -> None:
+        return None
+
+
+class _EngineDirtyHook:
+    """``load_state_dict`` post-hook: the engine's tiled operand copies must be refreshed from theta.  A
+    module-level class (not a closure) so that the reference's ``t.save(self.algo.actor, ...)``
+    (trainers/base_trainer.py ``_save_policy``, distrib ``save_policy``) can pickle the module; the engine
+    handle itself never travels."""
+
+    def __init__(self, engine: UpdateEngine) -> None:
+        self._engine = engine
+
+    def __call__(self, *_) -> None:
+        self._engine.mark_params_dirty()
+
+    def __reduce__(self):
+        return (_DetachedHook, ())
+
+
 class EngineAdam:
     """Read-only view of the engine's fused Adam state (stands where the reference keeps a
     ``torch.optim.Adam``: ddpg.py:51,56)."""
@@ -70,18 +93,41 @@ class OffPolicyAlgorithm:
             disable_gradient(self.actor_target)
         for mod in (self.actor, self.critic, self.critic_target, getattr(self, "actor_target", None)):
             if mod is not None:
-                mod.register_load_state_dict_post_hook(lambda *_: self.engine.mark_params_dirty())
+                mod.register_load_state_dict_post_hook(_EngineDirtyHook(self.engine))
         self.engine.mark_params_dirty()
 
     def _hand_batch(self, state, action, reward, done, next_state) -> None:
         """update() accepts any five tensors (int64 ``done`` and aliased state / next_state
         included: tests/functional/test_rl_algos.py:25-31); tensors that are the engine's own
         sampled batch (``attach_buffer`` + ``sample``) are used in place."""
+        five = (state, action, reward, done, next_state)
         token = getattr(state, "_oprl_batch_token", None)
         if token is not None and token == getattr(self.engine, "last_batch_token", None):
-            return
+            # skip the copy-in only if ALL five tensors are the ones the latest sample() call handed out, with no
+            # in-place edit since (tensor._version as stamped): the engine's operand layout then already holds them
+            if all(getattr(x, "_oprl_batch_token", None) == token and x._version == getattr(x, "_oprl_version", -1)
+                   for x in five):
+                return
         self.engine.last_batch_token = None
-        self.engine.load_batch(state, action, reward, done, next_state)
+        self.engine.load_batch(*five)
+
+    # ------------------------------------------------------------------ host rollouts
+    def enable_host_rollout(self, refresh_every: int = 1):
+        """``actor.explore`` / ``actor.exploit`` run on a CPU mirror of the actor whose weights follow the device
+        arena through asynchronous D2H copies into pinned memory every ``refresh_every`` updates -- the
+        environment loop never synchronises with the GPU (reference acting path
+        trainers/base_trainer.py:46-54)."""
+        from .host_mirror import HostPolicyMirror
+
+        if self.engine._params_dirty:
+            self.engine.sync_params()
+        self._mirror = HostPolicyMirror(self.actor, self.engine.arena["actor"]["theta"], refresh_every)
+        self.actor.__dict__["_host_mirror"] = self._mirror
+        return self._mirror
+
+    def disable_host_rollout(self) -> None:
+        self.actor.__dict__.pop("_host_mirror", None)
+        self._mirror = None
 
     def attach_buffer(self, buffer) -> None:
         """Fuse ``buffer.sample()`` with this algorithm's engine: the gather kernel then writes
@@ -117,6 +163,12 @@ class OffPolicyAlgorithm:
             dist.barrier(group=self._dp_group)
 
     def _run_update(self, actor_step: bool) -> None:
+        self._run_update_device(actor_step)
+        mirror = getattr(self, "_mirror", None)
+        if mirror is not None:
+            mirror.after_update()
+
+    def _run_update_device(self, actor_step: bool) -> None:
         eng = self.engine
         group = getattr(self, "_dp_group", None)
         if group is None or eng.fused_comm:
@@ -148,7 +200,10 @@ class OffPolicyAlgorithm:
             eng.step(batch_size, self._wants_actor_step())
         else:
             eng.sample(batch_size, None)
-            self._run_update(self._wants_actor_step())
+            self._run_update_device(self._wants_actor_step())
+        mirror = getattr(self, "_mirror", None)
+        if mirror is not None:
+            mirror.after_update()
         self._after_update()
 
     def _after_update(self) -> None:

@@ -106,11 +106,17 @@ class DeterministicPolicy(nn.Module):
         return t.tanh(self.mlp(states))
 
     def exploit(self, state: npt.NDArray) -> npt.NDArray:
+        mirror = self.__dict__.get("_host_mirror")
+        if mirror is not None:  # rollouts on the host copy (algos/host_mirror.py): no device round trip
+            return mirror.exploit(state)
         with t.no_grad():
             x = t.as_tensor(state).unsqueeze(0).to(self._device)
             return self.forward(x).cpu().numpy().flatten()
 
     def explore(self, state: npt.NDArray) -> npt.NDArray:
+        mirror = self.__dict__.get("_host_mirror")
+        if mirror is not None:
+            return mirror.explore(state)
         # reference quirk kept: exploration acts on the pre-tanh output (nn_models.py:144-150)
         with t.no_grad():
             x = t.as_tensor(state, device=self._device).unsqueeze(0)
@@ -153,11 +159,17 @@ class GaussianActor(nn.Module):
         return action, dist.log_prob(pre).sum(dim=1, keepdim=True)
 
     def explore(self, state: npt.NDArray) -> npt.NDArray:
+        mirror = self.__dict__.get("_host_mirror")
+        if mirror is not None:  # rollouts on the host copy (algos/host_mirror.py): no device round trip
+            return mirror.explore(state)
         with t.no_grad():
             action, _ = self.forward(t.as_tensor(state, device=self.device).unsqueeze(0))
         return action.cpu().numpy()[0]
 
     def exploit(self, state: npt.NDArray) -> npt.NDArray:
+        mirror = self.__dict__.get("_host_mirror")
+        if mirror is not None:
+            return mirror.exploit(state)
         was_training = self.training
         self.eval()
         try:

@@ -43,6 +43,9 @@ class EpisodicReplayBuffer:
     max_episode_lenth: int = 1000  # [sic] reference spelling, episodic_buffer.py:19
     episodes_counter: int = 1
     device: str = "cuda"
+    # False (default): sample() returns fresh tensors like the reference's advanced indexing does.  True: it
+    # returns views of the engine's one batch arena -- no copy, but the NEXT sample() overwrites them.
+    zero_copy_batches = False  # (plain class attribute: the dataclass fields stay exactly the reference's)
 
     _tensors: dict = field(init=False, default_factory=dict)
     _max_episodes: int = field(init=False, default=0)
@@ -63,6 +66,7 @@ class EpisodicReplayBuffer:
         self._tensors = {"actions": z(E, Lmax, self.action_dim), "rewards": z(E, Lmax, 1),
                          "dones": z(E, Lmax, 1), "states": z(E, Lmax + 1, self.state_dim)}
         self.ep_lens = [0] * E
+        self._stage_init()
         self._engine = None
         self._token = 0
         self._idx_dev = None
@@ -76,31 +80,94 @@ class EpisodicReplayBuffer:
     @property
     def states(self) -> t.Tensor:
         self.check_created()
+        self.flush()  # readers see every transition added so far
         return self._tensors["states"]
 
     @property
     def actions(self) -> t.Tensor:
         self.check_created()
+        self.flush()  # readers see every transition added so far
         return self._tensors["actions"]
 
     @property
     def rewards(self) -> t.Tensor:
         self.check_created()
+        self.flush()  # readers see every transition added so far
         return self._tensors["rewards"]
 
     @property
     def dones(self) -> t.Tensor:
         self.check_created()
+        self.flush()  # readers see every transition added so far
         return self._tensors["dones"]
 
     # ------------------------------------------------------------------ ingest edge
+    # Transitions are staged in a pinned host ring ([state | action | reward | done | episode | step] per row) and
+    # reach the replay storage in batches: ONE async H2D copy + ONE scatter kernel per flush -- before the next
+    # sample(), when the ring is half full, and once per add_episode() -- instead of the two pageable copies and
+    # two fill kernels per transition of a literal translation (episodic_buffer.py:89-96).
+    _STAGE_ROWS = 4096
+
+    def _stage_init(self) -> None:
+        W = self.state_dim + self.action_dim + 4
+        self._stage_host = t.zeros(self._STAGE_ROWS, W, dtype=t.float32).pin_memory()
+        self._stage_np = self._stage_host.numpy()
+        self._stage_int = self._stage_np.view(np.int32)
+        self._stage_dev = t.zeros(self._STAGE_ROWS, W, dtype=t.float32, device=self.device)
+        self._stage_lo = 0  # first row not yet flushed
+        self._stage_hi = 0  # next free row
+        self._stage_events = []  # (first row, last row + 1, event) of flushes whose H2D may still read the ring
+
+    def _stage_wait_rows(self, lo: int, hi: int) -> None:
+        keep = []
+        for a, b, ev in self._stage_events:
+            if a < hi and lo < b:
+                ev.synchronize()
+            elif not ev.query():
+                keep.append((a, b, ev))
+        self._stage_events = keep
+
+    def flush(self) -> None:
+        """Move every staged transition into the replay storage (async on the current stream)."""
+        lo, hi = self._stage_lo, self._stage_hi
+        if hi == lo or not self._created:
+            return
+        dev = self._stage_dev[lo:hi]
+        dev.copy_(self._stage_host[lo:hi], non_blocking=True)
+        T = self._tensors
+        E, L1, S = T["states"].shape
+        with t.cuda.device(T["states"].device):
+            stream = t.cuda.current_stream(T["states"].device).cuda_stream or 1
+            L.check(L.lib().oprl_scatter_transitions(
+                T["states"].data_ptr(), T["actions"].data_ptr(), T["rewards"].data_ptr(), T["dones"].data_ptr(),
+                E, L1 - 1, S, self.action_dim, dev.data_ptr(), hi - lo, C.c_void_p(stream)))
+            ev = t.cuda.Event()
+            ev.record()
+        self._stage_events.append((lo, hi, ev))
+        if hi >= self._STAGE_ROWS:
+            hi = 0
+        self._stage_lo = self._stage_hi = hi
+
     def add_transition(self, state: npt.NDArray, action: npt.NDArray, reward: float, done: bool,
                        episode_done: bool | None = None) -> None:
         ep, i = self._ep_pointer, self.ep_lens[self._ep_pointer]
-        self.states[ep, i].copy_(t.as_tensor(np.asarray(state)), non_blocking=True)
-        self.actions[ep, i].copy_(t.as_tensor(np.asarray(action)), non_blocking=True)
-        self.rewards[ep, i] = reward
-        self.dones[ep, i] = float(done)
+        if i >= self.max_episode_lenth:
+            raise IndexError(f"episode {ep} exceeds max_episode_lenth={self.max_episode_lenth}")
+        row = self._stage_hi
+        if self._stage_events:
+            self._stage_wait_rows(row, row + 1)
+        S, A = self.state_dim, self.action_dim
+        r = self._stage_np[row]
+        r[:S] = state
+        r[S:S + A] = action
+        r[S + A] = reward
+        r[S + A + 1] = float(done)
+        ri = self._stage_int[row]
+        ri[S + A + 2] = ep
+        ri[S + A + 3] = i
+        self._stage_hi = row + 1
+        if self._stage_hi - self._stage_lo >= self._STAGE_ROWS // 2 or self._stage_hi >= self._STAGE_ROWS:
+            self.flush()
         self.ep_lens[ep] += 1
         self._number_transitions = min(self._number_transitions + 1, self.buffer_size_transitions)
         if episode_done:
@@ -118,12 +185,18 @@ class EpisodicReplayBuffer:
         for s, a, r, d, _ in episode:
             self.add_transition(s, a, r, d, episode_done=d)
         self._inc_episode()
+        self.flush()
 
     # --------------------------------------------------------------------- sample
     def attach_engine(self, engine) -> None:
         """Let ``sample()`` gather straight into ``engine``'s operand layout."""
         engine.bind_buffer(self.states, self.actions, self.rewards, self.dones)
         self._engine = engine
+
+    def storage(self) -> dict:
+        """The four storage tensors with every staged transition flushed (checkpoints, tests)."""
+        self.flush()
+        return self._tensors
 
     def draw_indices(self, batch_size: int) -> np.ndarray:
         """The reference's index draw: global numpy RNG, uniform over stored transitions."""
@@ -132,13 +205,21 @@ class EpisodicReplayBuffer:
         return np.stack([ep, step], axis=1).astype(np.int32)
 
     def sample(self, batch_size: int) -> tuple[t.Tensor, t.Tensor, t.Tensor, t.Tensor, t.Tensor]:
+        self.flush()
         ep_step = self.draw_indices(batch_size)
         if self._engine is not None:
             out = self._engine.sample(batch_size, ep_step)
+            if not self.zero_copy_batches:
+                out = self._engine.batch_copy(batch_size)
             self._token += 1
             token = (id(self), self._token)
+            # The gather also wrote the engine's operand layout, so update(*batch) can skip its copy-in -- but
+            # only for exactly these five tensors, unmodified, before another sample(): the token + version
+            # stamp let update() detect anything else (a batch kept across a later sample(), replaced or edited
+            # tensors) and fall back to loading what it was actually passed.
             for x in out:
                 x._oprl_batch_token = token
+                x._oprl_version = x._version
             self._engine.last_batch_token = token
             return out
         return self.gather(ep_step)

@@ -40,7 +40,7 @@ def load_algo_state(algo, state: dict[str, Any]) -> None:
 
 def buffer_state(buf) -> dict[str, Any]:
     return {
-        "tensors": {k: v.detach().cpu().clone() for k, v in buf._tensors.items()},
+        "tensors": {k: v.detach().cpu().clone() for k, v in buf.storage().items()},
         "ep_lens": list(buf.ep_lens),
         "ep_pointer": buf._ep_pointer,
         "episodes_counter": buf.episodes_counter,
@@ -49,6 +49,7 @@ def buffer_state(buf) -> dict[str, Any]:
 
 
 def load_buffer_state(buf, state: dict[str, Any]) -> None:
+    buf.flush()
     for k, v in state["tensors"].items():
         buf._tensors[k].copy_(v.to(buf._tensors[k].device))
     buf.ep_lens = list(state["ep_lens"])
@@ -65,7 +66,7 @@ def save_checkpoint(path, algo, replay_buffer=None) -> None:
 
 
 def load_checkpoint(path, algo, replay_buffer=None) -> None:
-    blob = torch.load(path, map_location="cpu", weights_only=False)
+    blob = torch.load(path, map_location="cpu", weights_only=True)  # tensors + plain containers only
     load_algo_state(algo, blob["algo"])
     if replay_buffer is not None and "buffer" in blob:
         load_buffer_state(replay_buffer, blob["buffer"])

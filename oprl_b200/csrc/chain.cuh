@@ -23,12 +23,17 @@
 // epilogue of the layer that produces their input (fp32 FMA, warp butterfly + fixed-order
 // cross-warp sum), and K <= 8 layers (the policy head backward) are a few FMAs per thread.
 //
-// Warp roles (17 warps, 96 registers each: a sub-partition of the SM hosts five of them): 0 = MMA
-// issuer (+ TMEM owner), 1-8 = weight feeders (two per TMEM lane quarter, alternating 16 KB chunks,
-// one chunk prefetched in registers, split and stored eight K columns at a time to stay inside the
-// register budget), 9-16 = epilogue (lane quarter x M tile).  The weight stream is the bound (measured 303 cycles per [128 x 32] chunk,
-// tools/experiments/chain_probe3.cu) and runs ahead of the MMAs through a 5-slot TMEM ring, across
-// layer boundaries, so a layer costs its chunk count x ~0.16 us and nothing else.
+// Warp roles (18 warps; a sub-partition of the SM hosts at most five, so 96 registers per thread):
+//   0-1   MMA issuers, one per M tile (128 output features) of the layer.  A single warp issuing every MMA is
+//         the bottleneck of this design: the ~100 scalar instructions between two chunks (barrier wait, fence,
+//         elect, descriptor words into uniform registers, 12 MMAs, commit) are serial latency, ~500 cycles per
+//         chunk against ~130 of tensor time.  The two M tiles have separate accumulators, so two warps can
+//         issue side by side without changing any accumulation order; the chunk stream interleaves the tiles.
+//   2-9   weight feeders, two per TMEM lane quarter alternating 16 KB chunks: L2 -> registers (one chunk
+//         prefetched) -> tf32 hi/lo split -> tcgen05.st, eight K columns at a time (register budget).
+//   10-17 epilogue, one per (lane quarter, M tile): a thread owns one feature row of the layer output.
+// The weight stream runs ahead of the MMAs through a ring of TMEM slots, across layer boundaries; the
+// accumulators are double-buffered so the read-out of one layer overlaps the MMAs of the next.
 //
 // Reference semantics: ddpg.py:86-107, td3.py:95-141 (see engine.cu build_chain_ddpg_td3).
 #pragma once
@@ -37,18 +42,19 @@
 namespace oprl {
 
 constexpr int kNB = 16;                  // batch rows (MMA N) per CTA
-constexpr int kChainWarps = 17;
+constexpr int kChainWarps = 18;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kChainThreads = kChainWarps * 32;
 constexpr int kCorePitch = 144;          // bytes between K-adjacent 8x16B core matrices of an operand buffer
                                          // (128 + 16: the feature-per-lane scalar stores hit 32 distinct banks)
-constexpr int kCSlots = 5;               // TMEM ring of split A chunks (64 columns each)
-constexpr int kCAcc = 5;                 // accumulators per M tile: cross terms + up to 4 hi*hi groups
-constexpr int kCACol0 = 192;             // first TMEM column of the A ring (accumulators: 2 x 5 x 16 = 160)
+constexpr int kCSlots = 6;               // most TMEM ring slots of split A chunks (64 columns each; ChainLaunch::n_slots are used)
+constexpr int kCAcc = 5;                 // accumulator slots per M tile: cross terms + up to 4 hi*hi groups
 constexpr int kCMaxOps = 16;
 constexpr int kCMaxChunks = 192;
 constexpr int kCMaxBufs = 12;
 constexpr int kCMaxVec = 8;
-constexpr int kCMaxJ = 8;
+constexpr int kCMaxJ = 6;               // widest narrow head (action dimensions) done in an epilogue
 constexpr int kCMaskSlots = 4;
 constexpr int kCFeat = 256;              // widest layer (2 M tiles)
 
@@ -82,6 +88,7 @@ struct ChainOp {
   float* hout;          // CH_ACTION: row-major [Bp x J] (nullable) ; CH_DXA: CT32 [128 x Bp] (dz of the policy head, transposed)
   float* hout2;         // CH_ACTION: CT32 [Bp x ..] input matrix whose action columns get the result (nullable)
   int w_rows, mtiles, kchunks;
+  int group;            // K chunks per hi*hi accumulator (2: chains of 8 MMAs; 4: chains of 16, two accumulators fewer to read out)
   int in_hi, in_lo, in_sbo, in_bar, in_phase;   // input operand buffer (byte offsets into dynamic smem)
   int out_hi, out_lo, out_sbo, out_bar;         // CF_OUT_SMEM / head output buffer
   int x_hi, x_lo, x_sbo, x_bar;                 // CH_ACTION: operand buffer receiving the action rows (x_bar < 0: none)
@@ -100,8 +107,17 @@ struct ChainInput {   // tiled [Bp x 32 * kchunks] matrix whose 16-row slice bec
   int hi, lo, sbo, bar;
 };
 
+struct ChainMmaOp {  // what the MMA-issuing warp needs of one op, in kernel-parameter (constant) space so that its
+                     // loop runs on the uniform datapath
+  uint32_t in_hi, in_lo;  // byte offsets of the input operand buffer (hi / lo halves) in dynamic shared memory
+  uint32_t dw_hi;         // descriptor high word: SBO >> 4 | version 1 << 14
+  uint8_t in_bar, in_phase, mtiles, kchunks;
+  uint8_t group, pad[3];
+};
+
 struct ChainLaunch {
   const ChainOp* ops;
+  ChainMmaOp mop[kCMaxOps];
   int n_ops;
   int B, Bp, n_cta;
   int n_in;
@@ -125,19 +141,24 @@ struct ChainLaunch {
   int J;
   DevState* st;
   int bump, bump_actor;
+  // TMEM plan: two accumulator regions of d_cols columns (op i uses region i & 1, so the read-out of one
+  // op overlaps the MMAs of the next), then n_slots x 64 columns of split A chunks from column a_col0
+  int d_cols, a_col0, n_slots;
   long long* prof;  // selftest / profiling: clock64 stamps of CTA 0 (nullable)
+  int pitch;        // bytes between K-adjacent core matrices of the operand buffers (kCorePitch)
+  int debug;        // timing experiments only: 2 = no weight loads, 4 = no tcgen05.st (results invalid); 8 = waiting warps poll in a tight loop instead of backing off with nanosleep
 };
 
 struct ChainCtl {
   uint64_t a_full[kCSlots], a_empty[kCSlots];
-  uint64_t d_full, d_free;
+  uint64_t d_full[2], d_free[2];
   uint64_t buf_bar[kCMaxBufs];
   uint32_t tmem_slot;
   uint32_t last_flag;
   const float* chunk_src[kCMaxChunks];
   ChainOp ops[kCMaxOps];
   uint32_t mask[kCMaskSlots][kCFeat];
-  float red[2][8][kCMaxJ][kNB];
+  float red[2][kEpiWarps][kCMaxJ][kNB];
   float qn_s[2][kNB];
   float dq_s[2][kNB];
   float rr[kNB], dd[kNB];
@@ -212,7 +233,51 @@ __device__ __forceinline__ float half_warp_sum(float x) {
   return x;
 }
 
+// wait with back-off: a warp that polls an mbarrier in a tight loop takes issue slots and shared-memory
+// cycles from the warps it is waiting for
+__device__ __forceinline__ void chain_wait(uint64_t* bar, uint32_t parity, bool backoff) {
+  if (!backoff) {
+    ptx::mbar_wait(bar, parity);
+    return;
+  }
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    __nanosleep(40);
+    if (++spins > (1u << 24)) {
+      if ((threadIdx.x & 31) == 0) printf("oprl: chain mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 #define CHAIN_EPI_BAR() asm volatile("bar.sync 1, 256;\n" ::: "memory")
+
+// one feature row (16 batch columns) -> operand buffer (tf32 hi / lo), K-major core-matrix layout
+__device__ __forceinline__ void chain_store_operand(uint8_t* csm, int off_hi, int off_lo, int sbo, int pitch, int f, const float* x) {
+  uint8_t* bh = csm + off_hi + (f >> 2) * pitch + (f & 3) * 4;
+  uint8_t* bl = csm + off_lo + (f >> 2) * pitch + (f & 3) * 4;
+#pragma unroll
+  for (int n = 0; n < kNB; ++n) {
+    float h, l;
+    ptx::split_tf32(x[n], h, l);
+    const int off = (n >> 3) * sbo + (n & 7) * 16;
+    *reinterpret_cast<float*>(bh + off) = h;
+    *reinterpret_cast<float*>(bl + off) = l;
+  }
+}
+// one feature row -> transposed-tiled global matrix [rows x Bp], columns n0 .. n0 + 15
+__device__ __forceinline__ void chain_store_gout(float* g, int rows, int f, int n0, const float* x) {
+  float* dst = g + ct_index(rows, f, n0);
+#pragma unroll
+  for (int n4 = 0; n4 < kNB / 4; ++n4)
+    *reinterpret_cast<float4*>(dst + n4 * 32) = make_float4(x[4 * n4], x[4 * n4 + 1], x[4 * n4 + 2], x[4 * n4 + 3]);
+}
+// total of the eight epilogue warps' partials, in warp order
+__device__ __forceinline__ float chain_red8(const float (*red)[kCMaxJ][kNB], int j, int n, int nw) {
+  float s = red[0][j][n];
+  for (int w = 1; w < nw; ++w) s += red[w][j][n];
+  return s;
+}
 
 __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_constant__ ChainLaunch L) {
   extern __shared__ __align__(1024) uint8_t csm[];
@@ -234,12 +299,12 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   if (warp == 0) {
     if (lane < kCSlots) {
       ptx::mbar_init(&C.a_full[lane], 4);   // the four quarter warps of one feeder half
-      ptx::mbar_init(&C.a_empty[lane], 1);  // tcgen05.commit
-    } else if (lane == kCSlots) {
-      ptx::mbar_init(&C.d_full, 1);
-      ptx::mbar_init(&C.d_free, 8);
+      ptx::mbar_init(&C.a_empty[lane], 1);  // tcgen05.commit of the MMA warp that consumed the chunk
+    } else if (lane < kCSlots + 2) {
+      ptx::mbar_init(&C.d_full[lane - kCSlots], 2);          // one commit per MMA warp
+      ptx::mbar_init(&C.d_free[lane - kCSlots], kEpiWarps);  // one arrival per epilogue warp
     } else if (lane >= 8 && lane < 8 + kCMaxBufs) {
-      ptx::mbar_init(&C.buf_bar[lane - 8], 8);  // one arrival per epilogue warp
+      ptx::mbar_init(&C.buf_bar[lane - 8], kEpiWarps);
     }
     ptx::fence_mbar_init();
     __syncwarp();
@@ -248,94 +313,119 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  // chunk table: flat chunk index -> source of its 16 KB (op, M tile, K chunk)
+  // chunk table: flat chunk index -> source of its 16 KB.  Inside an op the M tiles alternate (K chunk 0 of
+  // tile 0, K chunk 0 of tile 1, K chunk 1 of tile 0, ...) so that both MMA warps always have work.
   if (tid < L.n_ops) {
     int g0 = 0;
     for (int i = 0; i < tid; ++i) g0 += C.ops[i].mtiles * C.ops[i].kchunks;
     const ChainOp& o = C.ops[tid];
-    for (int mt = 0; mt < o.mtiles; ++mt)
-      for (int c = 0; c < o.kchunks; ++c)
-        C.chunk_src[g0 + mt * o.kchunks + c] = o.w + (static_cast<size_t>(c) * (o.w_rows >> 3) + mt * 16) * 256;
+    for (int c = 0; c < o.kchunks; ++c)
+      for (int mt = 0; mt < o.mtiles; ++mt)
+        C.chunk_src[g0 + c * o.mtiles + mt] = o.w + (static_cast<size_t>(c) * (o.w_rows >> 3) + mt * 16) * 256;
   }
   if (tid < 32) C.tail_s[tid] = 0.f;
   __syncthreads();
   int total_chunks = 0;
   for (int i = 0; i < L.n_ops; ++i) total_chunks += C.ops[i].mtiles * C.ops[i].kchunks;
   const uint32_t tmem = C.tmem_slot;
+  const int n_slots = L.n_slots;
+  const uint32_t a_col0 = static_cast<uint32_t>(L.a_col0);
+  const int pitch = L.pitch;
+  const bool backoff = (L.debug & 8) == 0;  // default on; OPRL_B200_CHAIN_DEBUG=8 makes every wait a tight poll
 
-  if (warp == 0) {
-    // ================================================================= MMA issuer
+  if (warp < 2) {
+    // ================================================================= MMA issuers (warp m: M tile m)
+    const int m = warp;
     const uint32_t idesc = ptx::idesc_tf32(128, kNB, 0, 0);
-    int g = 0;
+    const uint32_t kstep = static_cast<uint32_t>(2 * pitch) >> 4;  // one K = 8 step, in the descriptor's 16-byte units
+    const uint32_t smem_base16 = ptx::smem_u32(csm) >> 4;
+    const uint32_t lbo_bits = (static_cast<uint32_t>(pitch) >> 4) << 16;
+    uint32_t slot = 0, full_par = 0;  // running over ALL chunks (both warps count every chunk)
+    long long m_opwait = 0;
     for (int oi = 0; oi < L.n_ops; ++oi) {
-      const ChainOp& o = C.ops[oi];
-      ptx::mbar_wait(&C.buf_bar[o.in_bar], static_cast<uint32_t>(o.in_phase & 1));
-      if (oi > 0) ptx::mbar_wait(&C.d_free, static_cast<uint32_t>((oi - 1) & 1));
+      const ChainMmaOp o = L.mop[oi];
+      const int r = oi & 1, k = oi >> 1;  // accumulator region, its k-th use
+      const long long tw0 = prof ? clock64() : 0;
+      chain_wait(&C.buf_bar[o.in_bar], static_cast<uint32_t>(o.in_phase & 1), backoff);
+      if (k > 0) chain_wait(&C.d_free[r], static_cast<uint32_t>((k - 1) & 1), backoff);
       ptx::tc_fence_after();
-      if (prof && lane == 0 && oi < 16) prof[16 + oi] = clock64();
-      const uint32_t b_hi0 = ptx::smem_u32(csm + o.in_hi);
-      const uint32_t b_lo0 = ptx::smem_u32(csm + o.in_lo);
-      const uint32_t sbo = static_cast<uint32_t>(o.in_sbo);
-      for (int mt = 0; mt < o.mtiles; ++mt) {
-        const uint32_t d_cross = tmem + static_cast<uint32_t>(mt * kCAcc * kNB);
-        uint32_t big = d_cross + kNB;
-        int in_group = 0;
-        for (int c = 0; c < o.kchunks; ++c, ++g) {
-          const int slot = g % kCSlots;
-          ptx::mbar_wait(&C.a_full[slot], static_cast<uint32_t>((g / kCSlots) & 1));
-          ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint32_t ta_hi = tmem + kCACol0 + static_cast<uint32_t>(slot * 64);
-            const uint32_t ta_lo = ta_hi + 32u;
+      if (prof) m_opwait += clock64() - tw0;
+      if (prof && lane == 0 && m == 0 && oi < 16) prof[16 + oi] = clock64();
+      // descriptor words: low = start >> 4 | LBO >> 4 << 16, high = SBO >> 4 | version 1 << 14
+      const uint32_t dw_hi = o.dw_hi;
+      uint32_t dl_hi = ((smem_base16 + (o.in_hi >> 4)) & 0x3FFFu) | lbo_bits;
+      uint32_t dl_lo = ((smem_base16 + (o.in_lo >> 4)) & 0x3FFFu) | lbo_bits;
+      const int group = o.group;
+      const int kchunks = o.kchunks;
+      const int mtiles = o.mtiles;
+      const uint32_t acc_cols = static_cast<uint32_t>((1 + (kchunks + group - 1) / group) * kNB);
+      const uint32_t d_cross = tmem + static_cast<uint32_t>(r * L.d_cols) + static_cast<uint32_t>(m) * acc_cols;
+      uint32_t big = d_cross + kNB;
+      int in_group = 0;
+      for (int c = 0; c < kchunks; ++c) {
+        for (int mt = 0; mt < mtiles; ++mt) {
+          if (mt == m) {
+            ptx::mbar_wait(&C.a_full[slot], full_par);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t ta_hi = tmem + a_col0 + slot * 64u;
+              const uint32_t ta_lo = ta_hi + 32u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t koff = static_cast<uint32_t>((c * 8 + 2 * j) * kCorePitch);
-              const uint64_t db_hi = ptx::smem_desc(b_hi0 + koff, kCorePitch, sbo);
-              const uint64_t db_lo = ptx::smem_desc(b_lo0 + koff, kCorePitch, sbo);
-              ptx::mma_tf32_ts(d_cross, ta_lo + 8u * j, db_hi, idesc, (c | j) ? 1u : 0u);
-              ptx::mma_tf32_ts(d_cross, ta_hi + 8u * j, db_lo, idesc, 1u);
-              ptx::mma_tf32_ts(big, ta_hi + 8u * j, db_hi, idesc, (in_group | j) ? 1u : 0u);
+              for (int j = 0; j < 4; ++j) {
+                ptx::mma_tf32_ts2(d_cross, ta_lo + 8u * j, dl_hi + j * kstep, dw_hi, idesc, (c | j) ? 1u : 0u);
+                ptx::mma_tf32_ts2(d_cross, ta_hi + 8u * j, dl_lo + j * kstep, dw_hi, idesc, 1u);
+                ptx::mma_tf32_ts2(big, ta_hi + 8u * j, dl_hi + j * kstep, dw_hi, idesc, (in_group | j) ? 1u : 0u);
+              }
+              ptx::mma_commit(&C.a_empty[slot]);
             }
-            ptx::mma_commit(&C.a_empty[slot]);
+            __syncwarp();
           }
-          __syncwarp();
-          if (++in_group == 2) {
-            in_group = 0;
-            big += kNB;
+          if (++slot == static_cast<uint32_t>(n_slots)) {
+            slot = 0;
+            full_par ^= 1u;
           }
         }
+        dl_hi += 4 * kstep;
+        dl_lo += 4 * kstep;
+        if (++in_group == group) {
+          in_group = 0;
+          big += kNB;
+        }
       }
-      if (ptx::elect_one()) ptx::mma_commit(&C.d_full);
+      if (ptx::elect_one()) ptx::mma_commit(&C.d_full[r]);  // (a warp that issued nothing for this op arrives at once)
       __syncwarp();
     }
-  } else if (warp <= 8) {
+    if (prof && lane == 0 && m == 0) prof[61] = m_opwait;  // cycles waiting at op boundaries (operand written, region free)
+  } else if (warp < 10) {
     // ================================================================= weight feeders
-    const int q = warp & 3, half = (warp - 1) >> 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const uint32_t ta_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + kCACol0;
+    const uint32_t ta_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + a_col0;
     const int roff = (row >> 3) * 64 + (row & 7);  // float4 index of this row inside a chunk (+ 8 per k core)
     ptx::pdl_wait();  // the weights are the previous launch's (Adam) output
+    long long t_wait = 0, t_work = 0;
     float4 nx[8];
     if (half < total_chunks) {
       const float4* s = reinterpret_cast<const float4*>(C.chunk_src[half]) + roff;
 #pragma unroll
       for (int j = 0; j < 8; ++j) nx[j] = __ldg(s + j * 8);
     }
+    int slot = half % n_slots, wraps = half / n_slots;
     for (int g = half; g < total_chunks; g += 2) {
       float4 x[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) x[j] = nx[j];
-      if (g + 2 < total_chunks) {
+      if (g + 2 < total_chunks && !(L.debug & 2)) {
         const float4* s = reinterpret_cast<const float4*>(C.chunk_src[g + 2]) + roff;
 #pragma unroll
         for (int j = 0; j < 8; ++j) nx[j] = __ldg(s + j * 8);
       }
-      const int slot = g % kCSlots;
-      const int use = g / kCSlots;
-      if (use > 0) {
-        ptx::mbar_wait(&C.a_empty[slot], static_cast<uint32_t>((use - 1) & 1));
+      const long long t0 = prof ? clock64() : 0;
+      if (wraps > 0) {
+        chain_wait(&C.a_empty[slot], static_cast<uint32_t>((wraps - 1) & 1), backoff);
         ptx::tc_fence_after();
       }
+      const long long t1 = prof ? clock64() : 0;
       const uint32_t ta = ta_lane + static_cast<uint32_t>(slot * 64);
 #pragma unroll
       for (int j2 = 0; j2 < 4; ++j2) {  // eight K columns at a time: hi -> columns [8 j2, +8), lo -> 32 + the same
@@ -355,12 +445,27 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&C.a_full[slot]);
+      if (prof) {
+        const long long t2 = clock64();
+        t_wait += t1 - t0;
+        t_work += t2 - t1;
+      }
+      slot += 2;
+      if (slot >= n_slots) {
+        slot -= n_slots;
+        wraps += 1;
+      }
+    }
+    if (prof && warp == 2 && lane == 0) {
+      prof[56] = t_wait;   // cycles this feeder waited for a free TMEM slot (MMA / epilogue bound)
+      prof[57] = t_work;   // cycles in split + tcgen05.st + wait + arrive
+      prof[58] = total_chunks;
     }
   } else {
     // ================================================================= epilogue warps
-    const int e = warp - 9;           // 0..7
+    const int e = warp - 10;  // 0..7
     const int q = warp & 3, mt = e >> 2;
-    const int f = mt * 128 + q * 32 + lane;  // feature (row of the layer output) this thread owns
+    const int f = mt * 128 + q * 32 + lane;  // feature row of the layer output this thread owns
     const int et = e * 32 + lane;            // 0..255
     ptx::pdl_wait();
     if (L.bump && cta == 0 && et == 0) bump_counters(L.st, L.bump_actor);
@@ -368,25 +473,25 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     for (int ii = 0; ii < L.n_in; ++ii) {
       const ChainInput& in = L.in[ii];
       const int nf4 = in.kchunks * 128;  // float4s: 16 rows x 32 k per chunk
-      for (int i = et; i < nf4; i += 256) {
+      for (int i = et; i < nf4; i += kEpiThreads) {
         const int c = i >> 7, w = i & 127;
-        const int grp = w >> 6, j = (w >> 3) & 7, r = w & 7;
+        const int grp = w >> 6, j = (w >> 3) & 7, rr8 = w & 7;
         const float4 x = __ldg(reinterpret_cast<const float4*>(
-                                   in.src + (static_cast<size_t>(c) * (in.rows >> 3) + (n0 >> 3) + grp) * 256) + j * 8 + r);
+                                   in.src + (static_cast<size_t>(c) * (in.rows >> 3) + (n0 >> 3) + grp) * 256) + j * 8 + rr8);
         float4 h, l;
         ptx::split_tf32(x.x, h.x, l.x);
         ptx::split_tf32(x.y, h.y, l.y);
         ptx::split_tf32(x.z, h.z, l.z);
         ptx::split_tf32(x.w, h.w, l.w);
-        const int off = grp * in.sbo + (c * 8 + j) * kCorePitch + r * 16;
+        const int off = grp * in.sbo + (c * 8 + j) * pitch + rr8 * 16;
         *reinterpret_cast<float4*>(csm + in.hi + off) = h;
         *reinterpret_cast<float4*>(csm + in.lo + off) = l;
       }
     }
     if (et < kNB) {
-      const int m = min(n0 + et, L.B - 1);
-      C.rr[et] = L.r ? __ldg(L.r + m) : 0.f;
-      C.dd[et] = L.d ? __ldg(L.d + m) : 0.f;
+      const int mrow = min(n0 + et, L.B - 1);
+      C.rr[et] = L.r ? __ldg(L.r + mrow) : 0.f;
+      C.dd[et] = L.d ? __ldg(L.d + mrow) : 0.f;
     }
     for (int k = 0; k < L.n_gm; ++k) C.mask[L.gm_slot[k]][et] = __ldg(L.gm_src[k] + static_cast<size_t>(cta) * kCFeat + et);
     ptx::fence_proxy_async_smem();
@@ -398,43 +503,68 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 
     float* mypart = L.part + static_cast<size_t>(cta) * L.part_stride;
     int hcount = 0;
+    const int hj = et >> 4, hn = et & 15;  // head finisher thread -> (output j, batch column n)
+    const bool col_valid = n0 + hn < L.B;
     for (int oi = 0; oi < L.n_ops; ++oi) {
       const ChainOp& o = C.ops[oi];
       const bool act = mt < o.mtiles;  // this thread owns a row of the output
       const int flags = o.flags;
+      const int head = o.head;
+      const int J = (head == CH_ACTION || head == CH_DXA) ? o.J : 1;
+      const int nw = 4 * o.mtiles;  // epilogue warps that hold a partial
+      // ---- everything that comes from global memory is requested before the accumulators are waited for
       float bv = 0.f;
-      if ((flags & CF_BIAS_RELU) && act) bv = __ldg(o.bias + f);
-      uint32_t mbits = 0;
-      if ((flags & CF_APPLY_MASK) && act) mbits = C.mask[o.mask_slot][f];
+      uint32_t mbits = 0u;
       float hwv[kCMaxJ];
 #pragma unroll
       for (int j = 0; j < kCMaxJ; ++j) hwv[j] = 0.f;
       if (act) {
-        if (o.head == CH_ACTION) {
+        if (flags & CF_BIAS_RELU) bv = __ldg(o.bias + f);
+        if (flags & CF_APPLY_MASK) mbits = C.mask[o.mask_slot][f];
+        if (head == CH_ACTION) {
 #pragma unroll
           for (int j = 0; j < kCMaxJ; ++j)
-            if (j < o.J) hwv[j] = __ldg(o.hw + static_cast<size_t>(j) * o.hw_ld + f);
-        } else if (o.head == CH_DXA) {
+            if (j < J) hwv[j] = __ldg(o.hw + static_cast<size_t>(j) * o.hw_ld + f);
+        } else if (head == CH_DXA) {
 #pragma unroll
           for (int j = 0; j < kCMaxJ; ++j)
-            if (j < o.J) hwv[j] = __ldg(o.hw + static_cast<size_t>(f) * o.hw_ld + j);
-        } else if (o.head != CH_NONE) {
+            if (j < J) hwv[j] = __ldg(o.hw + static_cast<size_t>(f) * o.hw_ld + j);
+        } else if (head != CH_NONE) {
           hwv[0] = __ldg(o.hw + f);
         }
       }
-      // ---- accumulators -> registers (hi*hi groups in order, then the cross terms), release TMEM
-      ptx::mbar_wait(&C.d_full, static_cast<uint32_t>(oi & 1));
+      float fin_b = 0.f, fin_aux = 0.f;  // head bias / per-(row, output) extra of the finisher threads
+      if (head == CH_ACTION) {
+        if (et < J * kNB) {
+          fin_b = __ldg(o.hb + hj);
+          if (o.aux) fin_aux = __ldg(o.aux + static_cast<size_t>(min(n0 + hn, L.B - 1)) * J + hj);
+        }
+      } else if (head == CH_DXA) {
+        if (et < J * kNB) fin_aux = __ldg(o.aux + static_cast<size_t>(n0 + hn) * J + hj);
+      } else if (head != CH_NONE) {
+        fin_b = __ldg(o.hb);
+      }
+      float w2v[kCMaxJ];
+      uint32_t m2 = 0u;
+      if (head == CH_DXA) {
+#pragma unroll
+        for (int j = 0; j < kCMaxJ; ++j) w2v[j] = (j < J && f < o.Ha) ? __ldg(o.w2 + static_cast<size_t>(j) * o.Ha + f) : 0.f;
+        if (f < o.Ha) m2 = C.mask[o.mask2_slot][f];
+      }
+      // ---- accumulators -> registers (hi*hi groups in order, then the cross terms), release the region
+      const int r = oi & 1;
+      chain_wait(&C.d_full[r], static_cast<uint32_t>((oi >> 1) & 1), backoff);
       ptx::tc_fence_after();
       if (prof && et == 0 && oi < 16) prof[32 + oi] = clock64();
       float v[kNB];
-#pragma unroll
-      for (int n = 0; n < kNB; ++n) v[n] = 0.f;
       if (act) {
-        const uint32_t base = tmem + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(mt * kCAcc * kNB);
-        const int n_big = (o.kchunks + 1) >> 1;
+        const int n_big = (o.kchunks + o.group - 1) / o.group;
+        const uint32_t base = tmem + (static_cast<uint32_t>(q * 32) << 16) +
+                              static_cast<uint32_t>(r * L.d_cols + mt * (n_big + 1) * kNB);
         float p1[kNB], p2[kNB];
         ptx::tmem_ld16_nowait(base + kNB, v);
         if (n_big > 1) ptx::tmem_ld16_nowait(base + 2 * kNB, p1);
+        if (n_big <= 2) ptx::tmem_ld16_nowait(base, p2);
         ptx::tmem_ld_wait();
         if (n_big > 1) {
 #pragma unroll
@@ -450,15 +580,23 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
 #pragma unroll
             for (int n = 0; n < kNB; ++n) v[n] += p2[n];
           }
+          ptx::tmem_ld16_nowait(base, p2);
+          ptx::tmem_ld_wait();
         }
-        ptx::tmem_ld16_nowait(base, p1);
-        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int n = 0; n < kNB; ++n) v[n] += p1[n];
+        for (int n = 0; n < kNB; ++n) v[n] += p2[n];
+      } else {
+#pragma unroll
+        for (int n = 0; n < kNB; ++n) v[n] = 0.f;
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&C.d_free);
+      if (lane == 0) ptx::mbar_arrive(&C.d_free[r]);
+      const bool stamp = prof && et == 0 && (head == CH_QLOSS || head == CH_DXA);
+      if (stamp) {
+        prof[62] = oi;
+        prof[63] = clock64();  // accumulators in registers
+      }
 
       // ---- layer epilogue
       if (flags & CF_BIAS_RELU) {
@@ -476,50 +614,35 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         if (flags & CF_SAVE_MASK) C.mask[o.mask_slot][f] = bits;
         if (flags & CF_MASK_GLOBAL) o.gmask[static_cast<size_t>(cta) * kCFeat + f] = bits;
       }
-
-      const int head = o.head;
       if (head == CH_NONE || head == CH_ACTION || head == CH_QTARGET) {
-        // the layer output itself is what the next op / the weight-gradient GEMM consumes
-        if (act) {
-          if (flags & CF_OUT_GLOBAL) {
-            float* dst = o.gout + ct_index(o.gout_rows, f, n0);
-#pragma unroll
-            for (int n4 = 0; n4 < kNB / 4; ++n4)
-              *reinterpret_cast<float4*>(dst + n4 * 32) = make_float4(v[4 * n4], v[4 * n4 + 1], v[4 * n4 + 2], v[4 * n4 + 3]);
-          }
-          if (flags & CF_COLSUM) {
-            float s = 0.f;
-#pragma unroll
-            for (int n = 0; n < kNB; ++n) s += v[n];
-            mypart[o.vec_slot * kCFeat + f] = s;
-          }
-          if (flags & CF_OUT_SMEM) {
-            uint8_t* bh = csm + o.out_hi + (f >> 2) * kCorePitch + (f & 3) * 4;
-            uint8_t* bl = csm + o.out_lo + (f >> 2) * kCorePitch + (f & 3) * 4;
-#pragma unroll
-            for (int n = 0; n < kNB; ++n) {
-              float h, l;
-              ptx::split_tf32(v[n], h, l);
-              const int off = (n >> 3) * o.out_sbo + (n & 7) * 16;
-              *reinterpret_cast<float*>(bh + off) = h;
-              *reinterpret_cast<float*>(bl + off) = l;
-            }
-          }
-        }
+        // the layer output itself is what the next op / the weight-gradient GEMM consumes: operand first
         if (flags & CF_OUT_SMEM) {
+          if (act) chain_store_operand(csm, o.out_hi, o.out_lo, o.out_sbo, pitch, f, v);
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&C.buf_bar[o.out_bar]);
         }
       }
-      if (head == CH_NONE) continue;
-
-      // ---- narrow head: dot products over the feature axis
       const int rb = hcount & 1;
-      ++hcount;
-      const int J = (head == CH_ACTION || head == CH_DXA) ? o.J : 1;
-      const int nwarps_act = 4 * o.mtiles;
-      if (act) {
+      if (head != CH_NONE) ++hcount;
+      if (head == CH_QACTOR) {
+        // actor loss -mean q(s, pi(s)) (ddpg.py:104, td3.py:135-137): the seed dL/dq = -1/count is a constant,
+        // so dz of this layer needs no reduction -- it goes out first, q (logged only) afterwards
+        if (act) {
+          const float seed = -L.inv_count * hwv[0];
+          float dz[kNB];
+#pragma unroll
+          for (int n = 0; n < kNB; ++n) dz[n] = (v[n] > 0.f && n0 + n < L.B) ? seed : 0.f;
+          chain_store_operand(csm, o.out_hi, o.out_lo, o.out_sbo, pitch, f, dz);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&C.buf_bar[o.out_bar]);
+      }
+      if (stamp) prof[64] = clock64();  // layer epilogue done
+
+      // ---- narrow head: dot products over the feature axis (per-warp butterfly, then the warps in order)
+      if (head != CH_NONE && act) {
 #pragma unroll
         for (int j = 0; j < kCMaxJ; ++j) {
           if (j < J) {
@@ -531,56 +654,89 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           }
         }
       }
-      CHAIN_EPI_BAR();
-      float hsum = 0.f;  // finisher thread (j, n) = (et >> 4, et & 15): total over the warps, in warp order
-      const int hj = et >> 4, hn = et & 15;
-      if (et < J * kNB) {
-        for (int w8 = 0; w8 < nwarps_act; ++w8) hsum += C.red[rb][w8][hj][hn];
+      if ((head == CH_NONE || head == CH_ACTION || head == CH_QTARGET) && act) {
+        // global side outputs of the plain layer, off the critical path
+        if (flags & CF_OUT_GLOBAL) chain_store_gout(o.gout, o.gout_rows, f, n0, v);
+        if (flags & CF_COLSUM) {
+          float s = 0.f;
+#pragma unroll
+          for (int n = 0; n < kNB; ++n) s += v[n];
+          mypart[o.vec_slot * kCFeat + f] = s;
+        }
       }
-      const bool col_valid = n0 + hn < L.B;
+      if (head == CH_NONE) continue;
+      if (stamp) prof[65] = clock64();  // head partials written
+      CHAIN_EPI_BAR();
+      if (stamp) prof[66] = clock64();  // behind barrier A
 
       if (head == CH_ACTION) {
         if (et < J * kNB) {
-          float a = tanhf(hsum + __ldg(o.hb + hj));
-          if (o.aux) a += __ldg(o.aux + static_cast<size_t>(min(n0 + hn, L.B - 1)) * J + hj);
+          float a = tanhf(chain_red8(C.red[rb], hj, hn, nw) + fin_b);
+          if (o.aux) a += fin_aux;
           if (o.clamp > 0.f) a = fminf(fmaxf(a, -o.clamp), o.clamp);
-          if (o.hout) o.hout[static_cast<size_t>(n0 + hn) * J + hj] = a;
-          if (o.hout2) o.hout2[ct_index(L.Bp, n0 + hn, hj)] = a;
           if (o.x_bar >= 0) {
             float h, l;
             ptx::split_tf32(a, h, l);
-            const int off = (hn >> 3) * o.x_sbo + (hj >> 2) * kCorePitch + (hn & 7) * 16 + (hj & 3) * 4;
+            const int off = (hn >> 3) * o.x_sbo + (hj >> 2) * pitch + (hn & 7) * 16 + (hj & 3) * 4;
             *reinterpret_cast<float*>(csm + o.x_hi + off) = h;
             *reinterpret_cast<float*>(csm + o.x_lo + off) = l;
           }
+          if (o.hout) o.hout[static_cast<size_t>(n0 + hn) * J + hj] = a;
+          if (o.hout2) o.hout2[ct_index(L.Bp, n0 + hn, hj)] = a;
         }
-        if (o.x_bar >= 0) {
+        if (o.x_bar >= 0) {  // every warp arrives behind its own writes (warps without finisher threads: at once)
           ptx::fence_proxy_async_smem();
-          CHAIN_EPI_BAR();
+          __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&C.buf_bar[o.x_bar]);
         }
         continue;
       }
       if (head == CH_QTARGET) {
-        if (et < kNB) C.qn_s[o.crit][et] = hsum + __ldg(o.hb);
-        continue;  // read back by the same threads in CH_QLOSS
+        if (et < kNB) C.qn_s[o.crit][et] = chain_red8(C.red[rb], 0, et, nw) + fin_b;
+        continue;  // read by the same threads in the CH_QLOSS op that follows
       }
       if (head == CH_QLOSS) {
-        // TD target and MSE seed per batch row (ddpg.py:94-98, td3.py:105-112)
+        // TD target and MSE seed per batch row (ddpg.py:94-98, td3.py:105-112): 16 column threads, then everybody
         float c_loss = 0.f, c_q = 0.f, c_y = 0.f, c_e = 0.f, c_dq = 0.f;
         if (et < kNB) {
-          const float qv = hsum + __ldg(o.hb);
+          const float qv = chain_red8(C.red[rb], 0, et, nw) + fin_b;
           float qn = C.qn_s[0][et];
           if (L.nq == 2) qn = fminf(qn, C.qn_s[1][et]);
           const float y = C.rr[et] + ((1.0f - C.dd[et]) * L.gamma) * qn;
           const float diff = qv - y;
-          const float dq = col_valid ? L.inv_count * (2.0f * diff) : 0.f;
-          C.dq_s[rb][et] = dq;
+          const float dqv = col_valid ? L.inv_count * (2.0f * diff) : 0.f;
+          C.dq_s[rb][et] = dqv;
           if (col_valid) {
             c_loss = diff * diff;
-            c_dq = dq;
-            if (o.crit == 0) { c_q = qv; c_y = y; c_e = diff; }
+            c_dq = dqv;
+            c_q = qv; c_y = y; c_e = diff;
           }
+        }
+        CHAIN_EPI_BAR();
+        float gw = 0.f, gb = 0.f;
+        if (act) {
+          float dz[kNB];
+#pragma unroll
+          for (int n = 0; n < kNB; ++n) {
+            const float dqv = C.dq_s[rb][n];
+            dz[n] = v[n] > 0.f ? dqv * hwv[0] : 0.f;
+            gw = fmaf(dqv, v[n], gw);
+            gb += dz[n];
+          }
+          chain_store_operand(csm, o.out_hi, o.out_lo, o.out_sbo, pitch, f, dz);
+#pragma unroll
+          for (int n = 0; n < kNB; ++n) v[n] = dz[n];
+        }
+        if (stamp) prof[67] = clock64();  // dz in the operand buffer
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&C.buf_bar[o.out_bar]);
+        if (stamp) prof[68] = clock64();  // arrived
+        // off the critical path: gradients for the GEMM launch / the totals
+        if (act) {
+          mypart[o.vec_slot * kCFeat + f] = gw;   // head weight gradient
+          mypart[o.vec2_slot * kCFeat + f] = gb;  // bias gradient of this layer
+          chain_store_gout(o.gout, o.gout_rows, f, n0, v);
         }
         if (e == 0) {  // lanes 0-15 of the first epilogue warp hold the columns
           c_loss = half_warp_sum(c_loss);
@@ -590,124 +746,67 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           c_dq = half_warp_sum(c_dq);
           if (lane == 0) {
             C.tail_s[0] += c_loss;
-            C.tail_s[1] += c_q;
-            C.tail_s[2] += c_y;
-            C.tail_s[3] += c_e;
+            if (o.crit == 0) {
+              C.tail_s[1] += c_q;
+              C.tail_s[2] += c_y;
+              C.tail_s[3] += c_e;
+            }
             C.tail_s[4 + o.crit] = c_dq;
           }
         }
-        CHAIN_EPI_BAR();
-        if (act) {
-          float gw = 0.f, gb = 0.f;
-          float dz[kNB];
-#pragma unroll
-          for (int n = 0; n < kNB; ++n) {
-            const float dq = C.dq_s[rb][n];
-            dz[n] = v[n] > 0.f ? dq * hwv[0] : 0.f;
-            gw = fmaf(dq, v[n], gw);
-            gb += dz[n];
-          }
-          mypart[o.vec_slot * kCFeat + f] = gw;   // head weight gradient
-          mypart[o.vec2_slot * kCFeat + f] = gb;  // bias gradient of this layer
-          float* dst = o.gout + ct_index(o.gout_rows, f, n0);
-#pragma unroll
-          for (int n4 = 0; n4 < kNB / 4; ++n4)
-            *reinterpret_cast<float4*>(dst + n4 * 32) = make_float4(dz[4 * n4], dz[4 * n4 + 1], dz[4 * n4 + 2], dz[4 * n4 + 3]);
-          uint8_t* bh = csm + o.out_hi + (f >> 2) * kCorePitch + (f & 3) * 4;
-          uint8_t* bl = csm + o.out_lo + (f >> 2) * kCorePitch + (f & 3) * 4;
-#pragma unroll
-          for (int n = 0; n < kNB; ++n) {
-            float h, l;
-            ptx::split_tf32(dz[n], h, l);
-            const int off = (n >> 3) * o.out_sbo + (n & 7) * 16;
-            *reinterpret_cast<float*>(bh + off) = h;
-            *reinterpret_cast<float*>(bl + off) = l;
-          }
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&C.buf_bar[o.out_bar]);
         continue;
       }
       if (head == CH_QACTOR) {
-        // actor loss -mean q(s, pi(s)) (ddpg.py:104, td3.py:135-137): the seed dL/dq = -1/count is a constant
         if (e == 0) {
-          float c_q = (et < kNB && col_valid) ? hsum + __ldg(o.hb) : 0.f;
+          float c_q = (lane < kNB && n0 + lane < L.B) ? chain_red8(C.red[rb], 0, lane, nw) + fin_b : 0.f;
           c_q = half_warp_sum(c_q);
           if (lane == 0) C.tail_s[0] += c_q;
         }
-        if (act) {
-          const float seed = -L.inv_count * hwv[0];
-          uint8_t* bh = csm + o.out_hi + (f >> 2) * kCorePitch + (f & 3) * 4;
-          uint8_t* bl = csm + o.out_lo + (f >> 2) * kCorePitch + (f & 3) * 4;
-#pragma unroll
-          for (int n = 0; n < kNB; ++n) {
-            const float dz = (v[n] > 0.f && n0 + n < L.B) ? seed : 0.f;
-            float h, l;
-            ptx::split_tf32(dz, h, l);
-            const int off = (n >> 3) * o.out_sbo + (n & 7) * 16;
-            *reinterpret_cast<float*>(bh + off) = h;
-            *reinterpret_cast<float*>(bl + off) = l;
-          }
-        }
-        ptx::fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&C.buf_bar[o.out_bar]);
         continue;
       }
       if (head == CH_DXA) {
         // dL/da = dz0 . W0[:, S:S+A] ; through tanh: dz_head = dL/da * (1 - a^2) ; its bias gradient
+        float dza = 0.f;
         if (et < J * kNB) {
-          const float tv = __ldg(o.aux + static_cast<size_t>(n0 + hn) * J + hj);
-          const float dza = col_valid ? hsum * (1.f - tv * tv) : 0.f;
+          dza = col_valid ? chain_red8(C.red[rb], hj, hn, nw) * (1.f - fin_aux * fin_aux) : 0.f;
           C.dza_s[hj][hn] = dza;
-          o.hout[ct_index(128, hj, n0 + hn)] = dza;
-          hsum = dza;
-        } else {
-          hsum = 0.f;
         }
-        {
-          const float s = half_warp_sum(hsum);
-          if ((lane & 15) == 0 && et < J * kNB) C.tail_s[8 + hj] = s;
-        }
+        if (stamp) prof[69] = clock64();  // finisher done
         CHAIN_EPI_BAR();
+        if (stamp) prof[70] = clock64();  // behind barrier B
         // policy head backward (K = A): dz1[f][n] = relu'(h1) * sum_j W2[j][f] dza[j][n]
+        float gb = 0.f;
         const bool act2 = f < o.Ha;
         if (act2) {
-          float w2v[kCMaxJ];
-#pragma unroll
-          for (int j = 0; j < kCMaxJ; ++j) w2v[j] = j < J ? __ldg(o.w2 + static_cast<size_t>(j) * o.Ha + f) : 0.f;
-          const uint32_t m2 = C.mask[o.mask2_slot][f];
           float dz[kNB];
-          float gb = 0.f;
 #pragma unroll
           for (int n = 0; n < kNB; ++n) {
-            float s = 0.f;
+            float sacc = 0.f;
 #pragma unroll
             for (int j = 0; j < kCMaxJ; ++j)
-              if (j < J) s = fmaf(w2v[j], C.dza_s[j][n], s);
-            dz[n] = ((m2 >> n) & 1u) ? s : 0.f;
+              if (j < J) sacc = fmaf(w2v[j], C.dza_s[j][n], sacc);
+            dz[n] = ((m2 >> n) & 1u) ? sacc : 0.f;
             gb += dz[n];
           }
-          mypart[o.vec_slot * kCFeat + f] = gb;
-          float* dst = o.gout + ct_index(o.gout_rows, f, n0);
+          chain_store_operand(csm, o.out_hi, o.out_lo, o.out_sbo, pitch, f, dz);
 #pragma unroll
-          for (int n4 = 0; n4 < kNB / 4; ++n4)
-            *reinterpret_cast<float4*>(dst + n4 * 32) = make_float4(dz[4 * n4], dz[4 * n4 + 1], dz[4 * n4 + 2], dz[4 * n4 + 3]);
-          uint8_t* bh = csm + o.out_hi + (f >> 2) * kCorePitch + (f & 3) * 4;
-          uint8_t* bl = csm + o.out_lo + (f >> 2) * kCorePitch + (f & 3) * 4;
-#pragma unroll
-          for (int n = 0; n < kNB; ++n) {
-            float h, l;
-            ptx::split_tf32(dz[n], h, l);
-            const int off = (n >> 3) * o.out_sbo + (n & 7) * 16;
-            *reinterpret_cast<float*>(bh + off) = h;
-            *reinterpret_cast<float*>(bl + off) = l;
-          }
+          for (int n = 0; n < kNB; ++n) v[n] = dz[n];
         }
+        if (stamp) prof[67] = clock64();  // dz in the operand buffer
         ptx::fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&C.buf_bar[o.out_bar]);
+        if (stamp) prof[68] = clock64();  // arrived
+        // off the critical path
+        if (act2) {
+          mypart[o.vec_slot * kCFeat + f] = gb;
+          chain_store_gout(o.gout, o.gout_rows, f, n0, v);
+        }
+        if (et < J * kNB) o.hout[ct_index(128, hj, n0 + hn)] = dza;
+        {
+          const float ssum = half_warp_sum(dza);
+          if ((lane & 15) == 0 && et < J * kNB) C.tail_s[8 + hj] = ssum;
+        }
         continue;
       }
     }

@@ -276,6 +276,35 @@ __global__ void __launch_bounds__(kGatherThreads) gather_rows_kernel(RowGatherAr
   }
 }
 
+// ---------------------------------------------------------------- ingest scatter
+// EpisodicReplayBuffer.add_transition / add_episode (episodic_buffer.py:81-112): the host stages whole
+// transitions in a pinned ring, one row = [state S | action A | reward | done | episode (int bits) | step (int bits)];
+// one H2D copy of the staged rows and ONE launch of this kernel place them in the replay storage (one warp per
+// transition), instead of two small copies and two fill kernels per transition.
+struct ScatterArgs {
+  float *states, *actions, *rewards, *dones;
+  const float* staged;  // [n][S + A + 4]
+  int n, L, S, A;
+};
+constexpr int kScatterRows = 8;
+__global__ void __launch_bounds__(32 * kScatterRows) scatter_transitions_kernel(ScatterArgs g) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * kScatterRows + warp;
+  if (row >= g.n) return;
+  const int W = g.S + g.A + 4;
+  const float* src = g.staged + static_cast<size_t>(row) * W;
+  const int ep = __float_as_int(src[g.S + g.A + 2]);
+  const int step = __float_as_int(src[g.S + g.A + 3]);
+  float* ds = g.states + (static_cast<size_t>(ep) * (g.L + 1) + step) * g.S;
+  float* da = g.actions + (static_cast<size_t>(ep) * g.L + step) * g.A;
+  for (int c = lane; c < g.S; c += 32) ds[c] = src[c];
+  for (int c = lane; c < g.A; c += 32) da[c] = src[g.S + c];
+  if (lane == 0) {
+    g.rewards[static_cast<size_t>(ep) * g.L + step] = src[g.S + g.A];
+    g.dones[static_cast<size_t>(ep) * g.L + step] = src[g.S + g.A + 1];
+  }
+}
+
 // ---------------------------------------------------------------- block reduce
 template <int kThreads>
 __device__ __forceinline__ float block_sum(float v, float* sh) {

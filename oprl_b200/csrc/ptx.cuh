@@ -176,6 +176,18 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same, the shared-memory descriptor of B given as its two 32-bit words (the issuing warp advances the low
+// word -- start address field -- with a plain add instead of rebuilding the descriptor per MMA).
+__device__ __forceinline__ void mma_tf32_ts2(uint32_t tmem_d, uint32_t tmem_a, uint32_t desc_b_lo, uint32_t desc_b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "r"(desc_b_lo), "r"(desc_b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued MMAs of this thread retire.
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::

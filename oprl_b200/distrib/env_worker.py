@@ -3,10 +3,11 @@ episode to the learner and picks up fresh weights (reference distrib/env_worker.
 from __future__ import annotations
 
 import logging
-import pickle
 from typing import Any, Callable
 
-from .queue import Queue
+import numpy as np
+
+from .queue import Queue, pack_episode, unpack_weights
 
 log = logging.getLogger(__name__)
 
@@ -31,7 +32,8 @@ def run_env_worker(make_env: Callable[[int], Any], make_policy: Callable[[], Any
                 break
             state = next_state
             total_env_step += 1
-        q_env.push(pickle.dumps(episode))
+        s_dim, a_dim = int(np.asarray(episode[0][0]).size), int(np.asarray(episode[0][1]).size)
+        q_env.push(pack_episode(episode, s_dim, a_dim))  # raw float32 rows through shared memory, no pickle
         # lock-step with the learner: wait for the weights it publishes after consuming the episode
         data, waited = None, 0.0
         while data is None:
@@ -42,5 +44,5 @@ def run_env_worker(make_env: Callable[[int], Any], make_policy: Callable[[], Any
                 if waited >= 2.0 * 10 * config.learner_num_waits:
                     log.warning("worker %d: the learner is gone, exiting", id_worker)
                     return
-        policy.load_state_dict(pickle.loads(data))
+        policy.load_state_dict(unpack_weights(data))
     log.info("env worker %d done", id_worker)

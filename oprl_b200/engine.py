@@ -156,15 +156,32 @@ class UpdateEngine:
         if self._batch is None or self._batch_cap < B:
             cap = max(B, 128)
             sp = self.spec
-            z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.device)
-            self._batch = (z(cap, sp.state_dim), z(cap, sp.action_dim), z(cap, 1), z(cap, 1),
-                           z(cap, sp.state_dim))
+            widths = (sp.state_dim, sp.action_dim, 1, 1, sp.state_dim)
+            # one flat allocation, five row-major [cap, w] views: a caller-visible copy of a sampled batch is one
+            # D2D copy of `flat` (EpisodicReplayBuffer.sample)
+            self._batch_flat = torch.zeros(cap * sum(widths), dtype=torch.float32, device=self.device)
+            views, o = [], 0
+            for w in widths:
+                views.append(self._batch_flat[o:o + cap * w].view(cap, w))
+                o += cap * w
+            self._batch = tuple(views)
             self._batch_cap = cap
             L.check(self._lib.oprl_batch_bind(self._h, *[t.data_ptr() for t in self._batch], cap))
         return self._batch
 
     def batch_views(self, B):
         return tuple(t[:B] for t in self._ensure_batch(B))
+
+    def batch_copy(self, B):
+        """Fresh tensors holding the batch the last sample() gathered (one D2D copy of the flat arena)."""
+        self._ensure_batch(B)
+        flat = self._batch_flat.clone()
+        sp = self.spec
+        cap, out, o = self._batch_cap, [], 0
+        for w in (sp.state_dim, sp.action_dim, 1, 1, sp.state_dim):
+            out.append(flat[o:o + cap * w].view(cap, w)[:B])
+            o += cap * w
+        return tuple(out)
 
     def sample(self, B, ep_step: np.ndarray | None = None):
         """Gather B transitions straight from the bound replay storage into the engine's operand
@@ -262,6 +279,20 @@ class UpdateEngine:
         L.check(self._lib.oprl_profile(self._h, B, L.UPDATE_ACTOR if actor_step else 0, 2, iters,
                                        C.byref(ms), C.byref(n)))
         return ms.value / iters
+
+    def time_chain_only(self, B, iters=200, actor_step=True):
+        """(ms per update spent in the update's batch-slice chain launches, chain launches per update)."""
+        self._use_current_stream()
+        ms, n = C.c_float(), C.c_int()
+        L.check(self._lib.oprl_profile(self._h, B, L.UPDATE_ACTOR if actor_step else 0, 3, iters,
+                                       C.byref(ms), C.byref(n)))
+        return ms.value / iters, n.value
+
+    def chain_prof(self, B, which, actor_step=True):
+        """clock64 stamps of CTA 0 of the critic (0) / actor (1) chain launch (OPRL_B200_CHAIN_PROF=1)."""
+        out = (C.c_longlong * 256)()
+        L.check(self._lib.oprl_chain_prof(self._h, B, L.UPDATE_ACTOR if actor_step else 0, which, out))
+        return list(out)
 
     def time_gather_only(self, B, iters=200):
         """Microseconds per gather launch (device-side index draw)."""

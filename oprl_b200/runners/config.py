@@ -21,3 +21,4 @@ class DistribConfig(BaseSettings):
     episode_length: int = 1000
     learner_num_waits: int = 10
     warmup_env_steps: int = 1000
+    num_learners: int = 1  # oprl_b200 extension: data-parallel learners, one per GPU (reference: a single learner)

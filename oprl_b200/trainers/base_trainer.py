@@ -8,6 +8,9 @@ evaluate / save / log.  What changes is how the two hot calls meet the device:
   GEMM operand layout; no copy-in),
 * the sampled ``rewards`` are only pulled to the host on logging steps (the reference's
   ``rewards.mean().item()``, base_trainer.py:80, synchronises there as well),
+* the policy acts on a CPU mirror of the actor refreshed by async D2H copies into pinned memory
+  (``algo.enable_host_rollout``), and ``add_transition`` stages into a pinned ring flushed by one H2D +
+  one scatter kernel: the environment loop never waits for the device,
 * ``save_policy_every`` writes a CPU copy of the actor module that unpickles without the engine
   (scripts/visualize_policy_from_weights.py:66 only needs ``.exploit``).
 """
@@ -43,12 +46,16 @@ class BaseTrainer:
     stdout_log_every: int = int(1e5)
     device: str = "cuda"
     seed: int = 0
+    host_rollout_refresh_every: int = 1  # 0: act with the device network (H2D + sync per env step)
 
     def train(self) -> None:
         self.algo.check_created()
         self.replay_buffer.check_created()
         if hasattr(self.algo, "attach_buffer") and getattr(self.replay_buffer, "_engine", None) is None:
             self.algo.attach_buffer(self.replay_buffer)
+        if self.host_rollout_refresh_every > 0 and hasattr(self.algo, "enable_host_rollout") \
+                and getattr(self.algo, "_mirror", None) is None:
+            self.algo.enable_host_rollout(self.host_rollout_refresh_every)
 
         state, _ = self.env.reset()
         for env_step in range(self.num_steps + 1):
@@ -85,6 +92,9 @@ class BaseTrainer:
             self.logger.log_scalar(tag, value, env_step)
 
     def evaluate(self) -> dict[str, float]:
+        mirror = getattr(self.algo, "_mirror", None)
+        if mirror is not None:
+            mirror.refresh_now()  # evaluate the current weights, not a copy one update old
         returns = []
         for episode in range(self.num_eval_episodes):
             env = self.make_env_test(self.seed + episode)
