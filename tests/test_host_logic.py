@@ -186,22 +186,19 @@ def test_compat_overlay_redirects_reference_imports():
 
 
 def test_in_node_queue_surface():
-    """distrib/queue.py:4-19 surface (push / pop -> bytes | None) on the broker-less transport."""
-    import pickle
-
+    """distrib/queue.py:4-19 surface (push / pop -> bytes | None) on the broker-less shared-memory transport
+    (more in tests/test_queue_transport.py)."""
     from oprl_b200.distrib.queue import Queue, QueueServer
 
-    os.environ["OPRL_B200_QUEUE_PORT"] = str(_free_port())
-    try:
-        with QueueServer():
-            a, b = Queue("env_0"), Queue("env_0")
-            assert b.pop() is None
-            a.push(pickle.dumps([1, 2]))
-            assert pickle.loads(b.pop_wait(1.0)) == [1, 2]
-            assert b.pop_wait(0.05) is None
-            assert Queue("policy_0").pop() is None
-    finally:
-        del os.environ["OPRL_B200_QUEUE_PORT"]
+    with QueueServer(["env_0", "policy_0"]):
+        a, b = Queue("env_0"), Queue("env_0")
+        assert b.pop() is None
+        a.push(b"\x01\x02payload")
+        assert b.pop_wait(1.0) == b"\x01\x02payload"
+        assert b.pop_wait(0.05) is None
+        assert Queue("policy_0").pop() is None
+        a.close()
+        b.close()
 
 
 def test_config_records_match_reference_defaults():
