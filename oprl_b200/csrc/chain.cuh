@@ -14,11 +14,13 @@
 // exactly the [feature x batch] layout dW needs) and a handful of bias-gradient / loss partial sums
 // (per-CTA partials, fixed-order total by the last CTA to arrive).
 //
-//   D^T[feat x 16] (+)= W[feat x k] * H^T[k x 16]        tcgen05.mma kind::tf32, M = 128, N = 16
+//   D^T[feat x 16] (+)= W[feat x k] * H^T[k x 16]        tcgen05.mma kind::tf32, M = 128, N = 16 / 32
 //
-// Arithmetic is the same 3xTF32 scheme with cut accumulation chains as gemm.cuh (cross terms in
-// their own accumulator, hi*hi terms in one accumulator per two K chunks, fp32 adds in the
-// epilogue).  Narrow layers (<= 8 outputs: tanh policy heads, scalar Q heads, the action columns
+// Arithmetic is the same 3xTF32 scheme with cut accumulation chains as gemm.cuh (cross terms apart from
+// the hi*hi terms, one accumulator pair per group of K chunks, fp32 adds in the epilogue) -- but issued as
+// TWO MMAs per K step instead of three: with N this small an MMA costs what it takes to read its 4 KB A tile
+// out of tensor memory (~40 cycles measured; 8 cycles of math), so A_hi is read once against the
+// concatenated rows [H_hi ; H_lo] (N = 32 -> hi*hi and hi*lo side by side) and A_lo once against H_hi.  Narrow layers (<= 8 outputs: tanh policy heads, scalar Q heads, the action columns
 // of dX) never touch the tensor core: they are dot products over the feature axis done in the
 // epilogue of the layer that produces their input (fp32 FMA, warp butterfly + fixed-order
 // cross-warp sum), and K <= 8 layers (the policy head backward) are a few FMAs per thread.
@@ -30,7 +32,7 @@
 //         chunk against ~130 of tensor time.  The two M tiles have separate accumulators, so two warps can
 //         issue side by side without changing any accumulation order; the chunk stream interleaves the tiles.
 //   2-9   weight feeders, two per TMEM lane quarter alternating 16 KB chunks: L2 -> registers (one chunk
-//         prefetched) -> tf32 hi/lo split -> tcgen05.st, eight K columns at a time (register budget).
+//         prefetched) -> tf32 hi/lo split -> tcgen05.st, sixteen K columns at a time (register budget).
 //   10-17 epilogue, one per (lane quarter, M tile): a thread owns one feature row of the layer output.
 // The weight stream runs ahead of the MMAs through a ring of TMEM slots, across layer boundaries; the
 // accumulators are double-buffered so the read-out of one layer overlaps the MMAs of the next.
@@ -144,9 +146,10 @@ struct ChainLaunch {
   // TMEM plan: two accumulator regions of d_cols columns (op i uses region i & 1, so the read-out of one
   // op overlaps the MMAs of the next), then n_slots x 64 columns of split A chunks from column a_col0
   int d_cols, a_col0, n_slots;
+  int region_mask;  // 1: two accumulator regions (op i uses region i & 1); 0: one region, more ring slots
   long long* prof;  // selftest / profiling: clock64 stamps of CTA 0 (nullable)
   int pitch;        // bytes between K-adjacent core matrices of the operand buffers (kCorePitch)
-  int debug;        // timing experiments only: 2 = no weight loads, 4 = no tcgen05.st (results invalid); 8 = waiting warps poll in a tight loop instead of backing off with nanosleep
+  int debug;        // timing experiments only: 2 = no weight loads, 4 = no tcgen05.st (results invalid); 8 = waiting warps poll in a tight loop instead of backing off with nanosleep; 16 = no per-chunk commit, 32 = feeders never wait for a free slot, 64 = MMA warps never wait for a filled slot (48 / 112: handshake cost probes)
 };
 
 struct ChainCtl {
@@ -185,6 +188,15 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+// registers -> TMEM: thread i writes lane (lane_base + i), 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 // registers -> TMEM: thread i writes lane (lane_base + i), 8 consecutive fp32 columns
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -247,6 +259,22 @@ __device__ __forceinline__ void chain_wait(uint64_t* bar, uint32_t parity, bool 
       if ((threadIdx.x & 31) == 0) printf("oprl: chain mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
       __trap();
     }
+  }
+}
+
+// the same wait for ONE thread on a shared::cta address (the elected MMA-issuing thread; no printf in its loop)
+__device__ __forceinline__ void chain_wait1(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t ok = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}\n"
+        : "=r"(ok)
+        : "r"(bar_saddr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) __trap();
   }
 }
 
@@ -330,72 +358,97 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   const uint32_t tmem = C.tmem_slot;
   const int n_slots = L.n_slots;
   const uint32_t a_col0 = static_cast<uint32_t>(L.a_col0);
-  const int pitch = L.pitch;
+  constexpr int pitch = kCorePitch;  // compile-time: the per-K-step descriptor advance becomes an immediate
   const bool backoff = (L.debug & 8) == 0;  // default on; OPRL_B200_CHAIN_DEBUG=8 makes every wait a tight poll
 
   if (warp < 2) {
     // ================================================================= MMA issuers (warp m: M tile m)
+    // ONE elected thread runs the whole loop -- waits included -- inside a single elect.sync region: ptxas then
+    // keeps every address, descriptor word and counter in uniform registers and the MMAs issue back to back
+    // (~10 cycles each).  Electing per chunk instead left the loop on the vector datapath with an R2UR per MMA
+    // operand: 35-45 cycles per MMA, measured (tools/experiments/chain_probe4.cu).
     const int m = warp;
-    const uint32_t idesc = ptx::idesc_tf32(128, kNB, 0, 0);
-    const uint32_t kstep = static_cast<uint32_t>(2 * pitch) >> 4;  // one K = 8 step, in the descriptor's 16-byte units
-    const uint32_t smem_base16 = ptx::smem_u32(csm) >> 4;
-    const uint32_t lbo_bits = (static_cast<uint32_t>(pitch) >> 4) << 16;
-    uint32_t slot = 0, full_par = 0;  // running over ALL chunks (both warps count every chunk)
-    long long m_opwait = 0;
-    for (int oi = 0; oi < L.n_ops; ++oi) {
-      const ChainMmaOp o = L.mop[oi];
-      const int r = oi & 1, k = oi >> 1;  // accumulator region, its k-th use
-      const long long tw0 = prof ? clock64() : 0;
-      chain_wait(&C.buf_bar[o.in_bar], static_cast<uint32_t>(o.in_phase & 1), backoff);
-      if (k > 0) chain_wait(&C.d_free[r], static_cast<uint32_t>((k - 1) & 1), backoff);
-      ptx::tc_fence_after();
-      if (prof) m_opwait += clock64() - tw0;
-      if (prof && lane == 0 && m == 0 && oi < 16) prof[16 + oi] = clock64();
-      // descriptor words: low = start >> 4 | LBO >> 4 << 16, high = SBO >> 4 | version 1 << 14
-      const uint32_t dw_hi = o.dw_hi;
-      uint32_t dl_hi = ((smem_base16 + (o.in_hi >> 4)) & 0x3FFFu) | lbo_bits;
-      uint32_t dl_lo = ((smem_base16 + (o.in_lo >> 4)) & 0x3FFFu) | lbo_bits;
-      const int group = o.group;
-      const int kchunks = o.kchunks;
-      const int mtiles = o.mtiles;
-      const uint32_t acc_cols = static_cast<uint32_t>((1 + (kchunks + group - 1) / group) * kNB);
-      const uint32_t d_cross = tmem + static_cast<uint32_t>(r * L.d_cols) + static_cast<uint32_t>(m) * acc_cols;
-      uint32_t big = d_cross + kNB;
-      int in_group = 0;
-      for (int c = 0; c < kchunks; ++c) {
-        for (int mt = 0; mt < mtiles; ++mt) {
-          if (mt == m) {
-            ptx::mbar_wait(&C.a_full[slot], full_par);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint32_t ta_hi = tmem + a_col0 + slot * 64u;
-              const uint32_t ta_lo = ta_hi + 32u;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                ptx::mma_tf32_ts2(d_cross, ta_lo + 8u * j, dl_hi + j * kstep, dw_hi, idesc, (c | j) ? 1u : 0u);
-                ptx::mma_tf32_ts2(d_cross, ta_hi + 8u * j, dl_lo + j * kstep, dw_hi, idesc, 1u);
-                ptx::mma_tf32_ts2(big, ta_hi + 8u * j, dl_hi + j * kstep, dw_hi, idesc, (in_group | j) ? 1u : 0u);
-              }
-              ptx::mma_commit(&C.a_empty[slot]);
-            }
-            __syncwarp();
+    if (ptx::elect_one()) {
+      // This thread's program is serial: every instruction between two MMAs costs its full latency (~5 cycles each,
+      // nothing to overlap with), so the per-chunk path is kept to the wait, the operand words and the MMAs --
+      // every launch parameter is read into a register once, the ring position advances by adds.
+      const uint32_t idesc16 = ptx::idesc_tf32(128, kNB, 0, 0), idesc32 = ptx::idesc_tf32(128, 2 * kNB, 0, 0);
+      constexpr uint32_t kstep = static_cast<uint32_t>(2 * pitch) >> 4;  // one K = 8 step, in the descriptor's 16-byte units
+      const uint32_t smem_base16 = ptx::smem_u32(csm) >> 4;
+      const uint32_t lbo_bits = (static_cast<uint32_t>(pitch) >> 4) << 16;
+      const uint32_t full0 = ptx::smem_u32(&C.a_full[0]), empty0 = ptx::smem_u32(&C.a_empty[0]);
+      const uint32_t ta0 = tmem + a_col0;
+      const uint32_t nsl = static_cast<uint32_t>(n_slots);
+      const uint32_t d_cols = static_cast<uint32_t>(L.d_cols);
+      const int n_ops = L.n_ops;
+      const bool dbg_nowait = (L.debug & 64) != 0, dbg_nocommit = (L.debug & 16) != 0;  // timing probes only
+      uint32_t slot0 = 0, par0 = 0;  // ring position / phase parity of the op's first chunk (all chunks, both warps)
+      for (int oi = 0; oi < n_ops; ++oi) {
+        const ChainMmaOp o = L.mop[oi];
+        const uint32_t r = static_cast<uint32_t>(oi & L.region_mask);
+        const int k = L.region_mask ? (oi >> 1) : oi;  // use count of the accumulator region
+        chain_wait1(ptx::smem_u32(&C.buf_bar[o.in_bar]), static_cast<uint32_t>(o.in_phase & 1));
+        if (k > 0) chain_wait1(ptx::smem_u32(&C.d_free[r]), static_cast<uint32_t>((k - 1) & 1));
+        ptx::tc_fence_after();
+        if (prof && m == 0 && oi < 16) prof[16 + oi] = clock64();
+        const uint32_t mtiles = o.mtiles, kchunks = o.kchunks, group = o.group;
+        if (static_cast<uint32_t>(m) < mtiles) {
+          // descriptor words: low = start >> 4 | LBO >> 4 << 16, high = SBO >> 4 | version 1 << 14
+          const uint32_t dw_hi = o.dw_hi;
+          uint32_t dl = ((smem_base16 + (o.in_hi >> 4)) & 0x3FFFu) | lbo_bits;
+          // accumulators of one M tile: per group of K chunks a pair of column blocks [hi*hi | cross terms]
+          const uint32_t n_grp = (kchunks + group - 1) / group;
+          uint32_t dgrp = tmem + r * d_cols + static_cast<uint32_t>(m) * n_grp * 2 * kNB;
+          uint32_t s = slot0 + static_cast<uint32_t>(m), par = par0;
+          if (s >= nsl) {
+            s -= nsl;
+            par ^= 1u;
           }
-          if (++slot == static_cast<uint32_t>(n_slots)) {
-            slot = 0;
-            full_par ^= 1u;
+          // The barrier poll costs ~140 cycles of latency (mbarrier.try_wait round trip, chain_probe5): the state of
+          // the NEXT own chunk's slot is sampled (non-blocking test_wait) before this chunk's MMAs are issued.
+          uint32_t ok = 0, left = kchunks;
+          for (uint32_t g = 0; g < n_grp; ++g, dgrp += 2 * kNB) {
+            const uint32_t in_g = left < group ? left : group;
+            left -= in_g;
+            for (uint32_t cc = 0; cc < in_g; ++cc) {
+              if (!ok && !dbg_nowait) chain_wait1(full0 + s * 8u, par);
+              ptx::tc_fence_after();
+              if (prof && m == 0 && oi == 4) prof[160 + 2 * (g * group + cc)] = clock64();
+              uint32_t ns = s + mtiles, npar = par;
+              if (ns >= nsl) {
+                ns -= nsl;
+                npar ^= 1u;
+              }
+              ok = ptx::mbar_test_wait_addr(full0 + ns * 8u, npar);  // (past the op's last chunk: a harmless early look)
+              const uint32_t ta_hi = ta0 + s * 64u;
+              // A_hi . [B_hi ; B_lo] (N = 32: the lo rows follow the hi rows in the operand buffer) -> [hi*hi | hi*lo];
+              // A_lo . B_hi -> the cross-term block
+              ptx::mma_tf32_ts2(dgrp, ta_hi, dl, dw_hi, idesc32, cc);
+              ptx::mma_tf32_ts2(dgrp + kNB, ta_hi + 32u, dl, dw_hi, idesc16, 1u);
+#pragma unroll
+              for (uint32_t j = 1; j < 4; ++j) {
+                ptx::mma_tf32_ts2(dgrp, ta_hi + 8u * j, dl + j * kstep, dw_hi, idesc32, 1u);
+                ptx::mma_tf32_ts2(dgrp + kNB, ta_hi + 32u + 8u * j, dl + j * kstep, dw_hi, idesc16, 1u);
+              }
+              if (!dbg_nocommit) ptx::mma_commit_addr(empty0 + s * 8u);
+              if (prof && m == 0 && oi == 4) prof[161 + 2 * (g * group + cc)] = clock64();
+              dl += 4 * kstep;
+              s = ns;
+              par = npar;
+            }
+            ok = (left > 0) ? ok : 0u;
           }
         }
-        dl_hi += 4 * kstep;
-        dl_lo += 4 * kstep;
-        if (++in_group == group) {
-          in_group = 0;
-          big += kNB;
+        ptx::mma_commit_addr(ptx::smem_u32(&C.d_full[r]));  // (a warp that issued nothing for this op arrives at once)
+        // ring position of the next op's first chunk
+        slot0 += mtiles * kchunks;
+        while (slot0 >= nsl) {
+          slot0 -= nsl;
+          par0 ^= 1u;
         }
       }
-      if (ptx::elect_one()) ptx::mma_commit(&C.d_full[r]);  // (a warp that issued nothing for this op arrives at once)
-      __syncwarp();
     }
-    if (prof && lane == 0 && m == 0) prof[61] = m_opwait;  // cycles waiting at op boundaries (operand written, region free)
+    __syncwarp();
   } else if (warp < 10) {
     // ================================================================= weight feeders
     const int q = warp & 3, half = (warp - 2) >> 2;
@@ -403,43 +456,61 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     const uint32_t ta_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + a_col0;
     const int roff = (row >> 3) * 64 + (row & 7);  // float4 index of this row inside a chunk (+ 8 per k core)
     ptx::pdl_wait();  // the weights are the previous launch's (Adam) output
+    if (L.debug & 128) total_chunks = 0;  // (timing probe: no feeders at all)
     long long t_wait = 0, t_work = 0;
+    // One chunk of this half is prefetched in registers; the split goes sixteen K columns at a time (register budget).
+    // Measured on the way here (tools/chain_prof.py): tcgen05.st x8 instead of x16 costs +250 cycles per chunk (the
+    // tensor-memory stores are slow while MMAs run), a second prefetched chunk buys nothing (the ring of TMEM slots,
+    // not the L2 latency, paces the feeders).
     float4 nx[8];
     if (half < total_chunks) {
-      const float4* s = reinterpret_cast<const float4*>(C.chunk_src[half]) + roff;
+      const float4* sp = reinterpret_cast<const float4*>(C.chunk_src[half]) + roff;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) nx[j] = __ldg(s + j * 8);
+      for (int j = 0; j < 8; ++j) nx[j] = __ldg(sp + j * 8);
     }
     int slot = half % n_slots, wraps = half / n_slots;
+    const uint32_t empty0 = ptx::smem_u32(&C.a_empty[0]);
+    uint32_t free_seen = 0;  // the slot of the upcoming chunk was already seen released (sampled one chunk ahead)
     for (int g = half; g < total_chunks; g += 2) {
-      float4 x[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = nx[j];
-      if (g + 2 < total_chunks && !(L.debug & 2)) {
-        const float4* s = reinterpret_cast<const float4*>(C.chunk_src[g + 2]) + roff;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) nx[j] = __ldg(s + j * 8);
-      }
       const long long t0 = prof ? clock64() : 0;
       if (wraps > 0) {
-        chain_wait(&C.a_empty[slot], static_cast<uint32_t>((wraps - 1) & 1), backoff);
+        // (tight poll: the feeders are the pace setters -- a back-off sleep here was ~300 cycles per chunk)
+        if (!free_seen) chain_wait(&C.a_empty[slot], static_cast<uint32_t>((wraps - 1) & 1), (L.debug & 256) != 0);
         ptx::tc_fence_after();
       }
       const long long t1 = prof ? clock64() : 0;
       const uint32_t ta = ta_lane + static_cast<uint32_t>(slot * 64);
+      // ring position of this half's next chunk; its release is sampled now (non-blocking), the ~140-cycle
+      // round trip of the poll overlaps the split below
+      int nslot = slot + 2, nwraps = wraps;
+      while (nslot >= n_slots) {
+        nslot -= n_slots;
+        nwraps += 1;
+      }
+      free_seen = (nwraps > 0 && g + 2 < total_chunks)
+                      ? ptx::mbar_test_wait_addr(empty0 + static_cast<uint32_t>(nslot) * 8u, static_cast<uint32_t>((nwraps - 1) & 1))
+                      : 0u;
 #pragma unroll
-      for (int j2 = 0; j2 < 4; ++j2) {  // eight K columns at a time: hi -> columns [8 j2, +8), lo -> 32 + the same
-        float hi[8], lo[8];
-        ptx::split_tf32(x[2 * j2].x, hi[0], lo[0]);
-        ptx::split_tf32(x[2 * j2].y, hi[1], lo[1]);
-        ptx::split_tf32(x[2 * j2].z, hi[2], lo[2]);
-        ptx::split_tf32(x[2 * j2].w, hi[3], lo[3]);
-        ptx::split_tf32(x[2 * j2 + 1].x, hi[4], lo[4]);
-        ptx::split_tf32(x[2 * j2 + 1].y, hi[5], lo[5]);
-        ptx::split_tf32(x[2 * j2 + 1].z, hi[6], lo[6]);
-        ptx::split_tf32(x[2 * j2 + 1].w, hi[7], lo[7]);
-        ptx::tmem_st8(ta + 8u * j2, hi);
-        ptx::tmem_st8(ta + 32u + 8u * j2, lo);
+      for (int j4 = 0; j4 < 2; ++j4) {  // sixteen K columns at a time: hi -> columns [16 j4, +16), lo -> 32 + the same
+        float hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          ptx::split_tf32(nx[4 * j4 + j].x, hi[4 * j + 0], lo[4 * j + 0]);
+          ptx::split_tf32(nx[4 * j4 + j].y, hi[4 * j + 1], lo[4 * j + 1]);
+          ptx::split_tf32(nx[4 * j4 + j].z, hi[4 * j + 2], lo[4 * j + 2]);
+          ptx::split_tf32(nx[4 * j4 + j].w, hi[4 * j + 3], lo[4 * j + 3]);
+        }
+        if (!(L.debug & 4)) {
+          ptx::tmem_st16(ta + 16u * j4, hi);
+          ptx::tmem_st16(ta + 32u + 16u * j4, lo);
+        } else {
+          asm volatile("" ::"f"(hi[0] + lo[7] + hi[3] + lo[2]));
+        }
+      }
+      if (g + 2 < total_chunks && !(L.debug & 2)) {
+        const float4* sp = reinterpret_cast<const float4*>(C.chunk_src[g + 2]) + roff;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) nx[j] = __ldg(sp + j * 8);
       }
       ptx::tmem_st_wait();
       ptx::tc_fence_before();
@@ -449,12 +520,15 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         const long long t2 = clock64();
         t_wait += t1 - t0;
         t_work += t2 - t1;
+        if (warp == 2 && lane == 0 && g >= 22 && g < 38) {
+          prof[96 + 3 * ((g - 22) >> 1)] = t0;
+          prof[97 + 3 * ((g - 22) >> 1)] = t1;
+          prof[98 + 3 * ((g - 22) >> 1)] = t2;
+        }
+        if (warp < 6 && lane == 0 && g >= 22 && g < 38) prof[200 + 4 * ((g - 22) >> 1) + (warp - 2)] = t2;  // quarter-warp skew
       }
-      slot += 2;
-      if (slot >= n_slots) {
-        slot -= n_slots;
-        wraps += 1;
-      }
+      slot = nslot;
+      wraps = nwraps;
     }
     if (prof && warp == 2 && lane == 0) {
       prof[56] = t_wait;   // cycles this feeder waited for a free TMEM slot (MMA / epilogue bound)
@@ -552,39 +626,41 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
         if (f < o.Ha) m2 = C.mask[o.mask2_slot][f];
       }
       // ---- accumulators -> registers (hi*hi groups in order, then the cross terms), release the region
-      const int r = oi & 1;
-      chain_wait(&C.d_full[r], static_cast<uint32_t>((oi >> 1) & 1), backoff);
+      const int r = oi & L.region_mask;
+      chain_wait(&C.d_full[r], static_cast<uint32_t>((L.region_mask ? (oi >> 1) : oi) & 1), backoff);
       ptx::tc_fence_after();
       if (prof && et == 0 && oi < 16) prof[32 + oi] = clock64();
       float v[kNB];
       if (act) {
-        const int n_big = (o.kchunks + o.group - 1) / o.group;
+        // per group of K chunks a pair [hi*hi | cross]: the hi*hi blocks in order, then the cross blocks
+        const int n_grp = (o.kchunks + o.group - 1) / o.group;
         const uint32_t base = tmem + (static_cast<uint32_t>(q * 32) << 16) +
-                              static_cast<uint32_t>(r * L.d_cols + mt * (n_big + 1) * kNB);
+                              static_cast<uint32_t>(r * L.d_cols + mt * n_grp * 2 * kNB);
         float p1[kNB], p2[kNB];
-        ptx::tmem_ld16_nowait(base + kNB, v);
-        if (n_big > 1) ptx::tmem_ld16_nowait(base + 2 * kNB, p1);
-        if (n_big <= 2) ptx::tmem_ld16_nowait(base, p2);
+        ptx::tmem_ld16_nowait(base, v);
+        ptx::tmem_ld16_nowait(base + (n_grp > 1 ? 2 * kNB : kNB), p1);  // second hi*hi block, or the only cross block
         ptx::tmem_ld_wait();
-        if (n_big > 1) {
 #pragma unroll
-          for (int n = 0; n < kNB; ++n) v[n] += p1[n];
-        }
-        if (n_big > 2) {
-          ptx::tmem_ld16_nowait(base + 3 * kNB, p1);
-          if (n_big > 3) ptx::tmem_ld16_nowait(base + 4 * kNB, p2);
-          ptx::tmem_ld_wait();
+        for (int n = 0; n < kNB; ++n) v[n] += p1[n];
+        if (n_grp > 1) {
+          for (int g = 2; g < n_grp; ++g) {
+            ptx::tmem_ld16_nowait(base + g * 2 * kNB, p1);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int n = 0; n < kNB; ++n) v[n] += p1[n];
-          if (n_big > 3) {
-#pragma unroll
-            for (int n = 0; n < kNB; ++n) v[n] += p2[n];
+            for (int n = 0; n < kNB; ++n) v[n] += p1[n];
           }
-          ptx::tmem_ld16_nowait(base, p2);
-          ptx::tmem_ld_wait();
-        }
+          for (int g = 0; g < n_grp; g += 2) {
+            ptx::tmem_ld16_nowait(base + g * 2 * kNB + kNB, p1);
+            if (g + 1 < n_grp) ptx::tmem_ld16_nowait(base + (g + 1) * 2 * kNB + kNB, p2);
+            ptx::tmem_ld_wait();
 #pragma unroll
-        for (int n = 0; n < kNB; ++n) v[n] += p2[n];
+            for (int n = 0; n < kNB; ++n) v[n] += p1[n];
+            if (g + 1 < n_grp) {
+#pragma unroll
+              for (int n = 0; n < kNB; ++n) v[n] += p2[n];
+            }
+          }
+        }
       } else {
 #pragma unroll
         for (int n = 0; n < kNB; ++n) v[n] = 0.f;

@@ -668,8 +668,7 @@ static bool use_chain(const oprl_engine* e) {
 }
 
 static int chain_pitch() {
-  static const int p = getenv("OPRL_B200_CHAIN_PITCH") ? atoi(getenv("OPRL_B200_CHAIN_PITCH")) : kCorePitch;
-  return p;
+  return kCorePitch;
 }
 
 struct ChainBuf {  // one operand buffer in the chain kernel's shared memory (+ its "written" barrier)
@@ -710,11 +709,13 @@ struct ChainBuilder {
     o.mtiles = pad128(M) / 128; o.kchunks = K / 32;
     // K chunks per hi*hi accumulator: 2 = chains of 8 MMAs as in gemm.cuh; OPRL_B200_CHAIN_GROUP=4 / 8 trade
     // accumulation-chain length for fewer accumulators to read out of TMEM (64 B/clk: 256 cycles each)
-    static const int env_group = getenv("OPRL_B200_CHAIN_GROUP") ? atoi(getenv("OPRL_B200_CHAIN_GROUP")) : 2;
+    static const int env_group = getenv("OPRL_B200_CHAIN_GROUP") ? atoi(getenv("OPRL_B200_CHAIN_GROUP")) : 4;
     o.group = std::max(env_group, (o.kchunks + 3) / 4);
     if (o.mtiles > 2 || o.kchunks > 8 || wt.rows < o.mtiles * 128) throw std::runtime_error("chain: layer too wide");
     o.in_hi = in.hi; o.in_lo = in.lo; o.in_sbo = in.sbo; o.in_bar = in.bar; o.in_phase = in.prod - 1;
     if (in.prod < 1) throw std::runtime_error("chain: operand consumed before it is produced");
+    // the N = 32 MMA reads [hi rows ; lo rows] as ONE operand: the lo half must follow the hi half's two row groups
+    if (in.lo != in.hi + 2 * in.sbo) throw std::runtime_error("chain: operand buffer halves are not contiguous");
     o.out_bar = -1; o.x_bar = -1; o.vec_slot = -1; o.vec2_slot = -1;
     return o;
   }
@@ -752,9 +753,13 @@ struct ChainBuilder {
       m.group = static_cast<uint8_t>(ops[i].group);
     }
     int d_cols = 0;
-    for (auto& o : ops) d_cols = std::max(d_cols, o.mtiles * (1 + (o.kchunks + o.group - 1) / o.group) * kNB);
+    for (auto& o : ops) d_cols = std::max(d_cols, o.mtiles * ((o.kchunks + o.group - 1) / o.group) * 2 * kNB);
+    // OPRL_B200_CHAIN_DBUF=0: one accumulator region (the read-out of an op no longer overlaps the next op's MMAs)
+    // in exchange for two more ring slots of weights in flight
+    static const bool dbuf = !(getenv("OPRL_B200_CHAIN_DBUF") && atoi(getenv("OPRL_B200_CHAIN_DBUF")) == 0);
+    L.region_mask = dbuf ? 1 : 0;
     L.d_cols = d_cols;
-    L.a_col0 = (2 * d_cols + 31) & ~31;
+    L.a_col0 = ((dbuf ? 2 : 1) * d_cols + 31) & ~31;
     L.n_slots = std::min(kCSlots, (512 - L.a_col0) / 64);
     if (L.n_slots < 2) throw std::runtime_error("chain: no tensor memory left for the operand ring");
     L.B = B; L.Bp = Bp;

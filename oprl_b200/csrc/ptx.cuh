@@ -194,6 +194,21 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                    "r"(smem_u32(bar))
                : "memory");
 }
+// non-blocking look at an mbarrier phase (shared::cta address): 1 = the phase with this parity has completed
+__device__ __forceinline__ uint32_t mbar_test_wait_addr(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar_saddr), "r"(parity)
+      : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mma_commit_addr(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar_saddr) : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i gets lane (lane_base+i).
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);

@@ -98,7 +98,7 @@ def first_update_conditioning(name, S, A, B, seed, data_seed, synthetic_init, **
     return O.PREACT_PROBE["min_abs"]
 
 
-def run_case(name, S, A, B, K, seed, subsample=1, synthetic_init=False, min_preact=MIN_PREACT, **kw):
+def run_case(name, S, A, B, K, seed, subsample=1, synthetic_init=False, min_preact=MIN_PREACT, first_full=False, **kw):
     """Well-conditioned fixture.  "Parameters after one Adam step" is discontinuous where a hidden
     ReLU pre-activation sits within rounding noise of zero (the unit's gradient switches on/off and
     Adam's first step is lr * sign(g)): with ~1e6 pre-activations per update such knife edges are
@@ -111,7 +111,7 @@ def run_case(name, S, A, B, K, seed, subsample=1, synthetic_init=False, min_prea
         if m0 < min_preact:
             continue
         O.PREACT_PROBE.update(enabled=True, min_abs=float("inf"))
-        fx = _run_case(name, S, A, B, K, seed, data_seed, subsample, synthetic_init, **kw)
+        fx = _run_case(name, S, A, B, K, seed, data_seed, subsample, synthetic_init, first_full=first_full, **kw)
         O.PREACT_PROBE["enabled"] = False
         fx["min_abs_preactivation_first"] = np.float64(m0)
         fx["min_abs_preactivation_all"] = np.float64(O.PREACT_PROBE["min_abs"])
@@ -121,7 +121,7 @@ def run_case(name, S, A, B, K, seed, subsample=1, synthetic_init=False, min_prea
     raise RuntimeError("no well-conditioned data seed found")
 
 
-def _run_case(name, S, A, B, K, seed, data_seed, subsample=1, synthetic_init=False, **kw):
+def _run_case(name, S, A, B, K, seed, data_seed, subsample=1, synthetic_init=False, first_full=False, **kw):
     """Returns the fixture dict.  K updates; dumps after update 1 and after update K."""
     torch.manual_seed(seed)
     ref = ref_algo(name, S, A, **kw)
@@ -181,6 +181,11 @@ def _run_case(name, S, A, B, K, seed, data_seed, subsample=1, synthetic_init=Fal
                 fx[f"{tag}_{key}_l2"] = np.float64(np.sqrt((val.astype(np.float64) ** 2).sum()))
                 fx[f"{tag}_{key}_sum"] = np.float64(val.astype(np.float64).sum())
                 fx[f"{tag}_{key}"] = val[::subsample].copy()
+                # first_full: the COMPLETE parameter vectors after the first update as well, so that the GPU parity
+                # test measures the true L2 instead of scaling a subsample (the target nets are derived in the test:
+                # Polyak of the seeded init and these)
+                if first_full and k == 0 and key in ("actor", "critic"):
+                    fx[f"firstfull_{key}"] = val.copy()
             if k == 0:
                 # gradients of the first update (reference leaves them in .grad)
                 ga = torch.cat([p.grad.reshape(-1) for p in ref.actor.parameters()]).numpy()
@@ -268,7 +273,7 @@ def main():
         "sac_fixed": lambda: run_case("sac", 24, 6, 8, 3, 3, subsample=8, tune_alpha=False),
         # configs[3]: TQC walker-walk 5x25, batch 256; 2.8M params -> seeded init + 1/64 subsample
         # (5.9M pre-activations per update: the margin that can be found is smaller)
-        "tqc": lambda: run_case("tqc", 24, 6, 256, 2, 4, subsample=64, synthetic_init=True, min_preact=1.2e-7),
+        "tqc": lambda: run_case("tqc", 24, 6, 256, 2, 4, subsample=64, synthetic_init=True, min_preact=1.2e-7, first_full=True),
         # ragged batch of 8 on DDPG (reference test shape)
         "ddpg_b8": lambda: run_case("ddpg", 24, 6, 8, 2, 5, subsample=8),
     }

@@ -58,6 +58,30 @@ def engine_flat(algo, which):
     return None if t_ is None else t_.detach().cpu().numpy()
 
 
+def polyak_f32(target0, source, tau=np.float32(5e-3)):
+    """tau * p + (1 - tau) * t in fp32 with the reference's three roundings (ddpg.py:72-84, tqc.py:154-159)."""
+    one_minus = np.float32(1.0 - 5e-3)
+    return (tau * source.astype(np.float32) + one_minus * target0.astype(np.float32)).astype(np.float32)
+
+
+def compare_to_fixture_full(algo, fx, orc0):
+    """Exact parameter L2 after the first update against COMPLETE reference vectors (fixtures written with
+    first_full: actor + critic stored whole; the critic target is Polyak(init, critic) -- its own init equals the
+    critic's)."""
+    sq = 0.0
+    for key in ("actor", "critic"):
+        got = engine_flat(algo, key)
+        ref = fx[f"firstfull_{key}"]
+        assert got.shape == ref.shape
+        sq += float(((got.astype(np.float64) - ref.astype(np.float64)) ** 2).sum())
+    tgt = polyak_f32(orc0["critic"], fx["firstfull_critic"])
+    sq += float(((engine_flat(algo, "critic_target").astype(np.float64) - tgt.astype(np.float64)) ** 2).sum())
+    # cross-check of the derived target on the fixture's own subsample
+    sub = int(fx["subsample"])
+    assert np.array_equal(tgt[::sub], fx["first_critic_target"]), "derived target nets disagree with the fixture's subsample"
+    return np.sqrt(sq)
+
+
 def compare_to_fixture(algo, fx, tag):
     sub = int(fx["subsample"])
     sq = 0.0
@@ -76,6 +100,7 @@ def test_fixture_parity(name):
     orc = oracle_from_fixture(fx)
     algo = make_algo(fx)
     load_initial(algo, orc)
+    orc0 = {"critic": orc.flat("critic").copy()}
     K = int(fx["K"])
     for k in range(K):
         noise = fixture_noise(fx, k)
@@ -89,18 +114,37 @@ def test_fixture_parity(name):
             if fk in fx:
                 assert abs(sc[key] - float(fx[fk])) <= LOSS_TOL, (k, key, sc[key], float(fx[fk]))
         if k == 0:
-            l2 = compare_to_fixture(algo, fx, "first")
-            print(f"{name}: param L2 after 1 update = {l2:.3e}")
+            if "firstfull_critic" in fx:
+                l2 = compare_to_fixture_full(algo, fx, orc0)
+                print(f"{name}: param L2 after 1 update = {l2:.3e} (exact, complete vectors)")
+            else:
+                l2 = compare_to_fixture(algo, fx, "first")
+                print(f"{name}: param L2 after 1 update = {l2:.3e}" + (" (estimated from a 1/%d subsample)" % int(fx["subsample"]) if int(fx["subsample"]) > 1 else ""))
             assert l2 <= PARAM_L2_TOL
             if "first_log_alpha" in fx:
                 assert abs(algo.engine.state().log_alpha - float(fx["first_log_alpha"])) <= 1e-7
     l2 = compare_to_fixture(algo, fx, "last")
     margin = float(fx["min_abs_preactivation_all"])
-    print(f"{name}: param L2 after {K} updates = {l2:.3e} (min |pre-activation| over them {margin:.1e})")
-    # Later updates are not conditioned (oracle/gen_golden.py): a hidden pre-activation within
-    # rounding noise of zero flips a ReLU and with it the sign of a few near-zero Adam steps
-    # (2*lr = 6e-4 each).  Strict bar when the fixture stayed clear of that, loose bound otherwise.
-    assert l2 <= (PARAM_L2_TOL * K if margin >= 5e-7 else 5e-3)
+    # Later updates are not conditioned (oracle/gen_golden.py): a hidden pre-activation within rounding noise of zero
+    # flips a ReLU, and Adam's early steps are ~lr * sign(g), so a flipped unit moves a handful of elements by up to
+    # ~2 * lr * K.  Element-wise check: everything is held to 1e-5 * K in L2 EXCEPT at most `max_flipped` elements,
+    # each of which must still be within the flipped-ReLU signature (2 * lr * K).
+    sub, lr = int(fx["subsample"]), 3e-4
+    diffs = []
+    for key in ("actor", "critic", "critic_target", "actor_target"):
+        kk = f"last_{key}"
+        if kk in fx:
+            diffs.append(np.abs(engine_flat(algo, key)[::sub].astype(np.float64) - fx[kk].astype(np.float64)))
+    d = np.concatenate(diffs)
+    outlier = d > 1e-5
+    n_out = int(outlier.sum())
+    rest_l2 = float(np.sqrt((d[~outlier] ** 2).sum() * sub))
+    print(f"{name}: param L2 after {K} updates = {l2:.3e} (min |pre-activation| over them {margin:.1e}); "
+          f"{n_out} of {d.size} compared elements beyond 1e-5 (max {d.max():.2e}), L2 of the rest {rest_l2:.3e}")
+    max_flipped = 0 if margin >= 5e-7 else max(8, d.size // 20000)
+    assert n_out <= max_flipped, f"{n_out} elements off by more than 1e-5 (allowed {max_flipped})"
+    assert d.max() <= 2.5 * lr * K, "an element moved by more than a flipped ReLU can explain"
+    assert rest_l2 <= PARAM_L2_TOL * K
 
 
 def test_host_batch_and_int64_done_match_the_device_path():

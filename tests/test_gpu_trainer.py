@@ -98,6 +98,8 @@ def test_trainer_runs_and_resumes(tmp_path, algo_name):
     assert all(p.device.type == "cpu" for p in pol.parameters())
     live = export_policy(algo.actor)
     obs = np.ones(24, np.float32)
+    if getattr(algo, "_mirror", None) is not None:
+        algo._mirror.refresh_now()  # the host mirror may still be one asynchronous copy behind the last update
     np.testing.assert_allclose(live.exploit(obs), algo.actor.exploit(obs), atol=1e-5)
 
     # checkpoint -> two more updates -> restore -> the same two updates reproduce bit-exactly
@@ -125,3 +127,93 @@ def test_trainer_runs_and_resumes(tmp_path, algo_name):
         for k in ref[g]:
             assert torch.equal(ref[g][k], got[g][k]), (g, k)
     assert ref_alpha == got_alpha
+
+
+def test_staged_ingest_wraps_the_pinned_ring_and_stays_bit_exact():
+    """add_transition stages into a pinned ring (4096 rows) flushed by one H2D + one scatter launch: more
+    transitions than the ring holds, flushes forced at odd points, episode ring wrap -- storage must equal a
+    plain numpy replay of the same bookkeeping."""
+    from oprl_b200.buffers.episodic_buffer import EpisodicReplayBuffer
+
+    S, A, Lmax, E = 5, 3, 50, 120
+    buf = EpisodicReplayBuffer(buffer_size_transitions=E * Lmax, state_dim=S, action_dim=A, max_episode_lenth=Lmax).create()
+    rng = np.random.default_rng(0)
+    ref = {"states": np.zeros((E, Lmax + 1, S), np.float32), "actions": np.zeros((E, Lmax, A), np.float32),
+           "rewards": np.zeros((E, Lmax, 1), np.float32), "dones": np.zeros((E, Lmax, 1), np.float32)}
+    ep, lens = 0, [0] * E
+    n = 9500  # > 2 ring capacities, > E * Lmax: the episode ring wraps as well
+    for i in range(n):
+        s, a = rng.standard_normal(S).astype(np.float32), rng.uniform(-1, 1, A).astype(np.float32)
+        r, d = float(rng.uniform()), bool(rng.uniform() < 0.01)
+        done_ep = d or lens[ep] == Lmax - 1
+        buf.add_transition(s, a, r, d, episode_done=done_ep)
+        ref["states"][ep, lens[ep]] = s
+        ref["actions"][ep, lens[ep]] = a
+        ref["rewards"][ep, lens[ep], 0] = np.float32(r)
+        ref["dones"][ep, lens[ep], 0] = float(d)
+        lens[ep] += 1
+        if done_ep:
+            ep = (ep + 1) % E
+            lens[ep] = 0
+        if i % 1777 == 5:
+            buf.flush()
+    assert list(buf.ep_lens) == lens and buf._ep_pointer == ep
+    for name in ("states", "actions", "rewards", "dones"):
+        got = getattr(buf, name).cpu().numpy()
+        # rows of episodes that were reset keep their old content in both (only ep_lens shrinks)
+        assert np.array_equal(got, ref[name]), name
+
+
+def test_host_rollout_mirror_follows_the_device_weights_without_syncing():
+    """explore / exploit on a CPU mirror refreshed by async D2H copies into pinned memory."""
+    import time
+
+    from oprl_b200.algos.ddpg import DDPG
+
+    class NullLogger:
+        log_dir = "/tmp"
+
+        def log_scalar(self, *a, **k):
+            pass
+
+        def log_scalars(self, *a, **k):
+            pass
+
+    torch.manual_seed(0)
+    algo = DDPG(logger=NullLogger(), state_dim=24, action_dim=6).create()
+    obs = np.random.default_rng(0).standard_normal(24).astype(np.float32)
+    want = algo.actor.exploit(obs)  # device path
+    # env-steps/s of the acting call alone (no-op environment), device path vs host mirror
+    def rate(fn, n=300):
+        fn(obs)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn(obs)
+        return n / (time.perf_counter() - t0)
+
+    dev_rate = rate(algo.actor.explore)
+    mirror = algo.enable_host_rollout(refresh_every=1)
+    np.testing.assert_allclose(algo.actor.exploit(obs), want, atol=1e-6)
+    host_rate = rate(algo.actor.explore)
+    print(f"explore(): {dev_rate:.0f} calls/s on the device network, {host_rate:.0f} calls/s on the host mirror ({host_rate / dev_rate:.1f}x)")
+    assert host_rate > 2.0 * dev_rate
+    # the mirror follows the updates
+    g = torch.Generator().manual_seed(1)
+    batch = [torch.randn(64, 24, generator=g), torch.rand(64, 6, generator=g) * 2 - 1, torch.rand(64, 1, generator=g),
+             torch.zeros(64, 1), torch.randn(64, 24, generator=g)]
+    for _ in range(5):
+        algo.update(*batch)
+    torch.cuda.synchronize()
+    algo.actor.exploit(obs)  # picks up a completed copy
+    assert mirror.swaps >= 1
+    mirror.refresh_now()
+    algo.disable_host_rollout()
+    dev = algo.actor.exploit(obs)
+    algo.actor.__dict__["_host_mirror"] = mirror
+    np.testing.assert_allclose(algo.actor.exploit(obs), dev, atol=1e-5)
+    assert not np.allclose(dev, want)  # the weights did move
+    # and the policy still pickles with the mirror attached (torch.save(algo.actor) of the reference trainer)
+    import io
+
+    bio = io.BytesIO()
+    torch.save(algo.actor, bio)

@@ -36,6 +36,13 @@ for which in (0, 1):
     print(f"  feeder warp 1: waited for a free slot {p[56]} cycles, store+arrive {p[57]} cycles, over {p[58]//2} of {p[58]} chunks; "
           f"first arrivals at {[int(x - t0) for x in p[48:56]]}")
     print(f"  MMA warp: waited for filled slots {p[59]}, issued {p[60]}, waited at op boundaries {p[61]} cycles")
+    if which == 0:
+        print("  op 4 (16 chunks), M tile 0: MMA thread [slot seen filled, MMAs + commit issued] | feeder half 0 [top, slot free, arrived]")
+        for i in range(8):
+            print(f"    chunk {i}: MMA {[int(p[160 + 2 * i + k] - t0) for k in range(2)]}   feeder {[int(p[96 + 3 * i + k] - t0) for k in range(3)]}")
+    if which == 0:
+        for i in range(3, 8):
+            print(f"    chunk {i}: arrivals of the four quarter warps of feeder half 0: {[int(p[200 + 4 * i + k] - t0) for k in range(4)]}")
     names = ["accumulators in registers", "layer epilogue done", "head partials written", "behind barrier A", "dz in operand buffer", "arrived", "finisher done", "behind barrier B"]
     print(f"  epilogue of op {p[62]} (QLOSS / DXA), cycles since its accumulators were complete:")
     base = p[32 + p[62]] if 0 <= p[62] < 16 else 0
