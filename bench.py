@@ -51,26 +51,31 @@ MIN_SETTLE_STEPS = 16  # untimed steps before the timed window whatever --warmup
 
 def ncu_traffic_per_launch(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the newest committed
-    `ncu --set full` raw-page CSV under profiles/ (cold L2: ncu flushes caches between replays).  None if absent."""
+    `ncu --set full` raw-page CSV under profiles/ (cold L2: ncu flushes caches between replays).  None if absent.
+    The raw page is: a header row, a units row, then one row per profiled launch."""
     import csv
     import glob
 
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "": 1.0}
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*raw*.csv")), reverse=True):
         try:
-            rows = list(csv.DictReader(open(path)))
-        except Exception:
+            rows = [r for r in csv.reader(open(path)) if r]
+            hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
+            cols = {name: k for k, name in enumerate(rows[hdr])}
+            units = rows[hdr + 1] if hdr + 1 < len(rows) else []
+            kn, rd, wr = cols["Kernel Name"], cols["dram__bytes_read.sum"], cols["dram__bytes_write.sum"]
+        except (StopIteration, KeyError, OSError):
             continue
+        unit = lambda c: scale.get(units[c].strip() if c < len(units) else "", 1.0)
         tot, n = 0.0, 0
-        for r in rows:
-            if kernel_substr not in r.get("Kernel Name", ""):
+        for r in rows[hdr + 2:]:
+            if len(r) <= max(kn, rd, wr) or kernel_substr not in r[kn]:
                 continue
             try:
-                rd, wr = float(r["dram__bytes_read.sum"].replace(",", "")), float(r["dram__bytes_write.sum"].replace(",", ""))
-            except (KeyError, ValueError):
+                tot += float(r[rd].replace(",", "")) * unit(rd) + float(r[wr].replace(",", "")) * unit(wr)
+                n += 1
+            except ValueError:
                 continue
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-            tot += rd * scale.get(r.get("dram__bytes_read.sum.unit", "byte"), 1.0) + wr * scale.get(r.get("dram__bytes_write.sum.unit", "byte"), 1.0)
-            n += 1
         if n:
             return {"bytes_per_launch": tot / n, "launches": n, "source": os.path.relpath(path, ROOT)}
     return None
@@ -344,6 +349,48 @@ def run_engine(args):
         simt_ms = eng.time_simt_only(B, iters=200)
         gather_us = eng.time_gather_only(B, iters=200)
 
+    # ---- N > 1: the two other scaling modes SURVEY.md section 8e asks for, beside the weak-scaling headline
+    other_modes = None
+    if dp:
+        other_modes = {}
+        with torch.cuda.stream(stream):
+            sub_steps = max(50, min(args.steps, 500))
+            # strong scaling: the reference's global minibatch B split over the ranks (B / world rows each)
+            if B % world == 0 and B // world >= 1:
+                Bs = B // world
+                for _ in range(MIN_SETTLE_STEPS):
+                    algo.learner_step(Bs)
+                barrier()
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record(stream)
+                for _ in range(sub_steps):
+                    algo.learner_step(Bs)
+                s1.record(stream)
+                barrier()
+                t_ = torch.tensor([s0.elapsed_time(s1)], device=device, dtype=torch.float64)
+                dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+                other_modes["strong"] = {"value": sub_steps / (float(t_) * 1e-3), "unit": f"optimizer steps/s on a global minibatch of {B} ({Bs} rows per GPU)",
+                                         "ms_per_step": float(t_) / sub_steps, "steps": sub_steps}
+            # replicas: one independent learner per GPU, no collective (the reference's run_training(seeds=N), train.py:35-49)
+            solo = make_algo(args.algo, S, A, device)
+            solo.attach_buffer(buf)
+            solo.engine.set_prefix(buf.ep_lens[:buf.episodes_counter])
+            for _ in range(MIN_SETTLE_STEPS):
+                solo.learner_step(B)
+            barrier()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            for _ in range(sub_steps):
+                solo.learner_step(B)
+            r1.record(stream)
+            barrier()
+            t_ = torch.tensor([r0.elapsed_time(r1)], device=device, dtype=torch.float64)
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            other_modes["replicas"] = {"value": world * sub_steps / (float(t_) * 1e-3), "unit": f"updates/s summed over {world} independent learners (batch {B} each, no collective)",
+                                       "ms_per_step": float(t_) / sub_steps, "steps": sub_steps}
+            solo.engine.close()
+            algo.attach_buffer(buf)  # (the buffer's fused sample() goes back to the data-parallel learner's engine)
+
     t_ms = torch.tensor([ms, e2e_ms, api_ms, e2e_sync_ms], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
@@ -427,6 +474,8 @@ def run_engine(args):
         out["roofline_gemm"] = roof_gemm
     if dp_parity is not None:
         out["dp_parity"] = dp_parity
+    if other_modes:
+        out["scaling_modes"] = {"weak (headline `value`)": f"{B} rows per GPU, global minibatch {B * world}", **other_modes}
     if multi:
         out["multi_learner"] = multi
     if rank == 0:

@@ -117,6 +117,7 @@ class EpisodicReplayBuffer:
         self._stage_lo = 0  # first row not yet flushed
         self._stage_hi = 0  # next free row
         self._stage_events = []  # (first row, last row + 1, event) of flushes whose H2D may still read the ring
+        self._stage_eps = set()  # episode slots with staged, not yet flushed rows
 
     def _stage_wait_rows(self, lo: int, hi: int) -> None:
         keep = []
@@ -144,6 +145,7 @@ class EpisodicReplayBuffer:
             ev = t.cuda.Event()
             ev.record()
         self._stage_events.append((lo, hi, ev))
+        self._stage_eps.clear()
         if hi >= self._STAGE_ROWS:
             hi = 0
         self._stage_lo = self._stage_hi = hi
@@ -165,6 +167,7 @@ class EpisodicReplayBuffer:
         ri = self._stage_int[row]
         ri[S + A + 2] = ep
         ri[S + A + 3] = i
+        self._stage_eps.add(ep)
         self._stage_hi = row + 1
         if self._stage_hi - self._stage_lo >= self._STAGE_ROWS // 2 or self._stage_hi >= self._STAGE_ROWS:
             self.flush()
@@ -175,6 +178,10 @@ class EpisodicReplayBuffer:
 
     def _inc_episode(self) -> None:
         self._ep_pointer = (self._ep_pointer + 1) % self._max_episodes
+        if self._ep_pointer in self._stage_eps:
+            # the episode ring wrapped onto a slot that still has staged rows: one scatter launch writes its rows
+            # in no particular order, so the older rows must land before newer ones for the same cells are staged
+            self.flush()
         self.episodes_counter = min(self.episodes_counter + 1, self._max_episodes)
         self._number_transitions -= self.ep_lens[self._ep_pointer]
         self.ep_lens[self._ep_pointer] = 0

@@ -44,7 +44,9 @@
 namespace oprl {
 
 constexpr int kNB = 16;                  // batch rows (MMA N) per CTA
-constexpr int kChainWarps = 18;
+constexpr int kFeedGroups = 2;            // feeder groups of four warps (one per TMEM lane quarter); chunk g belongs to group g % kFeedGroups
+                                         // (3 groups = 22 warps at 80 registers measured no faster: the slot hand-shake, not the feeders' work, paces the ring)
+constexpr int kChainWarps = 2 + 4 * kFeedGroups + 8;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kChainThreads = kChainWarps * 32;
@@ -124,7 +126,10 @@ struct ChainLaunch {
   int B, Bp, n_cta;
   int n_in;
   ChainInput in[3];
-  const unsigned int* gm_src[2];  // mask bits written by an earlier chain launch
+  // ReLU masks of layers whose forward ran in an EARLIER launch (the actor's pi(s) pass): rebuilt at kernel start
+  // from the saved transposed activations (CT32 [gm_rows x Bp], h > 0)
+  const float* gm_src[2];
+  int gm_rows[2];
   int gm_slot[2];
   int n_gm;
   const float* r;
@@ -326,7 +331,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
   }
   if (warp == 0) {
     if (lane < kCSlots) {
-      ptx::mbar_init(&C.a_full[lane], 4);   // the four quarter warps of one feeder half
+      ptx::mbar_init(&C.a_full[lane], 4);   // the four quarter warps of one feeder group
       ptx::mbar_init(&C.a_empty[lane], 1);  // tcgen05.commit of the MMA warp that consumed the chunk
     } else if (lane < kCSlots + 2) {
       ptx::mbar_init(&C.d_full[lane - kCSlots], 2);          // one commit per MMA warp
@@ -449,9 +454,9 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       }
     }
     __syncwarp();
-  } else if (warp < 10) {
+  } else if (warp < 2 + 4 * kFeedGroups) {
     // ================================================================= weight feeders
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int q = warp & 3, half = (warp - 2) >> 2;  // half: this warp's feeder group
     const int row = q * 32 + lane;
     const uint32_t ta_lane = tmem + (static_cast<uint32_t>(q * 32) << 16) + a_col0;
     const int roff = (row >> 3) * 64 + (row & 7);  // float4 index of this row inside a chunk (+ 8 per k core)
@@ -471,7 +476,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     int slot = half % n_slots, wraps = half / n_slots;
     const uint32_t empty0 = ptx::smem_u32(&C.a_empty[0]);
     uint32_t free_seen = 0;  // the slot of the upcoming chunk was already seen released (sampled one chunk ahead)
-    for (int g = half; g < total_chunks; g += 2) {
+    for (int g = half; g < total_chunks; g += kFeedGroups) {
       const long long t0 = prof ? clock64() : 0;
       if (wraps > 0) {
         // (tight poll: the feeders are the pace setters -- a back-off sleep here was ~300 cycles per chunk)
@@ -480,14 +485,16 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       }
       const long long t1 = prof ? clock64() : 0;
       const uint32_t ta = ta_lane + static_cast<uint32_t>(slot * 64);
-      // ring position of this half's next chunk; its release is sampled now (non-blocking), the ~140-cycle
-      // round trip of the poll overlaps the split below
-      int nslot = slot + 2, nwraps = wraps;
+      // ring position of this group's next chunk; its release is sampled now (non-blocking), the ~140-cycle
+      // round trip of the poll overlaps the split below.  (Safe only because n_slots is a multiple of kFeedGroups:
+      // a group then always revisits ITS OWN slots, so the phase it asks about is at most one behind -- with slots
+      // shared between groups the parity test can alias a phase two uses back and release a slot still being read.)
+      int nslot = slot + kFeedGroups, nwraps = wraps;
       while (nslot >= n_slots) {
         nslot -= n_slots;
         nwraps += 1;
       }
-      free_seen = (nwraps > 0 && g + 2 < total_chunks)
+      free_seen = (nwraps > 0 && g + kFeedGroups < total_chunks)
                       ? ptx::mbar_test_wait_addr(empty0 + static_cast<uint32_t>(nslot) * 8u, static_cast<uint32_t>((nwraps - 1) & 1))
                       : 0u;
 #pragma unroll
@@ -507,8 +514,8 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
           asm volatile("" ::"f"(hi[0] + lo[7] + hi[3] + lo[2]));
         }
       }
-      if (g + 2 < total_chunks && !(L.debug & 2)) {
-        const float4* sp = reinterpret_cast<const float4*>(C.chunk_src[g + 2]) + roff;
+      if (g + kFeedGroups < total_chunks && !(L.debug & 2)) {
+        const float4* sp = reinterpret_cast<const float4*>(C.chunk_src[g + kFeedGroups]) + roff;
 #pragma unroll
         for (int j = 0; j < 8; ++j) nx[j] = __ldg(sp + j * 8);
       }
@@ -537,7 +544,7 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
     }
   } else {
     // ================================================================= epilogue warps
-    const int e = warp - 10;  // 0..7
+    const int e = warp - (2 + 4 * kFeedGroups);  // 0..7
     const int q = warp & 3, mt = e >> 2;
     const int f = mt * 128 + q * 32 + lane;  // feature row of the layer output this thread owns
     const int et = e * 32 + lane;            // 0..255
@@ -567,7 +574,19 @@ __global__ void __launch_bounds__(kChainThreads, 1) chain_kernel(const __grid_co
       C.rr[et] = L.r ? __ldg(L.r + mrow) : 0.f;
       C.dd[et] = L.d ? __ldg(L.d + mrow) : 0.f;
     }
-    for (int k = 0; k < L.n_gm; ++k) C.mask[L.gm_slot[k]][et] = __ldg(L.gm_src[k] + static_cast<size_t>(cta) * kCFeat + et);
+    for (int k = 0; k < L.n_gm; ++k) {
+      uint32_t bits = 0;
+      if (et < L.gm_rows[k]) {
+        const float4* src = reinterpret_cast<const float4*>(L.gm_src[k] + ct_index(L.gm_rows[k], et, n0));
+#pragma unroll
+        for (int n4 = 0; n4 < kNB / 4; ++n4) {
+          const float4 h4 = __ldg(src + n4 * 8);
+          bits |= (h4.x > 0.f ? 1u : 0u) << (4 * n4) | (h4.y > 0.f ? 2u : 0u) << (4 * n4) | (h4.z > 0.f ? 4u : 0u) << (4 * n4) |
+                  (h4.w > 0.f ? 8u : 0u) << (4 * n4);
+        }
+      }
+      C.mask[L.gm_slot[k]][et] = bits;
+    }
     ptx::fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0)

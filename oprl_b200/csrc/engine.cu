@@ -657,14 +657,30 @@ static void fill_constant_seed(oprl_engine* e, const TM& D, int B, int ncols, fl
 
 // ---------------------------------------------------------------- DDPG / TD3 on the chain kernel
 // One update = chain(critic step) -> grouped dW GEMM -> Adam(critic) -> chain(actor step) -> grouped dW
-// GEMM -> Adam(actor): 6 launches instead of 15 (chain.cuh).  OPRL_B200_CHAIN=0 keeps the stage path.
+// GEMM -> Adam(actor): 6 launches instead of 15 (chain.cuh).
 static bool use_chain(const oprl_engine* e) {
-  static const bool off = getenv("OPRL_B200_CHAIN") && atoi(getenv("OPRL_B200_CHAIN")) == 0;
+  // Off by default: measured on B200 the chain path takes 100 us per DDPG update against 92 us for the stage path
+  // (TD3: 101 vs 81) -- 7 launches instead of 15, but each CTA has to push every weight of every net through one
+  // tensor core, and the slot hand-shake between its feeder and issuing warps paces that at ~450-550 cycles per
+  // 16 KB chunk.  OPRL_B200_CHAIN=1 selects it (same parity tests).
+  static const bool on = getenv("OPRL_B200_CHAIN") && atoi(getenv("OPRL_B200_CHAIN")) != 0;
   const oprl_cfg& c = e->cfg;
   auto ok_h = [](int h) { return h == 128 || h == 256; };
-  return !off && (c.algo == OPRL_ALGO_DDPG || c.algo == OPRL_ALGO_TD3) && c.gemm_mode == OPRL_GEMM_TC_3XTF32 &&
+  return on && (c.algo == OPRL_ALGO_DDPG || c.algo == OPRL_ALGO_TD3) && c.gemm_mode == OPRL_GEMM_TC_3XTF32 &&
          c.actor_layers == 2 && c.critic_layers == 2 && ok_h(c.actor_hidden) && ok_h(c.critic_hidden) &&
-         c.action_dim <= kCMaxJ && e->Kin <= 256;
+         c.actor_hidden == c.critic_hidden && c.action_dim <= kCMaxJ && e->Kin <= 256;
+}
+
+// The hybrid: critic step on the stage path, actor step as one chain launch (12 launches per DDPG update instead of
+// 16).  Measured equal to the stage path (92.6 vs 92.8 us per DDPG update, 82.2 vs 81.4 TD3), so it stays opt-in:
+// OPRL_B200_CHAIN_ACTOR=1.
+static bool use_chain_actor(const oprl_engine* e) {
+  static const bool on = getenv("OPRL_B200_CHAIN_ACTOR") && atoi(getenv("OPRL_B200_CHAIN_ACTOR")) != 0;
+  const oprl_cfg& c = e->cfg;
+  auto ok_h = [](int h) { return h == 128 || h == 256; };
+  return on && (c.algo == OPRL_ALGO_DDPG || c.algo == OPRL_ALGO_TD3) && c.gemm_mode == OPRL_GEMM_TC_3XTF32 &&
+         c.actor_layers == 2 && c.critic_layers == 2 && ok_h(c.actor_hidden) && ok_h(c.critic_hidden) &&
+         c.actor_hidden == c.critic_hidden && c.action_dim <= kCMaxJ && e->Kin <= 256;
 }
 
 static int chain_pitch() {
@@ -760,7 +776,7 @@ struct ChainBuilder {
     L.region_mask = dbuf ? 1 : 0;
     L.d_cols = d_cols;
     L.a_col0 = ((dbuf ? 2 : 1) * d_cols + 31) & ~31;
-    L.n_slots = std::min(kCSlots, (512 - L.a_col0) / 64);
+    L.n_slots = std::min(kCSlots, (512 - L.a_col0) / 64) / kFeedGroups * kFeedGroups;  // (see the feeders' early release poll)
     if (L.n_slots < 2) throw std::runtime_error("chain: no tensor memory left for the operand ring");
     L.B = B; L.Bp = Bp;
     L.n_cta = (B + kNB - 1) / kNB;
@@ -783,6 +799,98 @@ struct ChainBuilder {
   }
 };
 
+// The actor step as ONE chain launch + one grouped weight-gradient GEMM launch (stages s0, s0 + 1): critic.Q1(s, pi(s))
+// with the updated critic, dX down to the action columns, tanh', policy backward.  Inputs left behind by the forward
+// pi(s) pass (chain A or the stage path): a_rm = tanh output row-major, a_h0T / a_h1T = the actor's hidden
+// activations transposed-tiled (also the source of its ReLU masks), w->Xp = tiled (s, pi(s)).
+static void add_chain_actor_step(oprl_engine* e, Builder& b, oprl_engine::Work* w, Program* p, int s0, float* a_rm,
+                                 const TM& a_h0T, const TM& a_h1T) {
+  const oprl_cfg& c = e->cfg;
+  const int B = w->B, Bp = w->Bp, A = c.action_dim, S = c.state_dim, A4 = e->A4;
+  const int Kin = e->Kin, Ha = c.actor_hidden, Hc = c.critic_hidden;
+  Group& ga = e->grp[OPRL_NET_ACTOR];
+  Group& gc = e->grp[OPRL_NET_CRITIC];
+  const Net& an = ga.nets[0];
+  const float inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
+  TM a_dz1T = e->alloc_tm(pad128(Ha), Bp), a_dz0T = e->alloc_tm(pad128(Ha), Bp), dzaT = e->alloc_tm(128, Bp);
+  if (!p->chain_prof[1]) {
+    static const bool want_prof = getenv("OPRL_B200_CHAIN_PROF") && atoi(getenv("OPRL_B200_CHAIN_PROF")) != 0;
+    if (want_prof) p->chain_prof[1] = reinterpret_cast<long long*>(e->alloc_floats(2 * 256));
+  }
+  // ---- chain C: critic.Q1(s, pi(s)) with the updated critic, dX down to the action, policy backward
+  {
+    const Net& cn = gc.nets[0];
+    ChainBuilder cb(e);
+    ChainBuf bXp = cb.buf(Kin);
+    cb.input(w->Xp, bXp);
+    ChainBuf big0 = cb.buf(Hc), big1 = cb.buf(Hc), big2 = cb.buf(Ha);
+    {
+      ChainOp o = cb.op(cn.L[0].W, Hc, Kin, bXp);
+      o.bias = gc.theta + cn.L[0].b_off; o.flags |= CF_BIAS_RELU | CF_SAVE_MASK;
+      o.mask_slot = 0;
+      cb.out(o, big0);
+      cb.ops.push_back(o);
+    }
+    {
+      ChainOp o = cb.op(cn.L[1].W, Hc, Hc, big0);
+      o.bias = gc.theta + cn.L[1].b_off; o.flags |= CF_BIAS_RELU;
+      o.head = CH_QACTOR;
+      o.hw = gc.theta + cn.L[2].w_off; o.hb = gc.theta + cn.L[2].b_off;
+      cb.out(o, big1);
+      o.flags &= ~CF_OUT_SMEM;
+      cb.ops.push_back(o);
+    }
+    {
+      ChainOp o = cb.op(cn.L[1].WT, Hc, Hc, big1);
+      o.flags |= CF_APPLY_MASK;
+      o.mask_slot = 0;
+      o.head = CH_DXA; o.J = A;
+      o.hw = gc.theta + cn.L[0].w_off + S; o.hw_ld = cn.L[0].in;  // W0[f][S + j]: the action columns
+      o.aux = a_rm;
+      o.w2 = ga.theta + an.L[2].w_off; o.Ha = Ha;
+      o.mask2_slot = 1;
+      o.hout = dzaT.p;
+      o.vec_slot = cb.vec(ga.grad + an.L[1].b_off, Ha);
+      cb.out(o, big2);
+      o.flags &= ~CF_OUT_SMEM;
+      o.gout = a_dz1T.p; o.gout_rows = a_dz1T.rows;
+      cb.ops.push_back(o);
+    }
+    {
+      ChainOp o = cb.op(an.L[1].WT, Ha, Ha, big2);
+      o.flags |= CF_APPLY_MASK | CF_COLSUM;
+      o.mask_slot = 2;
+      o.vec_slot = cb.vec(ga.grad + an.L[0].b_off, Ha);
+      cb.gout(o, a_dz0T);
+      cb.ops.push_back(o);
+    }
+    cb.L.kind = 1; cb.L.nq = 1;
+    cb.L.inv_count = inv_count;
+    cb.L.gb_head = ga.grad + an.L[2].b_off; cb.L.J = A;
+    cb.L.n_gm = 2;
+    cb.L.gm_src[0] = a_h1T.p; cb.L.gm_rows[0] = a_h1T.rows; cb.L.gm_slot[0] = 1;
+    cb.L.gm_src[1] = a_h0T.p; cb.L.gm_rows[1] = a_h0T.rows; cb.L.gm_slot[1] = 2;
+    b.stage(s0).add_simt(cb.finish(B, Bp, p->chain_prof[1]), 1, true);
+  }
+  // ---- actor weight gradients
+  {
+    GemmOp o = b.base_op(dzaT, a_h1T, 128, an.L[2].Kp, Bp);
+    o.rm = ga.grad + an.L[2].w_off; o.rm_ld = an.L[2].in; o.rm_m = an.L[2].out; o.rm_n = an.L[2].in;
+    b.stage(s0 + 1).ops.push_back(o);
+  }
+  {
+    GemmOp o = b.base_op(a_dz1T, a_h0T, pad128(Ha), an.L[1].Kp, Bp);
+    o.rm = ga.grad + an.L[1].w_off; o.rm_ld = an.L[1].in; o.rm_m = an.L[1].out; o.rm_n = an.L[1].in;
+    b.stage(s0 + 1).ops.push_back(o);
+  }
+  {
+    GemmOp o = b.base_op(a_dz0T, w->XT, pad128(Ha), an.L[0].Kp, Bp);
+    o.rm = ga.grad + an.L[0].w_off; o.rm_ld = an.L[0].in; o.rm_m = an.L[0].out; o.rm_n = an.L[0].Kp;
+    o.map_a = 0; o.map_a4 = A4; o.map_s = S;
+    b.stage(s0 + 1).ops.push_back(o);
+  }
+}
+
 static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   const oprl_cfg& c = e->cfg;
   const bool td3 = c.algo == OPRL_ALGO_TD3;
@@ -794,7 +902,6 @@ static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* 
   Group& gc = e->grp[OPRL_NET_CRITIC];
   const Net& an = ga.nets[0];
   const float inv_count = static_cast<float>(1.0 / (static_cast<double>(B) * c.world_size));
-  const int n_cta = (B + kNB - 1) / kNB;
   static const bool want_prof = getenv("OPRL_B200_CHAIN_PROF") && atoi(getenv("OPRL_B200_CHAIN_PROF")) != 0;
   if (want_prof)
     for (int k = 0; k < 2; ++k) p->chain_prof[k] = reinterpret_cast<long long*>(e->alloc_floats(2 * 256));
@@ -806,18 +913,12 @@ static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* 
     c_dz1T[i] = e->alloc_tm(pad128(Hc), Bp);
     c_dz0T[i] = e->alloc_tm(pad128(Hc), Bp);
   }
-  TM a_h0T{nullptr, 0, 0}, a_h1T{nullptr, 0, 0}, a_dz1T{nullptr, 0, 0}, a_dz0T{nullptr, 0, 0}, dzaT{nullptr, 0, 0};
+  TM a_h0T{nullptr, 0, 0}, a_h1T{nullptr, 0, 0};
   float* a_rm = nullptr;
-  unsigned int *a_mask0 = nullptr, *a_mask1 = nullptr;
   if (do_actor) {
     a_h0T = e->alloc_tm(pad128(Ha), Bp);
     a_h1T = e->alloc_tm(pad128(Ha), Bp);
-    a_dz1T = e->alloc_tm(pad128(Ha), Bp);
-    a_dz0T = e->alloc_tm(pad128(Ha), Bp);
-    dzaT = e->alloc_tm(128, Bp);
     a_rm = e->alloc_floats(static_cast<size_t>(Bp) * A);
-    a_mask0 = reinterpret_cast<unsigned int*>(e->alloc_floats(static_cast<size_t>(n_cta) * kCFeat));
-    a_mask1 = reinterpret_cast<unsigned int*>(e->alloc_floats(static_cast<size_t>(n_cta) * kCFeat));
   }
 
   // ---- chain A: targets, critic forward, TD loss, critic dX chain, and pi(s) for the actor step
@@ -853,8 +954,7 @@ static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* 
     }
     if (do_actor) {  // actor layer 0 over s (actor step forward: independent of the critic update)
       ChainOp o = cb.op(an.L[0].W, Ha, Kin, bXp);
-      o.bias = ga.theta + an.L[0].b_off; o.flags |= CF_BIAS_RELU | CF_MASK_GLOBAL;
-      o.gmask = a_mask0;
+      o.bias = ga.theta + an.L[0].b_off; o.flags |= CF_BIAS_RELU;
       cb.out(o, bigP);
       cb.gout(o, a_h0T);
       cb.ops.push_back(o);
@@ -875,8 +975,7 @@ static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* 
     }
     if (do_actor) {  // actor layer 1 + tanh head -> pi(s): row-major (tanh') and into the tiled (s, pi(s)) matrix
       ChainOp o = cb.op(an.L[1].W, Ha, Ha, bigP);
-      o.bias = ga.theta + an.L[1].b_off; o.flags |= CF_BIAS_RELU | CF_MASK_GLOBAL;
-      o.gmask = a_mask1;
+      o.bias = ga.theta + an.L[1].b_off; o.flags |= CF_BIAS_RELU;
       cb.gout(o, a_h1T);
       o.head = CH_ACTION; o.J = A;
       o.hw = ga.theta + an.L[2].w_off; o.hw_ld = Ha; o.hb = ga.theta + an.L[2].b_off;
@@ -958,78 +1057,7 @@ static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* 
     b.stage(2).add_simt([e, &gc, mode, exit_barrier, ltc](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc); });
   }
   if (!do_actor) return;
-  // ---- chain C: critic.Q1(s, pi(s)) with the updated critic, dX down to the action, policy backward
-  {
-    const Net& cn = gc.nets[0];
-    ChainBuilder cb(e);
-    ChainBuf bXp = cb.buf(Kin);
-    cb.input(w->Xp, bXp);
-    ChainBuf big0 = cb.buf(Hc), big1 = cb.buf(Hc), big2 = cb.buf(Ha);
-    {
-      ChainOp o = cb.op(cn.L[0].W, Hc, Kin, bXp);
-      o.bias = gc.theta + cn.L[0].b_off; o.flags |= CF_BIAS_RELU | CF_SAVE_MASK;
-      o.mask_slot = 0;
-      cb.out(o, big0);
-      cb.ops.push_back(o);
-    }
-    {
-      ChainOp o = cb.op(cn.L[1].W, Hc, Hc, big0);
-      o.bias = gc.theta + cn.L[1].b_off; o.flags |= CF_BIAS_RELU;
-      o.head = CH_QACTOR;
-      o.hw = gc.theta + cn.L[2].w_off; o.hb = gc.theta + cn.L[2].b_off;
-      cb.out(o, big1);
-      o.flags &= ~CF_OUT_SMEM;
-      cb.ops.push_back(o);
-    }
-    {
-      ChainOp o = cb.op(cn.L[1].WT, Hc, Hc, big1);
-      o.flags |= CF_APPLY_MASK;
-      o.mask_slot = 0;
-      o.head = CH_DXA; o.J = A;
-      o.hw = gc.theta + cn.L[0].w_off + S; o.hw_ld = cn.L[0].in;  // W0[f][S + j]: the action columns
-      o.aux = a_rm;
-      o.w2 = ga.theta + an.L[2].w_off; o.Ha = Ha;
-      o.mask2_slot = 1;
-      o.hout = dzaT.p;
-      o.vec_slot = cb.vec(ga.grad + an.L[1].b_off, Ha);
-      cb.out(o, big2);
-      o.flags &= ~CF_OUT_SMEM;
-      o.gout = a_dz1T.p; o.gout_rows = a_dz1T.rows;
-      cb.ops.push_back(o);
-    }
-    {
-      ChainOp o = cb.op(an.L[1].WT, Ha, Ha, big2);
-      o.flags |= CF_APPLY_MASK | CF_COLSUM;
-      o.mask_slot = 2;
-      o.vec_slot = cb.vec(ga.grad + an.L[0].b_off, Ha);
-      cb.gout(o, a_dz0T);
-      cb.ops.push_back(o);
-    }
-    cb.L.kind = 1; cb.L.nq = 1;
-    cb.L.inv_count = inv_count;
-    cb.L.gb_head = ga.grad + an.L[2].b_off; cb.L.J = A;
-    cb.L.n_gm = 2;
-    cb.L.gm_src[0] = a_mask1; cb.L.gm_slot[0] = 1;
-    cb.L.gm_src[1] = a_mask0; cb.L.gm_slot[1] = 2;
-    b.stage(3).add_simt(cb.finish(B, Bp, p->chain_prof[1]), 1, true);
-  }
-  // ---- actor weight gradients
-  {
-    GemmOp o = b.base_op(dzaT, a_h1T, 128, an.L[2].Kp, Bp);
-    o.rm = ga.grad + an.L[2].w_off; o.rm_ld = an.L[2].in; o.rm_m = an.L[2].out; o.rm_n = an.L[2].in;
-    b.stage(4).ops.push_back(o);
-  }
-  {
-    GemmOp o = b.base_op(a_dz1T, a_h0T, pad128(Ha), an.L[1].Kp, Bp);
-    o.rm = ga.grad + an.L[1].w_off; o.rm_ld = an.L[1].in; o.rm_m = an.L[1].out; o.rm_n = an.L[1].in;
-    b.stage(4).ops.push_back(o);
-  }
-  {
-    GemmOp o = b.base_op(a_dz0T, w->XT, pad128(Ha), an.L[0].Kp, Bp);
-    o.rm = ga.grad + an.L[0].w_off; o.rm_ld = an.L[0].in; o.rm_m = an.L[0].out; o.rm_n = an.L[0].Kp;
-    o.map_a = 0; o.map_a4 = A4; o.map_s = S;
-    b.stage(4).ops.push_back(o);
-  }
+  add_chain_actor_step(e, b, w, p, 3, a_rm, a_h0T, a_h1T);
   b.seg = 2;
   {
     LossTail lt{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
@@ -1156,6 +1184,18 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     if (!do_actor && (p->flags & kFlagPublish)) ltc.pub = e->h_pub;  // TD3 critic-only update: this is its last kernel
     b.stage(s).add_simt([e, &gc, mode, exit_barrier, ltc](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc); });
     ++s;
+  }
+  if (do_actor && use_chain_actor(e)) {
+    // ---- actor step on the chain kernel: its critical path (critic forward over (s, pi(s)), dX down to the
+    // action, policy backward) is strictly serial in the stage path too -- four launches plus the dz halves of two
+    // more -- and collapses into one launch (chain.cuh); the weight gradients follow as one grouped GEMM launch.
+    add_chain_actor_step(e, b, w, p, s, a_rm, p_a.hT[0], p_a.hT[1]);
+    s += 2;
+    b.seg = 2;
+    LossTail lt{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
+    lt.pub = (p->flags & kFlagPublish) ? e->h_pub : nullptr;
+    b.stage(s).add_simt([e, &ga, lt](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt); });
+    return;
   }
   if (do_actor) {
     // ---- actor step ----------------------------------------------------------

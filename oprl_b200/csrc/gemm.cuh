@@ -323,48 +323,59 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
   }
 
   if (!kSimt && warp == 1) {
-    // ===================== MMA issuer (warp converged, one elected lane issues)
+    // ===================== MMA issuer: ONE elected thread runs the whole K loop (waits included).
+    // Its program is serial -- every instruction between two MMAs costs its full latency -- so the loop keeps to
+    // the barrier poll, the operand words (descriptor low word advanced by adds, not rebuilt per MMA) and the
+    // MMAs; the poll of the NEXT chunk's barrier (~140 cycles round trip) is sampled before this chunk's MMAs
+    // are issued.  (Electing per chunk and rebuilding both 64-bit descriptors per MMA cost ~55 cycles per MMA,
+    // which -- not the L2 ingest -- was what bound the K loop; tools/experiments/chain_probe5.cu.)
     const uint32_t tmem_d = *tmem_slot;
-    const uint32_t idesc = ptx::idesc_tf32(kBM, kBN, 0, 0);
-    // B smem tile = [row group of 8][8 K-cores][8 rows][16 B]: K cores 128 B apart (LBO),
-    // 8-row groups 1 KB apart (SBO); one MMA (K=8) consumes two K cores = 256 B.
-    const uint32_t b_step = 256u;
-    const uint32_t b_lbo = 128u, b_sbo = 1024u;
-    int in_group = 0;
-    uint32_t big = tmem_d + 32u;
-    for (int c = 0; c < nloc; ++c) {  // c: local chunk index
-      const int s = c % kStages;
-      const uint32_t ph = (c / kStages) & 1;
-      ptx::mbar_wait(&conv[s], ph);
-      ptx::tc_fence_after();
-      if (prof && c == 0 && lane == 0) prof[3] = clock64();
-      if (ptx::elect_one()) {
-        const uint32_t sb_hi = ptx::smem_u32(smem + s * kStageFloats + kAFloats);
-        const uint32_t sb_lo = sb_hi + kBFloats * 4;
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::idesc_tf32(kBM, kBN, 0, 0);
+      // B smem tile = [row group of 8][8 K-cores][8 rows][16 B]: K cores 128 B apart (LBO), 8-row groups 1 KB
+      // apart (SBO); one MMA (K = 8) consumes two K cores = 256 B = 16 descriptor units.
+      const uint32_t dw_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14);
+      const uint32_t lbo_bits = (128u >> 4) << 16;
+      const uint32_t conv0 = ptx::smem_u32(&conv[0]), empty0 = ptx::smem_u32(&empty[0]);
+      const uint32_t sb0 = ptx::smem_u32(smem + kAFloats);
+      int in_group = 0;
+      uint32_t big = tmem_d + 32u;
+      uint32_t ok = 0;
+      for (int c = 0; c < nloc; ++c) {  // c: local chunk index
+        const int s = c % kStages;
+        if (!ok) {
+          const uint32_t par = static_cast<uint32_t>((c / kStages) & 1);
+          uint32_t spins = 0;
+          while (!ptx::mbar_test_wait_addr(conv0 + s * 8u, par)) {
+            if (++spins > (1u << 26)) __trap();
+          }
+        }
+        ptx::tc_fence_after();
+        if (prof && c == 0) prof[3] = clock64();
+        ok = (c + 1 < nloc) ? ptx::mbar_test_wait_addr(conv0 + ((c + 1) % kStages) * 8u, static_cast<uint32_t>(((c + 1) / kStages) & 1)) : 0u;
+        const uint32_t dl_hi = (((sb0 + static_cast<uint32_t>(s) * kStageBytes) >> 4) & 0x3FFFu) | lbo_bits;
+        const uint32_t dl_lo = dl_hi + ((kBFloats * 4u) >> 4);
         const uint32_t ta_hi = tmem_d + a_col0 + static_cast<uint32_t>((c % kASlots) * kATmemCols);
         const uint32_t ta_lo = ta_hi + kBK;
 #pragma unroll
         for (int j = 0; j < kBK / 8; ++j) {
-          const uint64_t db_hi = ptx::smem_desc(sb_hi + j * b_step, b_lbo, b_sbo);
           const uint32_t big_acc = (in_group | j) ? 1u : 0u;
           if (passes == 3) {
-            const uint64_t db_lo = ptx::smem_desc(sb_lo + j * b_step, b_lbo, b_sbo);
-            ptx::mma_tf32_ts(tmem_d, ta_lo + 8u * j, db_hi, idesc, (c | j) ? 1u : 0u);
-            ptx::mma_tf32_ts(tmem_d, ta_hi + 8u * j, db_lo, idesc, 1u);
+            ptx::mma_tf32_ts2(tmem_d, ta_lo + 8u * j, dl_hi + 16u * j, dw_hi, idesc, (c | j) ? 1u : 0u);
+            ptx::mma_tf32_ts2(tmem_d, ta_hi + 8u * j, dl_lo + 16u * j, dw_hi, idesc, 1u);
           }
-          ptx::mma_tf32_ts(big, ta_hi + 8u * j, db_hi, idesc, big_acc);
+          ptx::mma_tf32_ts2(big, ta_hi + 8u * j, dl_hi + 16u * j, dw_hi, idesc, big_acc);
         }
-        ptx::mma_commit(&empty[s]);
+        ptx::mma_commit_addr(empty0 + s * 8u);
+        if (++in_group == group) {
+          in_group = 0;
+          big += 32u;
+        }
       }
-      __syncwarp();
-      if (++in_group == group) {
-        in_group = 0;
-        big += 32u;
-      }
+      ptx::mma_commit(accum);
+      if (prof) prof[4] = clock64();
     }
-    if (ptx::elect_one()) ptx::mma_commit(accum);
     __syncwarp();
-    if (prof && lane == 0) prof[4] = clock64();
   } else if (warp >= 2) {
     // ===================== splitter + epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;

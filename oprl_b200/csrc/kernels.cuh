@@ -222,6 +222,38 @@ __global__ void __launch_bounds__(kGatherBlock)
     r = g.rewards[row];
     d = g.dones[row];
   }
+  // s and s' are ADJACENT rows of the replay storage: one contiguous 2S-float read.  When S is a multiple of 4 (and
+  // so is the padded action width, which makes every state quad land inside one 4-column core of the tiled
+  // matrices) the row goes as 16-byte vectors: a lane = four state columns -> one LDG.128, one 16-byte store per
+  // row-major / tiled destination (walker: 12 lanes cover both states instead of 48 scalar round trips).
+  if ((g.S & 3) == 0 && (g.A4 & 3) == 0 && (reinterpret_cast<uintptr_t>(src_s) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(src_s2) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.bs) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(g.bs2) & 15) == 0) {
+    const int q4 = g.S >> 2;  // quads per state row
+    for (int c = lane; c < 2 * q4; c += 32) {
+      const bool nxt = c >= q4;
+      const int j = (nxt ? c - q4 : c) * 4;
+      const float4 v = __ldg(reinterpret_cast<const float4*>((nxt ? src_s2 : src_s) + j));
+      if (!nxt) {
+        if (g.bs) *reinterpret_cast<float4*>(g.bs + static_cast<size_t>(b) * g.S + j) = v;
+        *reinterpret_cast<float4*>(g.X.p + ct_index(g.X.rows, b, g.A4 + j)) = v;
+        *reinterpret_cast<float4*>(g.Xp.p + ct_index(g.Xp.rows, b, g.A4 + j)) = v;
+        store_tiled(g.XT, g.A4 + j + 0, b, v.x);
+        store_tiled(g.XT, g.A4 + j + 1, b, v.y);
+        store_tiled(g.XT, g.A4 + j + 2, b, v.z);
+        store_tiled(g.XT, g.A4 + j + 3, b, v.w);
+      } else {
+        if (g.bs2) *reinterpret_cast<float4*>(g.bs2 + static_cast<size_t>(b) * g.S + j) = v;
+        *reinterpret_cast<float4*>(g.Xn.p + ct_index(g.Xn.rows, b, g.A4 + j)) = v;
+      }
+    }
+    for (int c = lane; c < g.A; c += 32) {
+      const float v = src_a[c];
+      if (g.ba) g.ba[static_cast<size_t>(b) * g.A + c] = v;
+      store_tiled(g.X, b, c, v);
+      store_tiled(g.XT, c, b, v);
+    }
+  } else {
   const int W = g.A + 2 * g.S;
   for (int c = lane; c < W; c += 32) {
     if (c < g.A) {
@@ -242,6 +274,7 @@ __global__ void __launch_bounds__(kGatherBlock)
       if (g.bs2) g.bs2[static_cast<size_t>(b) * g.S + j] = v;
       store_tiled(g.Xn, b, g.A4 + j, v);
     }
+  }
   }
   if (lane == 0) {
     if (g.br) g.br[b] = r;

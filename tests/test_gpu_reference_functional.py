@@ -104,9 +104,9 @@ def test_policy_pickles_like_the_reference_trainer_saves_it(name):
     buf = io.BytesIO()
     torch.save(algo.actor, buf)
     buf.seek(0)
-    loaded = torch.load(buf, weights_only=False, map_location="cpu")
+    loaded = torch.load(buf, weights_only=False)  # (as scripts/visualize_policy_from_weights.py does: same device)
     for (k, a), (k2, b) in zip(algo.actor.state_dict().items(), loaded.state_dict().items()):
-        assert k == k2 and torch.equal(a.cpu(), b), k
+        assert k == k2 and torch.equal(a.cpu(), b.cpu()), k
     loaded.load_state_dict(algo.get_policy_state_dict())  # the detached hook is a no-op
     obs = np.zeros(OBS_DIM, np.float32)
     assert loaded.exploit(obs).shape == (ACT_DIM,)

@@ -193,6 +193,7 @@ def test_host_rollout_mirror_follows_the_device_weights_without_syncing():
 
     dev_rate = rate(algo.actor.explore)
     mirror = algo.enable_host_rollout(refresh_every=1)
+    assert mirror._np is not None, "the numpy fast path must cover the reference's policy classes"
     np.testing.assert_allclose(algo.actor.exploit(obs), want, atol=1e-6)
     host_rate = rate(algo.actor.explore)
     print(f"explore(): {dev_rate:.0f} calls/s on the device network, {host_rate:.0f} calls/s on the host mirror ({host_rate / dev_rate:.1f}x)")
