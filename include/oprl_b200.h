@@ -103,6 +103,15 @@ int oprl_buffer_bind(oprl_engine* e, const float* states, const float* actions,
  * gather after it is ordered behind everything enqueued on the launch stream so far, later gathers
  * may run ahead of the update in flight (see oprl_step). */
 int oprl_buffer_set_prefix(oprl_engine* e, const int* prefix_host, int n_eps);
+/* n-step return assembly in the gather (BASELINE north_star; the reference keeps `gamma` in the buffer,
+ * src/oprl/buffers/episodic_buffer.py:18, but assembles 1-step transitions only -- this is an extension, off by
+ * default).  With n_step > 1, oprl_sample / oprl_step return for a drawn (episode, t):
+ *   reward R = sum_{k<m} gamma^k r_{t+k}, next_state = s_{t+m}, done d' = 1 - (1 - d_{t+m-1}) gamma^(m-1),
+ *   m = min(n_step, steps up to and including the first done, steps left in the episode),
+ * so the unchanged 1-step TD target r + (1 - d') gamma Q'(s') equals the n-step target.  Needs
+ * oprl_buffer_set_prefix (episode lengths).  n_step = 1 restores the reference's transitions bit for bit. */
+int oprl_buffer_set_nstep(oprl_engine* e, int n_step, double gamma);
+
 /* Row-major batch arrays the gather writes (what sample() returns): device pointers
  * s [cap,S], a [cap,A], r [cap], d [cap], s2 [cap,S]. */
 int oprl_batch_bind(oprl_engine* e, float* s, float* a, float* r, float* d, float* s2, int cap);

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "oprl_engine_sync_params": (C.c_int, [_P]),
     "oprl_buffer_bind": (C.c_int, [_P, _P, _P, _P, _P, C.c_int, C.c_int]),
     "oprl_buffer_set_prefix": (C.c_int, [_P, _P, C.c_int]),
+    "oprl_buffer_set_nstep": (C.c_int, [_P, C.c_int, C.c_double]),
     "oprl_batch_bind": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int]),
     "oprl_sample": (C.c_int, [_P, _P, C.c_int]),
     "oprl_load_batch": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int]),

@@ -45,6 +45,9 @@ class EpisodicReplayBuffer:
     device: str = "cuda"
     # False (default): sample() returns fresh tensors like the reference's advanced indexing does.  True: it
     # returns views of the engine's one batch arena -- no copy, but the NEXT sample() overwrites them.
+    # n-step returns assembled by the gather kernel (extension; needs an attached engine).  The reference stores
+    # `gamma` here and never uses it (episodic_buffer.py:18): n_step = 1 keeps its 1-step transitions bit for bit.
+    n_step = 1
     zero_copy_batches = False  # (plain class attribute: the dataclass fields stay exactly the reference's)
 
     _tensors: dict = field(init=False, default_factory=dict)
@@ -214,6 +217,13 @@ class EpisodicReplayBuffer:
     def sample(self, batch_size: int) -> tuple[t.Tensor, t.Tensor, t.Tensor, t.Tensor, t.Tensor]:
         self.flush()
         ep_step = self.draw_indices(batch_size)
+        if self.n_step > 1:
+            if self._engine is None:
+                raise L.EngineError("n_step > 1 needs an attached engine (algo.attach_buffer(buffer))")
+            if getattr(self, "_nstep_set", None) != (self.n_step, self.gamma):
+                self._engine.set_nstep(self.n_step, self.gamma)
+                self._nstep_set = (self.n_step, self.gamma)
+            self._engine.set_prefix(self.ep_lens[:self.episodes_counter])  # the window stops at the episode's end
         if self._engine is not None:
             out = self._engine.sample(batch_size, ep_step)
             if not self.zero_copy_batches:

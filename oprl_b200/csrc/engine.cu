@@ -144,6 +144,18 @@ struct Program {
   int n_chain_launches = 0;
   int n_launches = 0;
   long long* chain_prof[2] = {nullptr, nullptr};  // OPRL_B200_CHAIN_PROF=1: clock64 stamps of CTA 0 of the critic / actor chain
+  // Device workspaces this program owns (activations, op tables, partial buffers): freed with it, so that a learner
+  // whose programs are rebuilt (new batch size, rebound arenas, world size / comm changes) does not leak them.
+  std::vector<void*> blocks;
+  ~Program() {
+    bool any = !blocks.empty();
+    for (int k = 0; k < 8; ++k) any = any || graph[k];
+    if (!any) return;
+    cudaDeviceSynchronize();  // a launch that still reads these may be in flight (rare path: rebuilds only)
+    for (int k = 0; k < 8; ++k)
+      if (graph[k]) cudaGraphExecDestroy(graph[k]);
+    for (void* b : blocks) cudaFree(b);
+  }
 };
 
 }  // namespace oprl
@@ -183,6 +195,8 @@ struct oprl_engine {
   // replay + batch bindings
   const float *rb_states = nullptr, *rb_actions = nullptr, *rb_rewards = nullptr, *rb_dones = nullptr;
   int rb_E = 0, rb_L = 0;
+  int n_step = 1;            // n-step return assembly in the gather (oprl_buffer_set_nstep); 1 = the reference's transitions
+  float nstep_gamma = 0.99f;
   int* d_prefix = nullptr;
   int prefix_cap = 0, n_eps = 0, n_trans = 0;
   float *bs = nullptr, *ba = nullptr, *br = nullptr, *bd = nullptr, *bs2 = nullptr;
@@ -234,12 +248,13 @@ struct oprl_engine {
     std::vector<void*> opened;
   } comm;
 
+  std::vector<void*>* alloc_scope = nullptr;  // while a Program is being built: its own block list
   float* alloc_floats(size_t n) {
     void* p = nullptr;
     const size_t bytes = ((n * 4 + 1023) / 1024) * 1024;
     CU(cudaMalloc(&p, bytes));
     CU(cudaMemsetAsync(p, 0, bytes, stream));
-    blocks.push_back(p);
+    (alloc_scope ? *alloc_scope : blocks).push_back(p);
     return static_cast<float*>(p);
   }
   TM alloc_tm(int rows, int cols) {
@@ -1596,9 +1611,16 @@ static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
   p->B = w->B;
   p->Bp = w->Bp;
   p->flags = flags;
-  if (e->cfg.algo == OPRL_ALGO_DDPG || e->cfg.algo == OPRL_ALGO_TD3) build_ddpg_td3(e, w, p.get());
-  else build_sac_tqc(e, w, p.get());
-  prepare_stage_tables(e, p.get());
+  e->alloc_scope = &p->blocks;
+  try {
+    if (e->cfg.algo == OPRL_ALGO_DDPG || e->cfg.algo == OPRL_ALGO_TD3) build_ddpg_td3(e, w, p.get());
+    else build_sac_tqc(e, w, p.get());
+    prepare_stage_tables(e, p.get());
+  } catch (...) {
+    e->alloc_scope = nullptr;
+    throw;
+  }
+  e->alloc_scope = nullptr;
   CU(cudaStreamSynchronize(e->stream));  // workspace memsets / constant uploads done
   // capture: one graph per segment + one for the whole update
   for (int k = 0; k < 8; ++k) {
@@ -1825,10 +1847,7 @@ void oprl_engine_destroy(oprl_engine* e) {
     if (kv.second->ev_ready) cudaEventDestroy(kv.second->ev_ready);
     if (kv.second->ev_free) cudaEventDestroy(kv.second->ev_free);
   }
-  for (auto& kv : e->work)
-    for (auto& pv : kv.second->prog)
-      for (int k = 0; k < 8; ++k)
-        if (pv.second->graph[k]) cudaGraphExecDestroy(pv.second->graph[k]);
+  for (auto& kv : e->work) kv.second->prog.clear();  // (~Program: graphs + the workspaces each program owns)
   for (void* p : e->comm.opened) cudaIpcCloseMemHandle(p);
   for (void* p : e->blocks) cudaFree(p);
   if (e->h_state) cudaFreeHost(e->h_state);
@@ -1921,6 +1940,15 @@ int oprl_buffer_set_prefix(oprl_engine* e, const int* prefix_host, int n_eps) {
   API_END
 }
 
+int oprl_buffer_set_nstep(oprl_engine* e, int n_step, double gamma) {
+  if (!e || n_step < 1 || n_step > 64 || !(gamma >= 0.0 && gamma <= 1.0)) return fail(-1, "bad n-step setting");
+  e->n_step = n_step;
+  e->nstep_gamma = static_cast<float>(gamma);
+  e->rb_dirty = true;
+  e->rb_epoch += 1;  // the in-graph gather of oprl_step is re-captured
+  return 0;
+}
+
 int oprl_batch_bind(oprl_engine* e, float* s, float* a, float* r, float* d, float* s2, int cap) {
   if (!e || !s || !a || !r || !d || !s2 || cap <= 0) return fail(-1, "bad batch arena");
   e->bs = s; e->ba = a; e->br = r; e->bd = d; e->bs2 = s2;
@@ -1946,6 +1974,11 @@ static int sample_impl(oprl_engine* e, const int* ep_step_host, int B, bool side
   } else if (!e->d_prefix || e->n_trans <= 0) {
     return fail(-1, "device sampling needs oprl_buffer_set_prefix");
   }
+  if (e->n_step > 1 && (!e->d_prefix || e->n_eps <= 0)) return fail(-1, "n-step sampling needs oprl_buffer_set_prefix (episode lengths)");
+  if (e->n_step > 1 && ep_step_host) {
+    for (int i = 0; i < B; ++i)
+      if (ep_step_host[2 * i] >= e->n_eps) return fail(-1, "index %d: episode %d has no length (prefix covers %d episodes)", i, ep_step_host[2 * i], e->n_eps);
+  }
   // replay rows / prefix sums written since the last gather, or injected noise copied on the launch
   // stream: this gather must be ordered behind them
   side = side && e->overlap && !ep_step_host && !e->rb_dirty && !e->ext_mask;
@@ -1955,9 +1988,13 @@ static int sample_impl(oprl_engine* e, const int* ep_step_host, int B, bool side
   g.states = e->rb_states; g.actions = e->rb_actions; g.rewards = e->rb_rewards; g.dones = e->rb_dones;
   g.L = e->rb_L;
   g.dense = 0;
+  g.n_step = e->n_step;
+  g.nstep_gamma = e->nstep_gamma;
   if (ep_step_host) {
     CU(cudaMemcpyAsync(w->d_idx, ep_step_host, sizeof(int) * 2 * B, cudaMemcpyHostToDevice, st));
     g.ep_step = w->d_idx;
+    g.prefix = e->d_prefix;  // (episode lengths for the n-step window; unused at n_step = 1)
+    g.n_eps = e->n_eps;
   } else {
     g.ep_step = nullptr;
     g.prefix = e->d_prefix;
@@ -2113,6 +2150,8 @@ static cudaGraphExec_t get_step_graph(oprl_engine* e, oprl_engine::Work* w, oprl
   g.states = e->rb_states; g.actions = e->rb_actions; g.rewards = e->rb_rewards; g.dones = e->rb_dones;
   g.L = e->rb_L;
   g.dense = 0;
+  g.n_step = e->n_step;
+  g.nstep_gamma = e->nstep_gamma;
   g.ep_step = nullptr;
   g.prefix = e->d_prefix;
   g.n_eps = e->n_eps;

@@ -120,6 +120,13 @@ struct GatherArgs {
   int ext;
   int dev_tick;  // 1: read DevState::tick instead (prefetching gather inside the update graph, placed
                  // behind the loss kernel that advances the counter -- nobody writes it after that)
+  // n-step returns (north_star; the reference stores `gamma` in the buffer and never uses it, episodic_buffer.py:18):
+  // with n_step > 1 a sampled (episode, step) yields  R = sum_{k<m} gamma^k r_{t+k},  s' = s_{t+m},
+  // m = min(n_step, steps up to and including the first done, steps left in the episode), and the EFFECTIVE done
+  // d' = 1 - (1 - d_{t+m-1}) gamma^{m-1}, so that the unchanged 1-step target r + (1 - d') gamma Q'(s') is the n-step
+  // target R + (1 - d) gamma^m Q'(s_{t+m}).  n_step <= 1: the reference's 1-step transition, bit for bit.
+  int n_step;
+  float nstep_gamma;
   int* out_ep_step;                 // [B][2] what was sampled (device sampling), nullable
   TM X, XT, Xn, Xp;
   NoiseSpec noise[2];  // blocks >= B draw the update's normals (n == 0: none)
@@ -221,6 +228,20 @@ __global__ void __launch_bounds__(kGatherBlock)
     src_s2 = src_s + g.S;
     r = g.rewards[row];
     d = g.dones[row];
+    if (g.n_step > 1) {
+      // (every lane computes the same few terms: n is small and the loads are broadcast)
+      const int ep_len = g.prefix[ep + 1] - g.prefix[ep];
+      float gpow = 1.f;  // gamma^(m-1)
+      int m = 1;
+      while (m < g.n_step && d == 0.f && step + m < ep_len) {
+        gpow = __fmul_rn(gpow, g.nstep_gamma);
+        r = __fadd_rn(r, __fmul_rn(gpow, g.rewards[row + m]));
+        d = g.dones[row + m];
+        ++m;
+      }
+      src_s2 = src_s + static_cast<size_t>(m) * g.S;
+      d = __fsub_rn(1.f, __fmul_rn(__fsub_rn(1.f, d), gpow));
+    }
   }
   // s and s' are ADJACENT rows of the replay storage: one contiguous 2S-float read.  When S is a multiple of 4 (and
   // so is the padded action width, which makes every state quad land inside one 4-column core of the tiled

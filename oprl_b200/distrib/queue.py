@@ -80,13 +80,9 @@ class Queue:
             raise ValueError("oprl_b200 queues are in-node shared memory: host must be localhost")
         self._name = name
         self._shm = shared_memory.SharedMemory(name=_shm_name(name))
-        # the attaching process must not unlink the segment when it exits (python's resource tracker would)
-        try:
-            from multiprocessing import resource_tracker
-
-            resource_tracker.unregister(self._shm._name, "shared_memory")
-        except Exception:
-            pass
+        # (python 3.12 registers the segment with the resource tracker on attach as well; the workers are spawned by
+        # the process that owns the QueueServer and share its tracker, whose name cache is a set -- the owner's
+        # unlink() is the one removal)
         self._hdr = np.ndarray(8, dtype=np.int64, buffer=self._shm.buf)
         self._cap = int(self._hdr[2])
         self._data = np.ndarray(self._cap, dtype=np.uint8, buffer=self._shm.buf, offset=_HDR)

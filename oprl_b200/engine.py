@@ -152,6 +152,10 @@ class UpdateEngine:
         np.cumsum(np.asarray(ep_lens, np.int64), out=pre[1:])
         L.check(self._lib.oprl_buffer_set_prefix(self._h, pre.ctypes.data, len(ep_lens)))
 
+    def set_nstep(self, n_step: int, gamma: float):
+        """n-step return assembly in the gather (extension; 1 = the reference's 1-step transitions)."""
+        L.check(self._lib.oprl_buffer_set_nstep(self._h, int(n_step), float(gamma)))
+
     def _ensure_batch(self, B):
         if self._batch is None or self._batch_cap < B:
             cap = max(B, 128)

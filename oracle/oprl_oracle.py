@@ -444,3 +444,36 @@ def synthetic_buffer(n_episodes, L, S, A, seed=0):
     rewards = rng.uniform(0, 1, (n_episodes, L, 1)).astype(np.float32)
     dones = np.zeros((n_episodes, L, 1), np.float32)
     return states, actions, rewards, dones
+
+
+# ---------------------------------------------------------------------------- n-step returns (extension)
+def nstep_batch(states, actions, rewards, dones, ep_lens, ep, step, n_step, gamma):
+    """CPU statement of the engine's n-step gather (include/oprl_b200.h oprl_buffer_set_nstep).  The reference
+    assembles 1-step transitions only (episodic_buffer.py:127-133; it stores `gamma`, :18, and never uses it), so
+    there is nothing in the reference to pin this against: it is an EXTENSION defined here, and at n_step = 1 it
+    must return exactly the reference's batch.  fp32 arithmetic in the kernel's order:
+        R = r_t ; g = 1 ; for k = 1..m-1: g = g * gamma ; R = R + g * r_{t+k}        (m = window length)
+        d' = 1 - (1 - d_{t+m-1}) * g ;  next_state = s_{t+m}
+    with m = min(n_step, steps up to and including the first done, steps left in the episode)."""
+    states, actions = np.asarray(states, np.float32), np.asarray(actions, np.float32)
+    rewards, dones = np.asarray(rewards, np.float32), np.asarray(dones, np.float32)
+    B = len(ep)
+    S = states.shape[-1]
+    out_s = states[ep, step].copy()
+    out_a = actions[ep, step].copy()
+    out_r = np.empty((B, 1), np.float32)
+    out_d = np.empty((B, 1), np.float32)
+    out_s2 = np.empty((B, S), np.float32)
+    gam = np.float32(gamma)
+    for i in range(B):
+        e, t0 = int(ep[i]), int(step[i])
+        R, d, g, m = np.float32(rewards[e, t0, 0]), np.float32(dones[e, t0, 0]), np.float32(1.0), 1
+        while m < n_step and d == 0.0 and t0 + m < ep_lens[e]:
+            g = np.float32(g * gam)
+            R = np.float32(R + np.float32(g * rewards[e, t0 + m, 0]))
+            d = np.float32(dones[e, t0 + m, 0])
+            m += 1
+        out_r[i, 0] = R
+        out_d[i, 0] = np.float32(np.float32(1.0) - np.float32(np.float32(np.float32(1.0) - d) * g)) if n_step > 1 else d
+        out_s2[i] = states[e, t0 + m]
+    return out_s, out_a, out_r, out_d, out_s2

@@ -195,3 +195,92 @@ def test_prefetching_learner_step_equals_the_in_order_sequence(name):
             if x is not None:
                 assert torch.equal(x, y), (grp, key)
     assert a.engine.state().log_alpha == b.engine.state().log_alpha
+
+
+def test_rebuilt_programs_release_their_workspaces():
+    """every program rebuild (new batch arena, world-size change) used to leak the previous program's
+    activation workspaces until engine destroy.  Programs now own and free them."""
+    from tests.test_gpu_parity import make_algo
+    from tests.util import load_case
+
+    fx = load_case("ddpg_b8")
+    algo = make_algo(fx)
+    eng = algo.engine
+    g = torch.Generator().manual_seed(0)
+
+    def one_update(B):
+        batch = [torch.randn(B, 24, generator=g), torch.rand(B, 6, generator=g) * 2 - 1, torch.rand(B, 1, generator=g),
+                 torch.zeros(B, 1), torch.randn(B, 24, generator=g)]
+        algo.update(*[x.cuda() for x in batch])
+
+    for B in (64, 64):
+        one_update(B)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for k in range(12):
+        eng.set_world_size(2 if k % 2 == 0 else 1)  # clears the programs: the next update rebuilds them
+        one_update(64)
+    eng.set_world_size(1)
+    one_update(64)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    # one program's workspaces are ~2 MB; twelve leaked rebuilds would be ~25 MB
+    assert free0 - free1 < 8 << 20, f"device memory shrank by {(free0 - free1) / 2**20:.1f} MiB over 12 program rebuilds"
+
+
+def test_nstep_gather_matches_the_oracle_bit_for_bit():
+    """n-step return assembly in the gather kernel (extension, oprl_buffer_set_nstep) against oracle.nstep_batch:
+    windows cut by a done flag and by the episode end, n = 1 identical to the plain gather, and the update consumes
+    the assembled batch (the effective done makes the 1-step target the n-step target)."""
+    from oracle import oprl_oracle as O
+    from oprl_b200.algos.ddpg import DDPG
+    from oprl_b200.buffers.episodic_buffer import EpisodicReplayBuffer
+
+    class NullLogger:
+        log_dir = "/tmp"
+
+        def log_scalar(self, *a, **k):
+            pass
+
+        def log_scalars(self, *a, **k):
+            pass
+
+    S, A, Lmax, E = 24, 6, 40, 25
+    rng = np.random.default_rng(5)
+    algo = DDPG(logger=NullLogger(), state_dim=S, action_dim=A, device="cuda").create()
+    buf = EpisodicReplayBuffer(buffer_size_transitions=E * Lmax, state_dim=S, action_dim=A, max_episode_lenth=Lmax, gamma=0.97).create()
+    st = rng.standard_normal((E, Lmax + 1, S)).astype(np.float32)
+    ac = rng.uniform(-1, 1, (E, Lmax, A)).astype(np.float32)
+    rw = rng.uniform(0, 1, (E, Lmax, 1)).astype(np.float32)
+    dn = (rng.uniform(0, 1, (E, Lmax, 1)) < 0.1).astype(np.float32)
+    buf.states.copy_(torch.from_numpy(st))
+    buf.actions.copy_(torch.from_numpy(ac))
+    buf.rewards.copy_(torch.from_numpy(rw))
+    buf.dones.copy_(torch.from_numpy(dn))
+    lens = [int(x) for x in rng.integers(3, Lmax + 1, size=E - 1)]
+    for e, n in enumerate(lens):
+        buf.ep_lens[e] = n
+    buf._number_transitions = sum(lens)
+    buf._ep_pointer = E - 1
+    buf.episodes_counter = E - 1
+    algo.attach_buffer(buf)
+    for n_step in (1, 3, 5):
+        buf.n_step = n_step
+        np.random.seed(11)
+        ep_step = buf.draw_indices(200)
+        np.random.seed(11)
+        got = [x.cpu().numpy() for x in buf.sample(200)]
+        want = O.nstep_batch(st, ac, rw, dn, buf.ep_lens, ep_step[:, 0], ep_step[:, 1], n_step, buf.gamma)
+        for nm, g_, w_ in zip(("s", "a", "r", "d", "s2"), got, want):
+            assert np.array_equal(g_, w_), (n_step, nm, np.abs(g_ - w_).max())
+        if n_step > 1:
+            assert (got[3] != dn[ep_step[:, 0], ep_step[:, 1]]).any()  # windows longer than one step were assembled
+    algo.update(*buf.sample(64))
+    torch.cuda.synchronize()
+    assert np.isfinite(algo.engine.scalars()["critic_loss"])
+    # the device-resident learner loop draws its indices on the GPU and assembles the same windows
+    algo.engine.set_prefix(buf.ep_lens[:buf.episodes_counter])
+    for _ in range(8):
+        algo.learner_step(64)
+    torch.cuda.synchronize()
+    assert np.isfinite(algo.engine.scalars()["critic_loss"])

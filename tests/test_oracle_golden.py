@@ -57,3 +57,40 @@ def test_buffer_index_math_and_gather_bit_exact():
 def test_oracle_header_declares_test_infrastructure():
     src = open(os.path.join(os.path.dirname(O.__file__), "oprl_oracle.py")).read()
     assert "TEST INFRASTRUCTURE ONLY" in src
+
+
+def test_nstep_oracle_reduces_to_the_reference_batch_and_telescopes():
+    """The n-step extension of the gather (oracle.nstep_batch): n = 1 is the reference's batch bit for bit, and the
+    1-step target on the assembled batch equals the n-step target (constant bootstrap value)."""
+    import numpy as np
+
+    from oracle import oprl_oracle as O
+
+    rng = np.random.default_rng(0)
+    E, Lmax, S, A = 6, 12, 5, 2
+    st = rng.standard_normal((E, Lmax + 1, S)).astype(np.float32)
+    ac = rng.uniform(-1, 1, (E, Lmax, A)).astype(np.float32)
+    rw = rng.uniform(0, 1, (E, Lmax, 1)).astype(np.float32)
+    dn = (rng.uniform(0, 1, (E, Lmax, 1)) < 0.15).astype(np.float32)
+    ep_lens = [12, 7, 12, 3, 9, 12]
+    ep = np.array([0, 1, 1, 3, 4, 5, 2, 0])
+    step = np.array([0, 5, 6, 2, 8, 10, 4, 11])
+    s, a, r, d, s2 = O.nstep_batch(st, ac, rw, dn, ep_lens, ep, step, 1, 0.99)
+    assert np.array_equal(s, st[ep, step]) and np.array_equal(a, ac[ep, step]) and np.array_equal(r, rw[ep, step])
+    assert np.array_equal(d, dn[ep, step]) and np.array_equal(s2, st[ep, step + 1])
+    gamma, q = 0.9, 3.0  # constant bootstrap value: compare against the explicit n-step sum in float64
+    for n in (2, 3, 5):
+        s, a, r, d, s2 = O.nstep_batch(st, ac, rw, dn, ep_lens, ep, step, n, gamma)
+        for i in range(len(ep)):
+            e, t0 = int(ep[i]), int(step[i])
+            m, R, done = 0, 0.0, 0.0
+            while m < n and t0 + m < ep_lens[e]:
+                R += gamma ** m * float(rw[e, t0 + m, 0])
+                done = float(dn[e, t0 + m, 0])
+                m += 1
+                if done:
+                    break
+            want = R + (1.0 - done) * gamma ** m * q
+            got = float(r[i, 0]) + (1.0 - float(d[i, 0])) * gamma * q
+            assert abs(got - want) < 1e-5, (n, i, got, want)
+            assert np.array_equal(s2[i], st[e, t0 + m])
