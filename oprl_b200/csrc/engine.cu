@@ -368,9 +368,21 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
     g.d_segs = static_cast<AdamSeg*>(p);
   }
   g.n_segs = static_cast<int>(segs.size());
+  // block table: (segment, first element) for the element-wise path, (segment, -1 - patch) for the 32 x 32 patch path
+  // (kernels.cuh adam_kernel).  Patches pay off where the scattered tiled stores dominate: groups of large plain
+  // matrices (TQC's five 512-wide critics); the small DDPG / TD3 / SAC nets keep one element per thread, which is
+  // what their latency-bound launch wants.  OPRL_B200_ADAM_PATCH=0 / 1 forces the choice.
+  static const int patch_env = getenv("OPRL_B200_ADAM_PATCH") ? atoi(getenv("OPRL_B200_ADAM_PATCH")) : -1;
+  const bool patches = patch_env >= 0 ? patch_env != 0 : g.floats > 400000;
   std::vector<int2> blocks;
-  for (int si = 0; si < g.n_segs; ++si)
-    for (int off = 0; off < segs[si].n; off += kAdamThreads) blocks.push_back(make_int2(si, off));
+  for (int si = 0; si < g.n_segs; ++si) {
+    const AdamSeg& sg = segs[si];
+    if (patches && sg.w && sg.rows % 32 == 0 && sg.cols % 32 == 0 && sg.split >= sg.cols && sg.off_lo == 0) {
+      for (int pi = 0; pi < (sg.rows / 32) * (sg.cols / 32); ++pi) blocks.push_back(make_int2(si, -1 - pi));
+    } else {
+      for (int off = 0; off < sg.n; off += kAdamThreads) blocks.push_back(make_int2(si, off));
+    }
+  }
   if (!g.d_blocks) {
     void* p;
     CU(cudaMalloc(&p, blocks.size() * sizeof(int2)));
@@ -649,7 +661,8 @@ static void add_critic_head(oprl_engine* e, Builder& b, int stage, int mode, int
   a.r = b.w->r; a.d = b.w->d; a.logp2 = logp2; a.logp = logp;
   const int blocks = (B + kHeadRows - 1) / kHeadRows;
   a.part = e->alloc_floats(static_cast<size_t>(blocks) * (nq * 2 * H + 8));
-  a.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+  a.part2 = e->alloc_floats(static_cast<size_t>((blocks + 15) / 16) * (nq * 2 * H + 8));
+  a.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1 + (blocks + 15) / 16));
   a.alpha_x = alpha_x;
   a.bump_actor = bump_actor ? 1 : 0;
   const int threads = pad32(H);
@@ -1337,14 +1350,17 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     s_act = b.forward(s, ga.nets[0], ga.theta, false, w->Xn, p_an, false, &last);
     last.rm = out_n; last.rm_ld = 2 * A; last.rm_m = Bp; last.rm_n = 2 * A;
     b.stage(s_act - 1).ops.push_back(last);
+    // every critic starts at stage 0 beside the policy: the nets are independent, one grouped launch per layer
+    int s_crit = 0;
     for (int i = 0; i < nc; ++i) {
       GemmOp lq;
-      const int se = b.forward(s, gc.nets[i], gc.theta, false, w->X, p_c[i], true, simt_head ? nullptr : &lq);
-      s = std::max(s, se);
+      const int se = b.forward(0, gc.nets[i], gc.theta, false, w->X, p_c[i], true, simt_head ? nullptr : &lq);
+      s_crit = std::max(s_crit, se);
       if (simt_head) continue;
       lq.rm = z + i * nq; lq.rm_ld = NT; lq.rm_m = Bp; lq.rm_n = nq;
       b.stage(se - 1).ops.push_back(lq);
     }
+    s = std::max(s, s_crit);
   }
   {
     // pi(s) for the actor step: independent of the critic update, so it rides along here
@@ -1357,7 +1373,8 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     h.out = out_n; h.eps = w->noise_raw[0]; h.B = B; h.A = A; h.X = w->Xn; h.a_rm = nullptr; h.logp = logp2;
     hp = h;
     hp.out = out_p; hp.eps = w->noise_raw[1]; hp.X = w->Xp; hp.a_rm = a_rm; hp.logp = logp;
-    const int blocks = (B + kHeadThreads - 1) / kHeadThreads;
+    if (A > kHeadThreads) throw std::runtime_error("action_dim exceeds the policy-head kernels' block");
+    const int blocks = (B + head_fwd_rows(A) - 1) / head_fwd_rows(A);
     b.stage(s_act).add_simt([h, hp, blocks](cudaStream_t sm) {
       launch_k(head_fwd_kernel, dim3(blocks), dim3(kHeadThreads), 0, sm, h);
       launch_k(head_fwd_kernel, dim3(blocks), dim3(kHeadThreads), 0, sm, hp);
@@ -1417,7 +1434,8 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     }
     t.dz_rm = e->alloc_floats(static_cast<size_t>(Bp) * NT);
     t.loss_part = e->alloc_floats(Bp);
-    t.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
+    t.part2 = e->alloc_floats(static_cast<size_t>((B + 15) / 16) * (NT + 1));
+    t.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1 + (B + 15) / 16));
     b.stage(s).add_simt([t, st, B](cudaStream_t sm) { launch_k(tqc_loss_kernel, dim3(B), dim3(kTqcThreads), 0, sm, t, st); });
     b.stage(s).bumps_tick = true;
   }
@@ -1498,12 +1516,11 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     hb.dz = e->alloc_tm(Bp, a_last.Np);
     hb.dzT = e->alloc_tm(pad128(a_last.out), Bp);
     hb.db = ga.grad + a_last.b_off;
-    const int blocks = (B + kHeadThreads - 1) / kHeadThreads;
+    const int blocks = (B + head_bwd_rows(A) - 1) / head_bwd_rows(A);
     hb.partial = e->alloc_floats(static_cast<size_t>(blocks) * 2 * A);
     hb.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1));
-    const size_t smem = static_cast<size_t>(kHeadThreads) * 2 * A * sizeof(float);
-    b.stage(s).add_simt([hb, st, blocks, smem](cudaStream_t sm) {
-      launch_k(head_bwd_kernel, dim3(blocks), dim3(kHeadThreads), smem, sm, hb, static_cast<const DevState*>(st));
+    b.stage(s).add_simt([hb, st, blocks](cudaStream_t sm) {
+      launch_k(head_bwd_kernel, dim3(blocks), dim3(kHeadBwdThreads), 0, sm, hb, static_cast<const DevState*>(st));
     });
     ++s;
   }
@@ -1560,6 +1577,26 @@ static void prepare_stage_tables(oprl_engine* e, Program* p) {
     }
   }
   CU(cudaStreamSynchronize(e->stream));
+  // OPRL_B200_DUMP_STAGES=1: the launch plan of every program, once, on stderr (tools/stage_profile.py pairs it with
+  // the measured cost of each stage)
+  static const bool dump = getenv("OPRL_B200_DUMP_STAGES") && atoi(getenv("OPRL_B200_DUMP_STAGES")) != 0;
+  if (dump) {
+    int k = 0;
+    fprintf(stderr, "oprl plan: B %d flags %d\n", p->B, p->flags);
+    for (auto& sg : p->stages) {
+      ++k;
+      for (size_t li = 0; li < sg.launches.size(); ++li) {
+        fprintf(stderr, "  stage %2d seg %d gemm launch: %d tiles x ksplit %d :", k, sg.segment, sg.launch_tiles[li],
+                sg.launches[li].ksplit);
+        for (size_t i = li * kMaxOps; i < std::min(sg.ops.size(), (li + 1) * kMaxOps); ++i)
+          fprintf(stderr, " [%dx%dx%d]", sg.ops[i].M, sg.ops[i].N, sg.ops[i].K);
+        fprintf(stderr, "\n");
+      }
+      for (size_t i = 0; i < sg.simt.size(); ++i)
+        fprintf(stderr, "  stage %2d seg %d %s: %d launch(es)\n", k, sg.segment, sg.simt_is_chain[i] ? "chain" : "simt",
+                sg.simt_launches[i]);
+    }
+  }
 }
 
 static void launch_gemm_ops(oprl_engine* e, const Stage& sg, cudaStream_t st) {

@@ -547,12 +547,9 @@ __global__ void __launch_bounds__(kAdamThreads)
   }
   const float s_step_size = st->step_size[sg.opt];
   const float s_bc2_sqrt = st->bc2_sqrt[sg.opt];
-  const float w1 = hp.w1;
-  const float w2 = hp.w2;
-  {
-    const int i = bt.y + threadIdx.x;
-    if (i < sg.n) {
-    float p = sg.theta[i];
+  // one element: all-reduce (rank order) -> Adam -> Polyak; returns the new online / target values
+  auto element = [&](int i, float& p, float& tp) {
+    p = sg.theta[i];
     if (mode & 1) {
       float g;
       if (reduce) {
@@ -570,15 +567,15 @@ __global__ void __launch_bounds__(kAdamThreads)
       }
       float m = sg.m[i];
       float v = sg.v[i];
-      m = fmaf(w1, g - m, m);                              // exp_avg.lerp_(grad, 1 - beta1)
-      v = __fadd_rn(__fmul_rn(v, hp.beta2f), __fmul_rn(__fmul_rn(w2, g), g));  // mul_().addcmul_()
+      m = fmaf(hp.w1, g - m, m);                              // exp_avg.lerp_(grad, 1 - beta1)
+      v = __fadd_rn(__fmul_rn(v, hp.beta2f), __fmul_rn(__fmul_rn(hp.w2, g), g));  // mul_().addcmul_()
       const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s_bc2_sqrt), hp.eps);
       p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-s_step_size, m), denom));  // addcdiv_: p + (value*m)/denom
       sg.m[i] = m;
       sg.v[i] = v;
       sg.theta[i] = p;
     }
-    float tp = 0.f;
+    tp = 0.f;
     if (sg.target) {
       tp = sg.target[i];
       if (mode & 2) {
@@ -586,16 +583,59 @@ __global__ void __launch_bounds__(kAdamThreads)
         sg.target[i] = tp;
       }
     }
-    if (sg.w) {
-      const int r = i / sg.cols;
-      const int j = i - r * sg.cols;
-      const int c = j < sg.split ? j + sg.off_lo : j - sg.split + sg.off_hi;
-      if (mode & 4) {
-        sg.w[ct_index(sg.w_rows, r, c)] = p;
-        if (sg.wt) sg.wt[ct_index(sg.wt_rows, c, r)] = p;
+  };
+  if (bt.y >= 0) {
+    const int i = bt.y + threadIdx.x;
+    if (i < sg.n) {
+      float p, tp;
+      element(i, p, tp);
+      if (sg.w) {
+        const int r = i / sg.cols;
+        const int j = i - r * sg.cols;
+        const int c = j < sg.split ? j + sg.off_lo : j - sg.split + sg.off_hi;
+        if (mode & 4) {
+          sg.w[ct_index(sg.w_rows, r, c)] = p;
+          if (sg.wt) sg.wt[ct_index(sg.wt_rows, c, r)] = p;
+        }
+        if (sg.tw && (mode & 8)) sg.tw[ct_index(sg.w_rows, r, c)] = tp;
       }
-      if (sg.tw && (mode & 8)) sg.tw[ct_index(sg.w_rows, r, c)] = tp;
     }
+  } else {
+    // Patch mode (large plain matrices, rows % 32 == cols % 32 == 0, identity column map): this block owns the
+    // 32 x 32 patch -1 - bt.y of the row-major tensor -- 128-byte row segments on the read side, and on the write
+    // side exactly one contiguous 4 KB run of each tiled copy (W: 4 row-blocks of one column block; W^T: 4 row-blocks
+    // of the transposed one), stored as float4 through a shared-memory transpose.  The element-wise path above
+    // scatters 4-byte stores over 16-byte core rows: 8x the L2 write sectors for W^T (TQC: 46 us of Adam).
+    __shared__ float pp[32][33], pt[32][33];
+    const int pc_n = sg.cols >> 5;
+    const int patch = -1 - bt.y;
+    const int r0 = (patch / pc_n) << 5, c0 = (patch % pc_n) << 5;
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int rr = wrp + 8 * q;
+      float p, tp;
+      element((r0 + rr) * sg.cols + c0 + lane, p, tp);
+      pp[rr][lane] = p;
+      pt[rr][lane] = tp;
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    const int hi = t >> 6, mid = (t >> 3) & 7, lo = t & 7;
+    if (mode & 4) {
+      float4* wdst = reinterpret_cast<float4*>(sg.w + ct_index(sg.w_rows, r0, c0));
+      wdst[t] = make_float4(pp[hi * 8 + lo][mid * 4], pp[hi * 8 + lo][mid * 4 + 1], pp[hi * 8 + lo][mid * 4 + 2],
+                            pp[hi * 8 + lo][mid * 4 + 3]);
+      if (sg.wt) {
+        float4* tdst = reinterpret_cast<float4*>(sg.wt + ct_index(sg.wt_rows, c0, r0));
+        tdst[t] = make_float4(pp[mid * 4][hi * 8 + lo], pp[mid * 4 + 1][hi * 8 + lo], pp[mid * 4 + 2][hi * 8 + lo],
+                              pp[mid * 4 + 3][hi * 8 + lo]);
+      }
+    }
+    if (sg.tw && (mode & 8)) {
+      float4* wdst = reinterpret_cast<float4*>(sg.tw + ct_index(sg.w_rows, r0, c0));
+      wdst[t] = make_float4(pt[hi * 8 + lo][mid * 4], pt[hi * 8 + lo][mid * 4 + 1], pt[hi * 8 + lo][mid * 4 + 2],
+                            pt[hi * 8 + lo][mid * 4 + 3]);
     }
   }
   if (lt.part && blockIdx.x == 0) {

@@ -29,14 +29,20 @@ struct HeadFwdArgs {
   float* a_rm;   // [Bp x A] (nullable)
   float* logp;   // [Bp]
 };
+// One thread per (row, action): kHeadThreads / A rows per block (a thread per ROW left a batch of 1024 on 8 SMs, each
+// thread walking its A actions one after the other); the row's log-probability is then added up in action order by
+// the thread of action 0.
+__host__ __device__ __forceinline__ int head_fwd_rows(int A) { return kHeadThreads / A; }
 __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(HeadFwdArgs g) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
-  const int m = blockIdx.x * kHeadThreads + threadIdx.x;
-  if (m >= g.B) return;
-  const float* o = g.out + static_cast<size_t>(m) * 2 * g.A;
-  float lp = 0.f;
-  for (int j = 0; j < g.A; ++j) {
+  __shared__ float term[kHeadThreads];
+  const int R = head_fwd_rows(g.A);
+  const int rl = threadIdx.x / g.A, j = threadIdx.x - rl * g.A;
+  const int m = blockIdx.x * R + rl;
+  const bool live = rl < R && m < g.B;
+  if (live) {
+    const float* o = g.out + static_cast<size_t>(m) * 2 * g.A;
     const float mu = o[j];
     const float ls = fminf(fmaxf(o[g.A + j], kLogStdMin), kLogStdMax);
     const float sigma = expf(ls);
@@ -47,11 +53,16 @@ __global__ void __launch_bounds__(kHeadThreads) head_fwd_kernel(HeadFwdArgs g) {
     const float diff = __fsub_rn(u, mu);
     const float nlp = __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(diff, diff), __fmul_rn(2.f, var)), logf(sigma)),
                                 0.9189385332046727f);
-    lp += __fsub_rn(nlp, log_det);
+    term[threadIdx.x] = __fsub_rn(nlp, log_det);
     store_tiled(g.X, m, j, a);
     if (g.a_rm) g.a_rm[static_cast<size_t>(m) * g.A + j] = a;
   }
-  g.logp[m] = lp;
+  __syncthreads();
+  if (live && j == 0) {
+    float lp = 0.f;
+    for (int k = 0; k < g.A; ++k) lp = __fadd_rn(lp, term[threadIdx.x + k]);
+    g.logp[m] = lp;
+  }
 }
 
 // ------------------------------------------------------------ tanh-Gaussian head, backward
@@ -74,18 +85,24 @@ struct HeadBwdArgs {
   float* partial;   // [gridDim.x x 2A]
   unsigned int* counter;
 };
-__global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadBwdArgs g, const DevState* st) {
+// One thread per (row, action), kHeadBwdThreads / A rows per block; deterministic bias sums: rows of a block in row
+// order, then the last block to arrive adds the blocks (G = kHeadBwdThreads / 2A lanes of blocks in parallel, each in
+// block order, then the G partial sums in order).
+constexpr int kHeadBwdThreads = 256;
+__host__ __device__ __forceinline__ int head_bwd_rows(int A) { return kHeadBwdThreads / A; }
+__global__ void __launch_bounds__(kHeadBwdThreads) head_bwd_kernel(HeadBwdArgs g, const DevState* st) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
-  extern __shared__ float sh[];  // [kHeadThreads x 2A]
-  const int m = blockIdx.x * kHeadThreads + threadIdx.x;
+  __shared__ float sh[2 * kHeadBwdThreads];  // [R x 2A] (R * A <= 256), then [G x 2A]
   const int W = 2 * g.A;
+  const int R = head_bwd_rows(g.A);
+  const int rl = threadIdx.x / g.A, j = threadIdx.x - rl * g.A;
+  const int m = blockIdx.x * R + rl;
   const float c = st->alpha * g.inv_count;
-  float* mine = sh + threadIdx.x * W;
-  for (int j = 0; j < W; ++j) mine[j] = 0.f;
-  if (m < g.B) {
-    const float* o = g.out + static_cast<size_t>(m) * W;
-    for (int j = 0; j < g.A; ++j) {
+  if (rl < R) {
+    float dmu = 0.f, dl = 0.f;
+    if (m < g.B) {
+      const float* o = g.out + static_cast<size_t>(m) * W;
       const float l = o[g.A + j];
       const float ls = fminf(fmaxf(l, kLogStdMin), kLogStdMax);
       const float sigma = expf(ls);
@@ -94,38 +111,51 @@ __global__ void __launch_bounds__(kHeadThreads) head_bwd_kernel(HeadBwdArgs g, c
       float da = 0.f;
       for (int k = 0; k < g.n_da; ++k) da += g.da[k][static_cast<size_t>(m) * g.A + j];
       const float du = da * (1.f - a * a);  // through tanh
-      const float dmu = c * (2.f * a) + du;
+      dmu = c * (2.f * a) + du;
       const float dsigma = c * (2.f * a * e - 1.f / sigma) + du * e;
-      const float dl = (l >= kLogStdMin && l <= kLogStdMax) ? dsigma * sigma : 0.f;
+      dl = (l >= kLogStdMin && l <= kLogStdMax) ? dsigma * sigma : 0.f;
       store_tiled(g.dz, m, j, dmu);
       store_tiled(g.dz, m, g.A + j, dl);
       store_tiled(g.dzT, j, m, dmu);
       store_tiled(g.dzT, g.A + j, m, dl);
-      mine[j] = dmu;
-      mine[g.A + j] = dl;
     }
+    sh[rl * W + j] = dmu;
+    sh[rl * W + g.A + j] = dl;
   }
   __syncthreads();
-  // deterministic column sums: per block, then the last block over blocks
-  for (int j = threadIdx.x; j < W; j += kHeadThreads) {
+  if (static_cast<int>(threadIdx.x) < W) {
     float s = 0.f;
-    for (int t = 0; t < kHeadThreads; ++t) s += sh[t * W + j];
-    g.partial[blockIdx.x * W + j] = s;
+    for (int t = 0; t < R; ++t) s += sh[t * W + threadIdx.x];
+    g.partial[blockIdx.x * W + threadIdx.x] = s;
   }
-  __threadfence();
   __syncthreads();
   __shared__ unsigned int ticket;
-  if (threadIdx.x == 0) ticket = atomicAdd(g.counter, 1u);
+  if (threadIdx.x == 0) ticket = ptx::atom_add_acq_rel_gpu(g.counter, 1u);
   __syncthreads();
-  if (ticket == gridDim.x - 1) {
-    __threadfence();
-    for (int j = threadIdx.x; j < W; j += kHeadThreads) {
-      float s = 0.f;
-      for (unsigned int b = 0; b < gridDim.x; ++b) s += __ldcg(g.partial + b * W + j);
-      g.db[j] = s;
+  if (ticket != gridDim.x - 1) return;
+  const int G = kHeadBwdThreads / W;
+  const int grp = threadIdx.x / W, col = threadIdx.x - grp * W;
+  if (grp < G) {
+    float s = 0.f;
+    for (unsigned int b0 = grp; b0 < gridDim.x; b0 += 16u * G) {
+      float tv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const unsigned int b = b0 + static_cast<unsigned int>(k * G);
+        tv[k] = b < gridDim.x ? __ldcg(g.partial + b * W + col) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += tv[k];
     }
-    if (threadIdx.x == 0) *g.counter = 0u;
+    sh[grp * W + col] = s;
   }
+  __syncthreads();
+  if (static_cast<int>(threadIdx.x) < W) {
+    float s = 0.f;
+    for (int gi = 0; gi < G; ++gi) s += sh[gi * W + threadIdx.x];
+    g.db[threadIdx.x] = s;
+  }
+  if (threadIdx.x == 0) *g.counter = 0u;
 }
 
 // ---------------------------------------------------------------------- actor-loss seeds
@@ -239,7 +269,8 @@ struct TqcArgs {
   float* db[kMaxNets];  // last-layer bias gradient slots [nq]
   float* dz_rm;         // [Bp x NT] scratch (row-major gradient, for the bias sums)
   float* loss_part;     // [B]
-  unsigned int* counter;
+  float* part2;         // [ceil(B / 16)][NT + 1] group partials of the two-level reduction
+  unsigned int* counter;  // [1 + ceil(B / 16)]
 };
 constexpr int kTqcThreads = 128;  // NT <= 128
 __global__ void __launch_bounds__(kTqcThreads) tqc_loss_kernel(TqcArgs a, DevState* st) {
@@ -295,27 +326,64 @@ __global__ void __launch_bounds__(kTqcThreads) tqc_loss_kernel(TqcArgs a, DevSta
   }
   const float bl = block_sum<kTqcThreads>(loss, red);
   if (tid == 0) a.loss_part[m] = bl;
-  // last block: bias gradients (column sums over rows) + loss, in a fixed order
-  __threadfence();
+  // bias gradients (column sums of dz over the rows) + loss, in a fixed order and two levels: the last block of
+  // every 16 consecutive rows adds that group (one batch of 16 loads in flight), the last group to finish adds the
+  // groups -- a single last block walking all B rows was 15 us of this kernel.
   __syncthreads();
   __shared__ unsigned int ticket;
-  if (tid == 0) ticket = atomicAdd(a.counter, 1u);
+  const unsigned int grp = blockIdx.x >> 4, ngrp = (gridDim.x + 15u) >> 4;
+  const unsigned int gsize = min(16u, gridDim.x - grp * 16u);
+  if (tid == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter + 1 + grp, 1u);
   __syncthreads();
-  if (ticket == gridDim.x - 1) {
-    __threadfence();
+  if (ticket != gsize - 1) return;
+  const int PW = NT + 1;  // group partial: NT column sums + the loss
+  {
+    float tv[16];
     if (tid < NT) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k)
+        tv[k] = static_cast<unsigned int>(k) < gsize ? __ldcg(a.dz_rm + static_cast<size_t>(grp * 16 + k) * NT + tid) : 0.f;
       float s = 0.f;
-      for (int r = 0; r < a.B; ++r) s += __ldcg(a.dz_rm + static_cast<size_t>(r) * NT + tid);
-      a.db[tid / a.nq][tid % a.nq] = s;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += tv[k];
+      a.part2[grp * PW + tid] = s;
     }
-    float l = 0.f;
-    for (int r = tid; r < a.B; r += kTqcThreads) l += __ldcg(a.loss_part + r);
-    const float tot = block_sum<kTqcThreads>(l, red);
     if (tid == 0) {
-      st->scalars[SC_CRITIC_LOSS] = tot * a.inv_total;
-      bump_counters(st, a.bump_actor);
-      *a.counter = 0u;
+      float lv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) lv[k] = static_cast<unsigned int>(k) < gsize ? __ldcg(a.loss_part + grp * 16 + k) : 0.f;
+      float l = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) l += lv[k];
+      a.part2[grp * PW + NT] = l;
+      a.counter[1 + grp] = 0u;
     }
+  }
+  __syncthreads();
+  if (tid == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
+  __syncthreads();
+  if (ticket != ngrp - 1) return;
+  if (tid <= NT && tid < kTqcThreads) {
+    // thread NT (or thread 0 when NT == 128, below) adds the losses
+    float s = 0.f;
+    for (unsigned int g0 = 0; g0 < ngrp; g0 += 16) {
+      float tv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tv[k] = g0 + k < ngrp ? __ldcg(a.part2 + (g0 + k) * PW + tid) : 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) s += tv[k];
+    }
+    if (tid < NT) a.db[tid / a.nq][tid % a.nq] = s;
+    else st->scalars[SC_CRITIC_LOSS] = s * a.inv_total;
+  }
+  if (tid == 0) {
+    if (NT == kTqcThreads) {
+      float s = 0.f;
+      for (unsigned int g0 = 0; g0 < ngrp; ++g0) s += __ldcg(a.part2 + g0 * PW + NT);
+      st->scalars[SC_CRITIC_LOSS] = s * a.inv_total;
+    }
+    bump_counters(st, a.bump_actor);
+    *a.counter = 0u;
   }
 }
 
@@ -356,8 +424,9 @@ struct CriticHeadArgs {
   float* gw3[2];
   float* gb3[2];
   float* gb2[2];
-  float* part;  // [gridDim.x][nq * 2 * H + 8]
-  unsigned int* counter;
+  float* part;   // [gridDim.x][nq * 2 * H + 8]
+  float* part2;  // [ceil(gridDim.x / 16)][same]: group partials of the two-level reduction (more than 32 blocks)
+  unsigned int* counter;  // [1 + ceil(gridDim.x / 16)]
   float* alpha_x;  // mode 1, SAC: share of mean(logp) behind the actor gradient arena (nullable)
   int bump_actor;
 };
@@ -509,17 +578,48 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
   // in every thread on both sides of a relaxed atomic.
   __syncthreads();
   __shared__ unsigned int ticket;
-  if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
-  __syncthreads();
-  if (ticket != gridDim.x - 1) return;
+  const float* part = a.part;  // what the final reduction adds up: `nparts` rows of W floats
+  unsigned int nparts = gridDim.x;
+  if (gridDim.x > 32) {
+    // batch > 256 rows: two levels.  The last block of every 16 consecutive blocks adds that group's partials
+    // (W columns over the threads, 16 loads in flight each), the last GROUP to finish adds the groups below: one
+    // block pulling all of [gridDim.x][W] through its SM (528 KB at batch 1024) was 15 us of this kernel.
+    const unsigned int grp = blockIdx.x >> 4, ngrp = (gridDim.x + 15u) >> 4;
+    const unsigned int gsize = min(16u, gridDim.x - grp * 16u);
+    if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter + 1 + grp, 1u);
+    __syncthreads();
+    if (ticket != gsize - 1) return;
+    const float* gp = a.part + static_cast<size_t>(grp) * 16 * W;
+    float* dst = a.part2 + static_cast<size_t>(grp) * W;
+    for (int c = n; c < W; c += blockDim.x) {
+      float tv[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) tv[k] = static_cast<unsigned int>(k) < gsize ? __ldcg(gp + static_cast<size_t>(k) * W + c) : 0.f;
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) sum += tv[k];
+      dst[c] = sum;
+    }
+    if (n == 0) a.counter[1 + grp] = 0u;
+    __syncthreads();
+    if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
+    __syncthreads();
+    if (ticket != ngrp - 1) return;
+    part = a.part2;
+    nparts = ngrp;
+  } else {
+    if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;
+  }
   // every load of the reduction is issued before the first add: the per-block scalar tails (warp 0:
   // lane = block, 7 values each) and, in the critic step, the head-weight / bias-gradient partials
   // of this thread's hidden unit (batches of sixteen blocks, two critics)
   float tl[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  const unsigned int nb32 = (gridDim.x + 31) / 32;
+  const unsigned int nb32 = (nparts + 31) / 32;
   if (warp == 0 && nb32 == 1) {
-    if (static_cast<unsigned int>(lane) < gridDim.x) {
-      const float* tp = a.part + static_cast<size_t>(lane) * W + a.nq * 2 * a.H;
+    if (static_cast<unsigned int>(lane) < nparts) {
+      const float* tp = part + static_cast<size_t>(lane) * W + a.nq * 2 * a.H;
 #pragma unroll
       for (int k = 0; k < 7; ++k) tl[k] = __ldcg(tp + k);
     }
@@ -528,12 +628,12 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
     for (int i = 0; i < a.nq; ++i) {
       // loads batched sixteen blocks at a time (independent L2 round trips), adds in block order
       float gw = 0.f, gb = 0.f;
-      for (unsigned int b0 = 0; b0 < gridDim.x; b0 += 16) {
+      for (unsigned int b0 = 0; b0 < nparts; b0 += 16) {
         float tw[16], tb[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const bool ok = b0 + k < gridDim.x;
-          const float* p = a.part + static_cast<size_t>(ok ? b0 + k : 0) * W + i * 2 * a.H;
+          const bool ok = b0 + k < nparts;
+          const float* p = part + static_cast<size_t>(ok ? b0 + k : 0) * W + i * 2 * a.H;
           tw[k] = ok ? __ldcg(p + n) : 0.f;
           tb[k] = ok ? __ldcg(p + a.H + n) : 0.f;
         }
@@ -562,11 +662,11 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
   } else {
     // more blocks (batch > 256): gathered by (block, k) threads in parallel, summed in block order
     __syncthreads();
-    for (unsigned int idx = n; idx < gridDim.x * 8; idx += blockDim.x)
-      sh[idx] = __ldcg(a.part + static_cast<size_t>(idx >> 3) * W + a.nq * 2 * a.H + (idx & 7));
+    for (unsigned int idx = n; idx < nparts * 8; idx += blockDim.x)
+      sh[idx] = __ldcg(part + static_cast<size_t>(idx >> 3) * W + a.nq * 2 * a.H + (idx & 7));
     __syncthreads();
     if (n == 0)
-      for (unsigned int b = 0; b < gridDim.x; ++b)
+      for (unsigned int b = 0; b < nparts; ++b)
         for (int k = 0; k < 7; ++k) t[k] += sh[b * 8 + k];
   }
   if (n == 0) {
