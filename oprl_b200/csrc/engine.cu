@@ -107,6 +107,7 @@ struct Group {  // actor (1 net) or critic (n_critics nets) -- one flat arena, o
   bool want_target = false;
   AdamSeg* d_segs = nullptr;
   int2* d_blocks = nullptr;  // block -> (segment, first element)
+  int adam_smem = 0;          // dynamic shared memory of this group's Adam launches (patch mode only)
   int n_segs = 0;
   int n_blocks = 0;
   size_t max_seg = 0;
@@ -374,11 +375,13 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
   // what their latency-bound launch wants.  OPRL_B200_ADAM_PATCH=0 / 1 forces the choice.
   static const int patch_env = getenv("OPRL_B200_ADAM_PATCH") ? atoi(getenv("OPRL_B200_ADAM_PATCH")) : -1;
   const bool patches = patch_env >= 0 ? patch_env != 0 : g.floats > 400000;
+  g.adam_smem = 0;
   std::vector<int2> blocks;
   for (int si = 0; si < g.n_segs; ++si) {
     const AdamSeg& sg = segs[si];
     if (patches && sg.w && sg.rows % 32 == 0 && sg.cols % 32 == 0 && sg.split >= sg.cols && sg.off_lo == 0) {
       for (int pi = 0; pi < (sg.rows / 32) * (sg.cols / 32); ++pi) blocks.push_back(make_int2(si, -1 - pi));
+      g.adam_smem = kAdamPatchSmem;
     } else {
       for (int off = 0; off < sg.n; off += kAdamThreads) blocks.push_back(make_int2(si, off));
     }
@@ -432,9 +435,14 @@ static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, boo
   // the gradient loads cross NVLink)
   dim3 grid(g.n_blocks);
   const int group = (&g == &e->grp[OPRL_NET_ACTOR]) ? 0 : 1;
-  launch_k(adam_kernel, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs),
-           static_cast<const int2*>(g.d_blocks), make_hyper(e->cfg),
-           static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt);
+  if (g.adam_smem)
+    launch_k(adam_kernel<true>, grid, dim3(kAdamThreads), static_cast<size_t>(g.adam_smem), st,
+             static_cast<const AdamSeg*>(g.d_segs), static_cast<const int2*>(g.d_blocks), make_hyper(e->cfg),
+             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt);
+  else
+    launch_k(adam_kernel<false>, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs),
+             static_cast<const int2*>(g.d_blocks), make_hyper(e->cfg),
+             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt);
 }
 
 // --------------------------------------------------------------- program builder
@@ -1562,7 +1570,8 @@ static void prepare_stage_tables(oprl_engine* e, Program* p) {
       int tiles = 0;
       L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, sg.ops.size() - i0));
       for (int i = 0; i < L.n_ops; ++i) {
-        gemm_finalize(sg.ops[i0 + i]);
+        static const int max_big = getenv("OPRL_B200_GEMM_MAXBIG") ? atoi(getenv("OPRL_B200_GEMM_MAXBIG")) : 7;
+        gemm_finalize(sg.ops[i0 + i], max_big);
         tiles += gemm_tiles(sg.ops[i0 + i]);
         L.tile_end[i] = tiles;
       }

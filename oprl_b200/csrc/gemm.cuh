@@ -162,9 +162,9 @@ __host__ __device__ __forceinline__ int gemm_tiles(const GemmOp& o) {
   return (o.M / kBM) * (o.N / kBN);
 }
 // host: derived fields (TMEM accumulator plan) -- call once per op before launching
-inline void gemm_finalize(GemmOp& o) {
+inline void gemm_finalize(GemmOp& o, int max_big = 7) {
   const int nchunks = o.K / kBK;
-  o.group = (nchunks + 6) / 7 > 2 ? (nchunks + 6) / 7 : 2;
+  o.group = (nchunks + max_big - 1) / max_big > 2 ? (nchunks + max_big - 1) / max_big : 2;
   o.n_big = (nchunks + o.group - 1) / o.group;
 }
 // host: CTAs per tile for one launch -- the largest of {4, 2, 1} that keeps the whole launch in one

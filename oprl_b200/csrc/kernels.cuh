@@ -512,6 +512,7 @@ struct AdamHyper {  // python doubles of torch.optim.Adam, rounded to fp32 where
   float tau, one_minus_tau;  // (float)tau, (float)(1 - tau)
 };
 constexpr int kAdamThreads = 256;
+constexpr int kAdamPatchSmem = 2 * 32 * 33 * 4;  // dynamic shared memory of a launch with 32 x 32 patches
 // Optional duty of block 0 of an Adam launch: the actor loss of the DDPG / TD3 actor step,
 //   out = scale * sum_{m < B} (b3 + sum_{p < nparts} part[p * ld + m])        (= -mean q(s, pi(s)))
 // from the per-tile partial head dot products the critic forward GEMM left behind (GemmOp::tail_out).
@@ -525,6 +526,10 @@ struct LossTail {
   float scale;
 };
 // mode: bit0 = Adam step, bit1 = Polyak, bit2 = (re)tile online weights, bit3 = tile targets
+// kPatch: compiled with the 32 x 32 patch path (groups of large matrices, TQC).  The plain instantiation is what the
+// latency-bound DDPG / TD3 / SAC launches run: the patch path's extra registers (48 -> 64) alone cost 1-2 us per
+// update there (measured A/B on one box), so it is kept out of their kernel.
+template <bool kPatch>
 __global__ void __launch_bounds__(kAdamThreads)
     adam_kernel(const AdamSeg* segs, const int2* blocks, AdamHyper hp, const DevState* st, int mode,
                 const __grid_constant__ CommArgs cm, const LossTail lt) {
@@ -584,7 +589,7 @@ __global__ void __launch_bounds__(kAdamThreads)
       }
     }
   };
-  if (bt.y >= 0) {
+  if (!kPatch || bt.y >= 0) {
     const int i = bt.y + threadIdx.x;
     if (i < sg.n) {
       float p, tp;
@@ -606,16 +611,59 @@ __global__ void __launch_bounds__(kAdamThreads)
     // side exactly one contiguous 4 KB run of each tiled copy (W: 4 row-blocks of one column block; W^T: 4 row-blocks
     // of the transposed one), stored as float4 through a shared-memory transpose.  The element-wise path above
     // scatters 4-byte stores over 16-byte core rows: 8x the L2 write sectors for W^T (TQC: 46 us of Adam).
-    __shared__ float pp[32][33], pt[32][33];
+    // (dynamic shared memory, requested only by launches that have patches: a static 8 KB in every Adam block kept the
+    // next GEMM's 214 KB CTAs from becoming resident under programmatic dependent launch -- +1..2 us per update)
+    extern __shared__ float adam_patch_smem[];
+    float (*pp)[33] = reinterpret_cast<float (*)[33]>(adam_patch_smem);
+    float (*pt)[33] = reinterpret_cast<float (*)[33]>(adam_patch_smem + 32 * 33);
     const int pc_n = sg.cols >> 5;
     const int patch = -1 - bt.y;
     const int r0 = (patch / pc_n) << 5, c0 = (patch % pc_n) << 5;
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    // all 4 x 5 loads of this thread are issued before the first store (the element-wise lambda interleaves loads
+    // and stores through pointers the compiler must assume to alias: four serial DRAM round trips per block)
+    float ep[4], eg[4], em[4], ev[4], et[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = (r0 + wrp + 8 * q) * sg.cols + c0 + lane;
+      ep[q] = sg.theta[i];
+      et[q] = sg.target ? sg.target[i] : 0.f;
+      if (mode & 1) {
+        em[q] = sg.m[i];
+        ev[q] = sg.v[i];
+        if (reduce) {
+          float gr[kMaxRanks];
+#pragma unroll
+          for (int r = 0; r < kMaxRanks; ++r) gr[r] = r < cm.world ? cm.peer_grad[r][sg.goff + i] : 0.f;
+          float g = 0.f;
+#pragma unroll
+          for (int r = 0; r < kMaxRanks; ++r)
+            if (r < cm.world) g += gr[r];
+          eg[q] = g;
+        } else {
+          eg[q] = sg.grad[i];
+        }
+      }
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int rr = wrp + 8 * q;
-      float p, tp;
-      element((r0 + rr) * sg.cols + c0 + lane, p, tp);
+      const int i = (r0 + rr) * sg.cols + c0 + lane;
+      float p = ep[q], tp = et[q];
+      if (mode & 1) {
+        const float g = eg[q];
+        const float m = fmaf(hp.w1, g - em[q], em[q]);
+        const float v = __fadd_rn(__fmul_rn(ev[q], hp.beta2f), __fmul_rn(__fmul_rn(hp.w2, g), g));
+        const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s_bc2_sqrt), hp.eps);
+        p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-s_step_size, m), denom));
+        sg.m[i] = m;
+        sg.v[i] = v;
+        sg.theta[i] = p;
+      }
+      if (sg.target && (mode & 2)) {
+        tp = __fadd_rn(__fmul_rn(hp.tau, p), __fmul_rn(hp.one_minus_tau, tp));
+        sg.target[i] = tp;
+      }
       pp[rr][lane] = p;
       pt[rr][lane] = tp;
     }

@@ -187,13 +187,28 @@ __global__ void __launch_bounds__(kTdThreads) actor_seed_kernel(ActorSeedArgs a,
       const float g1 = (q1 < q2) ? 1.f : (q1 == q2 ? 0.5f : 0.f);
       store_tiled(a.D[0], m, 0, -a.inv_count * g1);
       store_tiled(a.D[1], m, 0, -a.inv_count * (1.f - g1));
-    } else {
-      float s = 0.f;
-      for (int k = 0; k < a.nq; ++k) s += q[k];
-      qs += s / static_cast<float>(a.nq);
     }
     ls += a.logp[m];
     lts += a.logp[m] + a.target_entropy;
+  }
+  if (a.tqc) {
+    // mean over the n_nets * n_quantiles atoms of a row: one warp per row, coalesced, four rows in flight (a thread
+    // per row walked 125 strided loads one after the other: 13 us for a logging scalar on the critical path)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float inv_nq = 1.f / static_cast<float>(a.nq);
+    for (int m0 = warp * 4; m0 < a.B; m0 += (kTdThreads / 32) * 4) {
+      float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (m0 + u < a.B)
+          for (int k = lane; k < a.nq; k += 32) s[u] += a.q[static_cast<size_t>(m0 + u) * a.nq + k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
+        if (lane == 0 && m0 + u < a.B) qs += s[u] * inv_nq;
+      }
+    }
   }
   const float qsum = block_sum<kTdThreads>(qs, sh);
   const float lsum = block_sum<kTdThreads>(ls, sh);
@@ -309,16 +324,26 @@ __global__ void __launch_bounds__(kTqcThreads) tqc_loss_kernel(TqcArgs a, DevSta
     const int net = tid / a.nq, j = tid - net * a.nq;
     const float zq = a.z[static_cast<size_t>(m) * NT + tid];
     const float tau = static_cast<float>(j) / static_cast<float>(a.nq) + 0.5f / static_cast<float>(a.nq);
-    float grad = 0.f;
-    for (int k = 0; k < a.keep; ++k) {
+    // four independent accumulator pairs (k mod 4), added in a fixed order: one warp per scheduler walking `keep`
+    // dependent adds was the longest phase of this kernel
+    float lacc[4] = {0.f, 0.f, 0.f, 0.f}, gacc[4] = {0.f, 0.f, 0.f, 0.f};
+    auto term = [&](int k, float& l, float& g) {
       const float delta = srt[k] - zq;
       const float ad = fabsf(delta);
       const float hub = ad > 1.f ? ad - 0.5f : delta * delta * 0.5f;
       const float w = fabsf(tau - (delta < 0.f ? 1.f : 0.f));
-      loss += w * hub;
+      l += w * hub;
       // d/dz: delta = t - z  =>  -(w * huber'(delta))
-      grad -= w * (ad > 1.f ? (delta > 0.f ? 1.f : -1.f) : delta);
+      g -= w * (ad > 1.f ? (delta > 0.f ? 1.f : -1.f) : delta);
+    };
+    int k = 0;
+    for (; k + 4 <= a.keep; k += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) term(k + u, lacc[u], gacc[u]);
     }
+    for (int u = 0; k < a.keep; ++k, ++u) term(k, lacc[u], gacc[u]);
+    loss = (lacc[0] + lacc[1]) + (lacc[2] + lacc[3]);
+    float grad = (gacc[0] + gacc[1]) + (gacc[2] + gacc[3]);
     grad *= a.inv_total;
     store_tiled(a.dZ[net], m, j, grad);
     store_tiled(a.dZT[net], j, m, grad);
