@@ -1561,21 +1561,32 @@ namespace oprl {
 static void prepare_stage_tables(oprl_engine* e, Program* p) {
   // split-K over clusters when the launch leaves most SMs idle (OPRL_B200_KSPLIT=1 turns it off, 2 / 4 cap it)
   static const int ks_cap = getenv("OPRL_B200_KSPLIT") ? atoi(getenv("OPRL_B200_KSPLIT")) : 4;
+  static const int max_big = getenv("OPRL_B200_GEMM_MAXBIG") ? atoi(getenv("OPRL_B200_GEMM_MAXBIG")) : 7;
+  static const bool wide_on = !(getenv("OPRL_B200_GEMM_WIDE") && atoi(getenv("OPRL_B200_GEMM_WIDE")) == 0);
   for (auto& sg : p->stages) {
     sg.launches.clear();
     sg.launch_tiles.clear();
     for (size_t i0 = 0; i0 < sg.ops.size(); i0 += kMaxOps) {
       GemmLaunch L;
       memset(&L, 0, sizeof(L));
-      int tiles = 0;
       L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, sg.ops.size() - i0));
+      // 128 x 64 tiles where the narrow tiling would not fit one wave of SMs and every op of the launch can take them
+      // (gemm.cuh gemm_wide_ok); OPRL_B200_GEMM_WIDE=0 keeps 128 x 32 everywhere
+      int narrow_tiles = 0;
+      bool wide = wide_on && e->cfg.gemm_mode != OPRL_GEMM_SIMT;
       for (int i = 0; i < L.n_ops; ++i) {
-        static const int max_big = getenv("OPRL_B200_GEMM_MAXBIG") ? atoi(getenv("OPRL_B200_GEMM_MAXBIG")) : 7;
-        gemm_finalize(sg.ops[i0 + i], max_big);
-        tiles += gemm_tiles(sg.ops[i0 + i]);
+        narrow_tiles += gemm_tiles(sg.ops[i0 + i]);
+        wide = wide && gemm_wide_ok(sg.ops[i0 + i]);
+      }
+      wide = wide && narrow_tiles > e->n_sm;
+      L.nsub = wide ? 2 : 1;
+      int tiles = 0;
+      for (int i = 0; i < L.n_ops; ++i) {
+        gemm_finalize(sg.ops[i0 + i], wide ? kWideMaxBig : max_big);
+        tiles += gemm_tiles(sg.ops[i0 + i], L.nsub);
         L.tile_end[i] = tiles;
       }
-      int ks = gemm_choose_ksplit(&sg.ops[i0], L.n_ops, e->n_sm);
+      int ks = wide ? 1 : gemm_choose_ksplit(&sg.ops[i0], L.n_ops, e->n_sm);
       while (ks > 1 && ks > ks_cap) ks >>= 1;
       L.ksplit = ks;
       GemmOp* d = reinterpret_cast<GemmOp*>(e->alloc_floats((sizeof(GemmOp) * L.n_ops + 3) / 4));
@@ -1595,8 +1606,8 @@ static void prepare_stage_tables(oprl_engine* e, Program* p) {
     for (auto& sg : p->stages) {
       ++k;
       for (size_t li = 0; li < sg.launches.size(); ++li) {
-        fprintf(stderr, "  stage %2d seg %d gemm launch: %d tiles x ksplit %d :", k, sg.segment, sg.launch_tiles[li],
-                sg.launches[li].ksplit);
+        fprintf(stderr, "  stage %2d seg %d gemm launch: %d tiles (128 x %d) x ksplit %d :", k, sg.segment,
+                sg.launch_tiles[li], 32 * sg.launches[li].nsub, sg.launches[li].ksplit);
         for (size_t i = li * kMaxOps; i < std::min(sg.ops.size(), (li + 1) * kMaxOps); ++i)
           fprintf(stderr, " [%dx%dx%d]", sg.ops[i].M, sg.ops[i].N, sg.ops[i].K);
         fprintf(stderr, "\n");
@@ -1615,6 +1626,8 @@ static void launch_gemm_ops(oprl_engine* e, const Stage& sg, cudaStream_t st) {
     g_cluster_x = ks;
     if (e->cfg.gemm_mode == OPRL_GEMM_SIMT)
       launch_k(gemm_kernel<true>, dim3(sg.launch_tiles[i] * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
+    else if (L.nsub == 2)
+      launch_k(gemm_kernel<false, 2>, dim3(sg.launch_tiles[i]), dim3(kGemmThreads), kGemmSmemBytesWide, st, L);
     else
       launch_k(gemm_kernel<false>, dim3(sg.launch_tiles[i] * ks), dim3(kGemmThreads), kGemmSmemBytes, st, L);
     g_cluster_x = 1;
@@ -1853,6 +1866,7 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   e->stream = e->own_stream;
   CU(cudaFuncSetAttribute(gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
   CU(cudaFuncSetAttribute(gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+  CU(cudaFuncSetAttribute(gemm_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytesWide));
   CU(cudaFuncSetAttribute(chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kChainSmemMax));
   e->A4 = pad4(cfg->action_dim);
   e->Kin = pad32(e->A4 + cfg->state_dim);

@@ -149,6 +149,7 @@ struct GemmLaunch {
   // (DSMEM stores + a remote mbarrier arrive); rank 0 adds the partials in rank order and runs the
   // epilogue.  The launch carries cluster dimension (ksplit, 1, 1) and ksplit x the CTAs.
   int ksplit;
+  int nsub;               // 1: 128 x 32 tiles, 2: 128 x 64 tiles (gemm_kernel<.., 2>, ksplit == 1 only)
   int tile_end[kMaxOps];  // exclusive prefix sums of gemm_tiles(op[i])
   long long* prof;        // selftest only: per-phase clock64 stamps of CTA 0
   // The op descriptors (~400 B each) live in device memory, written once when the program is built:
@@ -158,8 +159,22 @@ struct GemmLaunch {
   const GemmOp* ops;
 };
 
-__host__ __device__ __forceinline__ int gemm_tiles(const GemmOp& o) {
-  return (o.M / kBM) * (o.N / kBN);
+__host__ __device__ __forceinline__ int gemm_tiles(const GemmOp& o, int nsub = 1) {
+  return (o.M / kBM) * (o.N / (kBN * nsub));
+}
+// Wide-tile variant (`GemmLaunch::nsub` = 2, tile 128 x 64): the same K loop with N = 64 MMAs -- the split A operand
+// is produced once per 64 output columns instead of once per 32, and a launch of T narrow tiles becomes T / 2 CTAs
+// (TQC's 160- and 480-tile launches drop from 2 and 4 waves of 148 SMs to 1 and 2).  Shared memory: 5 ring stages of
+// 32 KB (A 16 KB, B raw/hi 8 KB, B lo 8 KB) + a 32 KB mask tile; tensor memory: <= 5 accumulators x 64 columns +
+// 3 A slots x 64 columns = 512.  The epilogue runs the narrow tile's code twice (columns 0-31, then 32-63).
+// Not available to ops that use the tanh' factors, the fused layer-0 gradient or the riding scalar head (their
+// per-tile state is sized for 32 columns), nor to split-K launches.
+constexpr int kWideStages = 5;
+constexpr int kWideASlots = 3;
+constexpr int kWideMaxBig = 4;
+constexpr int kGemmSmemBytesWide = kWideStages * (kAFloats + 4 * kBFloats) * 4 + 2 * kMaskBytes + 1280;
+inline bool gemm_wide_ok(const GemmOp& o) {
+  return o.N % (2 * kBN) == 0 && !o.rs && !o.aux_vec && !o.dw0_out;
 }
 // host: derived fields (TMEM accumulator plan) -- call once per op before launching
 inline void gemm_finalize(GemmOp& o, int max_big = 7) {
@@ -196,17 +211,26 @@ __device__ __forceinline__ void pin_ptr(T*& x) {
   asm volatile("" : "+l"(x));
 }
 
-template <bool kSimt>
+template <bool kSimt, int kNSub = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     gemm_kernel(const __grid_constant__ GemmLaunch L) {
+  static_assert(kNSub == 1 || (kNSub == 2 && !kSimt), "wide tiles exist for the tensor-core path only");
+  // tile geometry of this instantiation (the k* names below shadow the narrow-tile constants of the file)
+  constexpr int kBNt = kBN * kNSub;                      // tile columns
+  constexpr int kBFl = kBFloats * kNSub;                 // floats of one raw B chunk
+  constexpr int kStageFl = kAFloats + 2 * kBFl;          // [A raw][B raw -> hi][B lo]
+  constexpr int kStageBy = kStageFl * 4;
+  constexpr int kNStages = kNSub == 2 ? kWideStages : kStages;
+  constexpr int kNASlots = kNSub == 2 ? kWideASlots : kASlots;
+  constexpr int kMaskBy = kMaskBytes * kNSub;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   float* smem = reinterpret_cast<float*>(smem_raw);
-  float* mask_smem = reinterpret_cast<float*>(smem_raw + kStages * kStageBytes);
-  uint8_t* ctl = smem_raw + kStages * kStageBytes + kMaskBytes;
+  float* mask_smem = reinterpret_cast<float*>(smem_raw + kNStages * kStageBy);
+  uint8_t* ctl = smem_raw + kNStages * kStageBy + kMaskBy;
   uint64_t* full = reinterpret_cast<uint64_t*>(ctl);
-  uint64_t* empty = full + kStages;
-  uint64_t* conv = empty + kStages;
-  uint64_t* accum = conv + kStages;
+  uint64_t* empty = full + kNStages;
+  uint64_t* conv = empty + kNStages;
+  uint64_t* accum = conv + kNStages;
   uint64_t* mask_bar = accum + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mask_bar + 1);
   float* cs_smem = reinterpret_cast<float*>(ctl + 256);    // [4][32]
@@ -221,7 +245,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
   ptx::pdl_trigger();
   // ---- which op / tile is this CTA
-  const int ks = L.ksplit > 1 ? L.ksplit : 1;
+  const int ks = (kNSub == 1 && L.ksplit > 1) ? L.ksplit : 1;
   const int kr = ks > 1 ? static_cast<int>(ptx::cluster_ctarank()) : 0;
   int t = ks > 1 ? static_cast<int>(blockIdx.x) / ks : static_cast<int>(blockIdx.x);
   int oi = 0;
@@ -236,10 +260,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     __syncthreads();
   }
   const GemmOp& o = so;
-  const int ntn = o.N / kBN;
+  const int ntn = o.N / kBNt;
   const int mt = t / ntn;
   const int m0 = mt * kBM;
-  const int n0 = (t % ntn) * kBN;
+  const int n0 = (t % ntn) * kBNt;
   const int nchunks = o.K / kBK;
   // this CTA's share of the K chunks: global chunk kr + ks * cl for cl < nloc
   const int nloc = kr < nchunks ? (nchunks - kr + ks - 1) / ks : 0;
@@ -266,19 +290,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     group = (nloc + 6) / 7 > 2 ? (nloc + 6) / 7 : 2;
     n_big = (nloc + group - 1) / group;
   }
-  const uint32_t a_col0 = static_cast<uint32_t>(32 * (n_big + 1));
+  const uint32_t a_col0 = static_cast<uint32_t>(kBNt * (n_big + 1));
   uint32_t tmem_cols = 32;
-  while (tmem_cols < a_col0 + kASlots * kATmemCols) tmem_cols <<= 1;
+  while (tmem_cols < a_col0 + kNASlots * kATmemCols) tmem_cols <<= 1;
 
   float v[kEN];
 
   if (warp == 0) {
     // ===================== producer: bulk copies HBM/L2 -> smem ring (fp32, once)
-    if (lane < kStages) {
+    if (lane < kNStages) {
       ptx::mbar_init(&full[lane], 1);
       ptx::mbar_init(&empty[lane], 1);
       ptx::mbar_init(&conv[lane], 4);  // one arrival per splitter warp
-    } else if (lane == kStages) {
+    } else if (lane == kNStages) {
       ptx::mbar_init(accum, 1);
       ptx::mbar_init(mask_bar, 1);
       ptx::mbar_init(xbar, static_cast<uint32_t>(active > 1 ? (active - 1) * 8 : 1));  // one arrival per remote epilogue warp
@@ -292,23 +316,27 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     ptx::pdl_wait();  // operands are the previous kernel's outputs
     const int a_rb = o.a_rows >> 3;
     const int b_rb = o.b_rows >> 3;
-    const uint32_t tx = (kAFloats + kBFloats) * 4u;
+    const uint32_t tx = (kAFloats + kBFl) * 4u;
     for (int cl = 0; cl < nloc; ++cl) {
       const int c = kr + cl * ks;
-      const int s = cl % kStages;
-      const uint32_t ph = (cl / kStages) & 1;
+      const int s = cl % kNStages;
+      const uint32_t ph = (cl / kNStages) & 1;
       ptx::mbar_wait(&empty[s], ph ^ 1);
       if (ptx::elect_one()) {
-        float* st = smem + s * kStageFloats;
+        float* st = smem + s * kStageFl;
         ptx::mbar_expect_tx(&full[s], tx);
         ptx::bulk_g2s(st, o.a + (static_cast<size_t>(c) * a_rb + (m0 >> 3)) * 256, kAFloats * 4, &full[s]);
-        ptx::bulk_g2s(st + kAFloats, o.b + (static_cast<size_t>(c) * b_rb + (n0 >> 3)) * 256, kBFloats * 4,
+        // (the 32 * kNSub rows of B are kNSub * 4 consecutive 1 KB row-group blocks of this K chunk)
+        ptx::bulk_g2s(st + kAFloats, o.b + (static_cast<size_t>(c) * b_rb + (n0 >> 3)) * 256, kBFl * 4,
                       &full[s]);
         if (c == 0 && o.mask) {  // (chunk 0 belongs to rank 0, the CTA that runs the epilogue)
-          // epilogue ReLU mask: the [128 x 32] tile of the saved activation is one contiguous 16 KB
-          ptx::mbar_expect_tx(mask_bar, kMaskBytes);
-          ptx::bulk_g2s(mask_smem, o.mask + (static_cast<size_t>(n0 >> 5) * (o.mask_rows >> 3) + (m0 >> 3)) * 256,
-                        kMaskBytes, mask_bar);
+          // epilogue ReLU mask: each [128 x 32] tile of the saved activation is one contiguous 16 KB
+          ptx::mbar_expect_tx(mask_bar, kMaskBy);
+#pragma unroll
+          for (int h = 0; h < kNSub; ++h)
+            ptx::bulk_g2s(mask_smem + h * (kMaskBytes / 4),
+                          o.mask + (static_cast<size_t>((n0 >> 5) + h) * (o.mask_rows >> 3) + (m0 >> 3)) * 256,
+                          kMaskBytes, mask_bar);
         }
       }
       __syncwarp();
@@ -331,7 +359,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // which -- not the L2 ingest -- was what bound the K loop; tools/experiments/chain_probe5.cu.)
     const uint32_t tmem_d = *tmem_slot;
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::idesc_tf32(kBM, kBN, 0, 0);
+      const uint32_t idesc = ptx::idesc_tf32(kBM, kBNt, 0, 0);
       // B smem tile = [row group of 8][8 K-cores][8 rows][16 B]: K cores 128 B apart (LBO), 8-row groups 1 KB
       // apart (SBO); one MMA (K = 8) consumes two K cores = 256 B = 16 descriptor units.
       const uint32_t dw_hi = ((1024u >> 4) & 0x3FFFu) | (1u << 14);
@@ -339,12 +367,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       const uint32_t conv0 = ptx::smem_u32(&conv[0]), empty0 = ptx::smem_u32(&empty[0]);
       const uint32_t sb0 = ptx::smem_u32(smem + kAFloats);
       int in_group = 0;
-      uint32_t big = tmem_d + 32u;
+      uint32_t big = tmem_d + static_cast<uint32_t>(kBNt);
       uint32_t ok = 0;
       for (int c = 0; c < nloc; ++c) {  // c: local chunk index
-        const int s = c % kStages;
+        const int s = c % kNStages;
         if (!ok) {
-          const uint32_t par = static_cast<uint32_t>((c / kStages) & 1);
+          const uint32_t par = static_cast<uint32_t>((c / kNStages) & 1);
           uint32_t spins = 0;
           while (!ptx::mbar_test_wait_addr(conv0 + s * 8u, par)) {
             if (++spins > (1u << 26)) __trap();
@@ -352,10 +380,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         ptx::tc_fence_after();
         if (prof && c == 0) prof[3] = clock64();
-        ok = (c + 1 < nloc) ? ptx::mbar_test_wait_addr(conv0 + ((c + 1) % kStages) * 8u, static_cast<uint32_t>(((c + 1) / kStages) & 1)) : 0u;
-        const uint32_t dl_hi = (((sb0 + static_cast<uint32_t>(s) * kStageBytes) >> 4) & 0x3FFFu) | lbo_bits;
-        const uint32_t dl_lo = dl_hi + ((kBFloats * 4u) >> 4);
-        const uint32_t ta_hi = tmem_d + a_col0 + static_cast<uint32_t>((c % kASlots) * kATmemCols);
+        ok = (c + 1 < nloc) ? ptx::mbar_test_wait_addr(conv0 + ((c + 1) % kNStages) * 8u, static_cast<uint32_t>(((c + 1) / kNStages) & 1)) : 0u;
+        const uint32_t dl_hi = (((sb0 + static_cast<uint32_t>(s) * kStageBy) >> 4) & 0x3FFFu) | lbo_bits;
+        const uint32_t dl_lo = dl_hi + ((kBFl * 4u) >> 4);
+        const uint32_t ta_hi = tmem_d + a_col0 + static_cast<uint32_t>((c % kNASlots) * kATmemCols);
         const uint32_t ta_lo = ta_hi + kBK;
 #pragma unroll
         for (int j = 0; j < kBK / 8; ++j) {
@@ -369,7 +397,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         ptx::mma_commit_addr(empty0 + s * 8u);
         if (++in_group == group) {
           in_group = 0;
-          big += 32u;
+          big += static_cast<uint32_t>(kBNt);
         }
       }
       ptx::mma_commit(accum);
@@ -385,7 +413,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int ct = (tid - 64) & 127;   // 0..127 inside the group
     ptx::pdl_wait();  // bias / mask / outputs alias buffers the previous kernel may still use
     if (tid - 64 < kBN) bias_smem[tid - 64] = (o.bias && n0 + tid - 64 < o.bias_n) ? __ldg(o.bias + n0 + tid - 64) : 0.f;
-    if (tid - 64 >= kBN && tid - 64 < 2 * kBN) aux_smem[tid - 64 - kBN] = o.aux_vec ? __ldg(o.aux_vec + n0 + tid - 64 - kBN) : 0.f;
+    if (tid - 64 >= kBN && tid - 64 < 2 * kBN) {
+      // narrow tile: this tile's slice of the riding head's weights; wide tile (no riding head): the bias of columns 32-63
+      if (kNSub == 1) aux_smem[tid - 64 - kBN] = o.aux_vec ? __ldg(o.aux_vec + n0 + tid - 64 - kBN) : 0.f;
+      else aux_smem[tid - 64 - kBN] = (o.bias && n0 + tid - 64 < o.bias_n) ? __ldg(o.bias + n0 + tid - 64) : 0.f;
+    }
     // epilogue plan, read from the kernel parameters now (while the first copies are in flight)
     enum : uint32_t { F_BIAS = 1, F_RELU = 2, F_TANH = 4, F_MASK = 8, F_RS = 16, F_ADDM = 32, F_CLAMP = 64,
                       F_ALPHA = 128, F_MVALID = 256, F_NVALID = 512, F_T = 1024, F_TT = 2048, F_RM = 4096,
@@ -417,16 +449,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 #pragma unroll
       for (int i = 0; i < kAFloats / 4 / 256; ++i) xr[i] = __ldg(xg + (tid - 64) + i * 256);
     }
+    // this thread's 16 columns of the 32-column sub-tile `h`: the hi*hi partial sums of the accumulator groups, then
+    // the cross terms, added with ordinary fp32 adds (accumulator blocks are kBNt columns apart)
+    auto read_acc = [&](int h) {
+      const uint32_t lane_base =
+          *tmem_slot + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cn0 + kBN * h);
+      float part[kEN];
+      ptx::tmem_ld16(lane_base + static_cast<uint32_t>(kBNt), v);
+      for (int gi = 1; gi < n_big; ++gi) {
+        ptx::tmem_ld16(lane_base + static_cast<uint32_t>(kBNt * (1 + gi)), part);
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) v[j] += part[j];
+      }
+      if (passes == 3) {
+        ptx::tmem_ld16(lane_base, part);
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) v[j] += part[j];
+      }
+    };
     if (!kSimt) {
       // ---- K loop: split every landed fp32 chunk into tf32 hi / lo.  A: this thread's row
       // (32 k) goes registers -> TMEM (the MMA reads A from tensor memory, so shared memory only
       // serves the narrow B operand); B: in place (hi) + a second 4 KB buffer (lo).
       const uint32_t ta_lane = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16) + a_col0;
       for (int c = half; c < nloc; c += 2) {  // c: local chunk index
-        const int s = c % kStages;
-        const uint32_t ph = (c / kStages) & 1;
+        const int s = c % kNStages;
+        const uint32_t ph = (c / kNStages) & 1;
         ptx::mbar_wait(&full[s], ph);
-        const float* st = smem + s * kStageFloats;
+        const float* st = smem + s * kStageFl;
         float hi[kBK], lo[kBK];
 #pragma unroll
         for (int j = 0; j < kBK / 4; ++j) {
@@ -436,20 +486,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           ptx::split_tf32(x.z, hi[4 * j + 2], lo[4 * j + 2]);
           ptx::split_tf32(x.w, hi[4 * j + 3], lo[4 * j + 3]);
         }
-        if (c >= kASlots) {
-          // the TMEM slot is free once the MMAs of chunk c - kASlots retired (their commit
+        if (c >= kNASlots) {
+          // the TMEM slot is free once the MMAs of chunk c - kNASlots retired (their commit
           // arrives on that chunk's `empty` barrier)
-          const int cp = c - kASlots;
-          ptx::mbar_wait(&empty[cp % kStages], (cp / kStages) & 1);
+          const int cp = c - kNASlots;
+          ptx::mbar_wait(&empty[cp % kNStages], (cp / kNStages) & 1);
           ptx::tc_fence_after();
         }
-        const uint32_t ta = ta_lane + static_cast<uint32_t>((c % kASlots) * kATmemCols);
+        const uint32_t ta = ta_lane + static_cast<uint32_t>((c % kNASlots) * kATmemCols);
         ptx::tmem_st32(ta, hi);
         if (passes == 3) ptx::tmem_st32(ta + kBK, lo);
-        float4* braw = reinterpret_cast<float4*>(smem + s * kStageFloats + kAFloats);
-        float4* blo = braw + kBFloats / 4;
+        float4* braw = reinterpret_cast<float4*>(smem + s * kStageFl + kAFloats);
+        float4* blo = braw + kBFl / 4;
 #pragma unroll
-        for (int i = 0; i < kBFloats / 4 / 128; ++i) {
+        for (int i = 0; i < kBFl / 4 / 128; ++i) {
           const int idx = ct + i * 128;
           const float4 x = braw[idx];
           float4 h, l;
@@ -469,21 +519,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       ptx::mbar_wait(accum, 0);
       ptx::tc_fence_after();
       if (prof && tid == 64) prof[5] = clock64();
-      {
-        const uint32_t lane_base = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(cn0);
-        float part[kEN];
-        ptx::tmem_ld16(lane_base + 32u, v);
-        for (int gi = 1; gi < n_big; ++gi) {
-          ptx::tmem_ld16(lane_base + 32u * static_cast<uint32_t>(1 + gi), part);
-#pragma unroll
-          for (int j = 0; j < kEN; ++j) v[j] += part[j];
-        }
-        if (passes == 3) {
-          ptx::tmem_ld16(lane_base, part);
-#pragma unroll
-          for (int j = 0; j < kEN; ++j) v[j] += part[j];
-        }
-      }
+      read_acc(0);
       if (prof && tid == 64) prof[6] = clock64();
     } else {
       // FFMA cross-check path: same smem contents, products on CUDA cores in plain fp32.
@@ -509,7 +545,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     // every MMA (or FFMA pass) of this tile is done: the smem ring is free for epilogue staging
     asm volatile("bar.sync 1, 256;\n" ::: "memory");  // also publishes bias_smem
-    if (active > 1) {
+    if (kNSub == 1 && active > 1) {
       // ---- split-K: partial tiles travel to rank 0 through distributed shared memory (plain
       // st.shared::cluster stores; a 16 KB cp.async.bulk shared::cta -> shared::cluster copy measured
       // slower, ~2 200 vs ~1 800 cycles: one SM pair moves only ~8 B/clk over DSMEM either way).
@@ -549,297 +585,309 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (prof && tid == 64) prof[11] = clock64();
 
     const int m = m0 + row;
-    const int nb = n0 + cn0;  // first global column of this thread
-    // ---- epilogue math
-    if (fl & F_BIAS) {
-#pragma unroll
-      for (int j = 0; j < kEN; ++j) v[j] += bias_smem[cn0 + j];
-    }
-    if (fl & F_RELU) {
-#pragma unroll
-      for (int j = 0; j < kEN; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if (fl & F_TANH) {
-#pragma unroll
-      for (int j = 0; j < kEN; ++j) v[j] = tanhf(v[j]);
-    }
-    if (fl & F_MASK) {
-      ptx::mbar_wait(mask_bar, 0);
-#pragma unroll
-      for (int j4 = 0; j4 < kEN / 4; ++j4) {
-        const float4 mk = *reinterpret_cast<const float4*>(mask_smem + ((row >> 3) * 8 + cn0 / 4 + j4) * 32 + (row & 7) * 4);
-        v[4 * j4 + 0] = mk.x > 0.f ? v[4 * j4 + 0] : 0.f;
-        v[4 * j4 + 1] = mk.y > 0.f ? v[4 * j4 + 1] : 0.f;
-        v[4 * j4 + 2] = mk.z > 0.f ? v[4 * j4 + 2] : 0.f;
-        v[4 * j4 + 3] = mk.w > 0.f ? v[4 * j4 + 3] : 0.f;
+    // The epilogue handles one 32-column sub-tile at a time (a wide tile has two; its second pass re-reads the
+    // accumulators and reuses the staging buffers behind a barrier).
+#pragma unroll 1
+    for (int h = 0; h < kNSub; ++h) {
+      if (h > 0) {
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        read_acc(h);
       }
-    }
-    if (fl & F_RS) {
+      const int n0h = n0 + kBN * h;
+      const int nb = n0h + cn0;  // first global column of this thread
+      const float* bsm = h ? aux_smem : bias_smem;
+      const float* msm = mask_smem + h * (kMaskBytes / 4);
+      // ---- epilogue math
+      if (fl & F_BIAS) {
 #pragma unroll
-      for (int j = 0; j < kEN; ++j) v[j] *= (1.f - rsv[j] * rsv[j]);  // rsv = 0 beyond rs_n
-    }
-    if (fl & F_ADDM) {
+        for (int j = 0; j < kEN; ++j) v[j] += bsm[cn0 + j];
+      }
+      if (fl & F_RELU) {
 #pragma unroll
-      for (int j = 0; j < kEN; ++j)
-        if (nb + j < o.addm_n) v[j] += o.addm[static_cast<size_t>(m) * o.addm_ld + nb + j];
-    }
-    if (fl & F_CLAMP) {
+        for (int j = 0; j < kEN; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (fl & F_TANH) {
 #pragma unroll
-      for (int j = 0; j < kEN; ++j) v[j] = fminf(fmaxf(v[j], -o.clamp), o.clamp);
-    }
-    if (fl & F_ALPHA) {
+        for (int j = 0; j < kEN; ++j) v[j] = tanhf(v[j]);
+      }
+      if (fl & F_MASK) {
+        ptx::mbar_wait(mask_bar, 0);
 #pragma unroll
-      for (int j = 0; j < kEN; ++j) v[j] *= o.alpha;
-    }
-    if ((fl & F_MVALID) && m >= o.m_valid) {
-#pragma unroll
-      for (int j = 0; j < kEN; ++j) v[j] = 0.f;
-    }
-    if (fl & F_NVALID) {
-#pragma unroll
-      for (int j = 0; j < kEN; ++j)
-        if (nb + j >= o.n_valid) v[j] = 0.f;
-    }
-    if (prof && tid == 64) prof[12] = clock64();
-    // ---- outputs
-    if (fl & F_AUX) {
-      float dot = 0.f;
-#pragma unroll
-      for (int j = 0; j < kEN; ++j) dot = fmaf(v[j], aux_smem[cn0 + j], dot);
-      o.tail_out[static_cast<size_t>(2 * (n0 >> 5) + half) * o.M + m] = dot;
-      const float aa = m < o.aux_m ? o.aux_alpha : 0.f;
-#pragma unroll
-      for (int j4 = 0; j4 < kEN / 4; ++j4)
-        *reinterpret_cast<float4*>(o.aux_t + ct_index(t_rows, m, nb + 4 * j4)) =
-            make_float4(v[4 * j4 + 0] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 0] : 0.f,
-                        v[4 * j4 + 1] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 1] : 0.f,
-                        v[4 * j4 + 2] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 2] : 0.f,
-                        v[4 * j4 + 3] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 3] : 0.f);
-    }
-    if (fl & F_T) {
-#pragma unroll
-      for (int j4 = 0; j4 < kEN / 4; ++j4) {
-        if (nb + 4 * j4 < t_n) {
-          *reinterpret_cast<float4*>(out_t + ct_index(t_rows, m, t_c0 + nb + 4 * j4)) =
-              make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        for (int j4 = 0; j4 < kEN / 4; ++j4) {
+          const float4 mk = *reinterpret_cast<const float4*>(msm + ((row >> 3) * 8 + cn0 / 4 + j4) * 32 + (row & 7) * 4);
+          v[4 * j4 + 0] = mk.x > 0.f ? v[4 * j4 + 0] : 0.f;
+          v[4 * j4 + 1] = mk.y > 0.f ? v[4 * j4 + 1] : 0.f;
+          v[4 * j4 + 2] = mk.z > 0.f ? v[4 * j4 + 2] : 0.f;
+          v[4 * j4 + 3] = mk.w > 0.f ? v[4 * j4 + 3] : 0.f;
         }
       }
-    }
-    if (fl & F_TT) {
-      // transposed output [32 n x 128 m]: stage through smem (lanes = consecutive m, conflict
-      // free), then each thread stores 4 coalesced float4 = (n, 4 consecutive m) of the CT32 blocks
-      float* sT = smem;  // [32][kTTPitch]
+      if (fl & F_RS) {
 #pragma unroll
-      for (int j = 0; j < kEN; ++j) sT[(cn0 + j) * kTTPitch + row] = v[j];
-      asm volatile("bar.sync 2, 256;\n" ::: "memory");
-#pragma unroll
-      for (int i = 0; i < (kBM * kBN / 4) / 256; ++i) {
-        const int f = (tid - 64) + i * 256;  // float4 index inside the tile, block-contiguous order
-        const int blk = f >> 6;              // 1 KB block: n-group (0..3) x m-chunk (0..3), m-chunk major
-        const int mc = blk >> 2, ng = blk & 3;
-        const int core = (f >> 3) & 7;       // 4-m core inside the block
-        const int nr = f & 7;                // n inside the group
-        const int n = ng * 8 + nr, mm = mc * 32 + core * 4;
-        const float4 x = *reinterpret_cast<const float4*>(sT + n * kTTPitch + mm);
-        *reinterpret_cast<float4*>(out_tt + ct_index(tt_rows, n0 + n, m0 + mm)) = x;
+        for (int j = 0; j < kEN; ++j) v[j] *= (1.f - rsv[j] * rsv[j]);  // rsv = 0 beyond rs_n
       }
-    }
-    if (fl & F_RM) {
-      if (!o.rm_trans) {
-        if (m < o.rm_m) {
+      if (fl & F_ADDM) {
 #pragma unroll
-          for (int j = 0; j < kEN; ++j) {
-            const int n = nb + j;
-            int col = n;
-            bool ok = n < o.rm_n;
-            if (o.map_a4 > 0) {  // [action | pad4 | state] -> [state | action]
-              if (n < o.map_a) col = o.map_s + n;
-              else if (n >= o.map_a4) col = n - o.map_a4;
-              else ok = false;
-              ok = ok && (n < o.map_a4 + o.map_s);
+        for (int j = 0; j < kEN; ++j)
+          if (nb + j < o.addm_n) v[j] += o.addm[static_cast<size_t>(m) * o.addm_ld + nb + j];
+      }
+      if (fl & F_CLAMP) {
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) v[j] = fminf(fmaxf(v[j], -o.clamp), o.clamp);
+      }
+      if (fl & F_ALPHA) {
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) v[j] *= o.alpha;
+      }
+      if ((fl & F_MVALID) && m >= o.m_valid) {
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) v[j] = 0.f;
+      }
+      if (fl & F_NVALID) {
+#pragma unroll
+        for (int j = 0; j < kEN; ++j)
+          if (nb + j >= o.n_valid) v[j] = 0.f;
+      }
+      if (prof && tid == 64) prof[12] = clock64();
+      // ---- outputs
+      if (fl & F_AUX) {
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) dot = fmaf(v[j], aux_smem[cn0 + j], dot);
+        o.tail_out[static_cast<size_t>(2 * (n0h >> 5) + half) * o.M + m] = dot;
+        const float aa = m < o.aux_m ? o.aux_alpha : 0.f;
+#pragma unroll
+        for (int j4 = 0; j4 < kEN / 4; ++j4)
+          *reinterpret_cast<float4*>(o.aux_t + ct_index(t_rows, m, nb + 4 * j4)) =
+              make_float4(v[4 * j4 + 0] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 0] : 0.f,
+                          v[4 * j4 + 1] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 1] : 0.f,
+                          v[4 * j4 + 2] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 2] : 0.f,
+                          v[4 * j4 + 3] > 0.f ? aa * aux_smem[cn0 + 4 * j4 + 3] : 0.f);
+      }
+      if (fl & F_T) {
+#pragma unroll
+        for (int j4 = 0; j4 < kEN / 4; ++j4) {
+          if (nb + 4 * j4 < t_n) {
+            *reinterpret_cast<float4*>(out_t + ct_index(t_rows, m, t_c0 + nb + 4 * j4)) =
+                make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          }
+        }
+      }
+      if (fl & F_TT) {
+        // transposed output [32 n x 128 m]: stage through smem (lanes = consecutive m, conflict
+        // free), then each thread stores 4 coalesced float4 = (n, 4 consecutive m) of the CT32 blocks
+        float* sT = smem;  // [32][kTTPitch]
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) sT[(cn0 + j) * kTTPitch + row] = v[j];
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < (kBM * kBN / 4) / 256; ++i) {
+          const int f = (tid - 64) + i * 256;  // float4 index inside the tile, block-contiguous order
+          const int blk = f >> 6;              // 1 KB block: n-group (0..3) x m-chunk (0..3), m-chunk major
+          const int mc = blk >> 2, ng = blk & 3;
+          const int core = (f >> 3) & 7;       // 4-m core inside the block
+          const int nr = f & 7;                // n inside the group
+          const int n = ng * 8 + nr, mm = mc * 32 + core * 4;
+          const float4 x = *reinterpret_cast<const float4*>(sT + n * kTTPitch + mm);
+          *reinterpret_cast<float4*>(out_tt + ct_index(tt_rows, n0h + n, m0 + mm)) = x;
+        }
+      }
+      if (fl & F_RM) {
+        if (!o.rm_trans) {
+          if (m < o.rm_m) {
+#pragma unroll
+            for (int j = 0; j < kEN; ++j) {
+              const int n = nb + j;
+              int col = n;
+              bool ok = n < o.rm_n;
+              if (o.map_a4 > 0) {  // [action | pad4 | state] -> [state | action]
+                if (n < o.map_a) col = o.map_s + n;
+                else if (n >= o.map_a4) col = n - o.map_a4;
+                else ok = false;
+                ok = ok && (n < o.map_a4 + o.map_s);
+              }
+              if (ok) o.rm[static_cast<size_t>(m) * o.rm_ld + col] = v[j];
             }
-            if (ok) o.rm[static_cast<size_t>(m) * o.rm_ld + col] = v[j];
           }
-        }
-      } else {
-        if (m < o.rm_m) {
+        } else {
+          if (m < o.rm_m) {
 #pragma unroll
-          for (int j = 0; j < kEN; ++j)
-            if (nb + j < o.rm_n) o.rm[static_cast<size_t>(nb + j) * o.rm_ld + m] = v[j];
-        }
-      }
-    }
-    if (fl & F_COLSUM) {
-#pragma unroll
-      for (int j = 0; j < kEN; ++j) {
-        float s = v[j];
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (lane == j) cs_smem[q * 32 + cn0 + j] = s;
-      }
-      asm volatile("bar.sync 2, 256;\n" ::: "memory");
-      if (warp == 2) {
-        const float s = cs_smem[lane] + cs_smem[32 + lane] + cs_smem[64 + lane] + cs_smem[96 + lane];
-        o.colsum[static_cast<size_t>(mt) * o.colsum_ld + n0 + lane] = s;
-        if (o.colsum_out && !(fl & F_DW0)) {  // (with a fused dW_0 its arrival ticket serves both totals)
-          // deterministic cross-CTA total: the last M tile to arrive sums all partials in order
-          // (release/acquire ticket by lane 0; the warp barrier orders the other lanes' stores before it)
-          const int mtiles = o.M / kBM;
-          __syncwarp();
-          unsigned int ticket = 0;
-          if (lane == 0) ticket = ptx::atom_add_acq_rel_gpu(o.colsum_cnt + (n0 / kBN), 1u);
-          ticket = __shfl_sync(0xffffffffu, ticket, 0);
-          if (ticket == static_cast<unsigned int>(mtiles - 1)) {
-            float tot = 0.f;
-            for (int i0 = 0; i0 < mtiles; i0 += 8) {  // up to 8 tiles in flight
-              float ld8[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                ld8[i] = (i0 + i < mtiles) ? __ldcg(o.colsum + static_cast<size_t>(i0 + i) * o.colsum_ld + n0 + lane) : 0.f;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) tot += ld8[i];
-            }
-            if (n0 + lane < o.colsum_n) o.colsum_out[n0 + lane] = tot;
-            if (lane == 0) o.colsum_cnt[n0 / kBN] = 0u;
+            for (int j = 0; j < kEN; ++j)
+              if (nb + j < o.rm_n) o.rm[static_cast<size_t>(nb + j) * o.rm_ld + m] = v[j];
           }
         }
       }
-    }
-    if (fl & F_DW0) {
-      // ---- fused layer-0 weight gradient (see GemmOp::dw0_*): P[n][k] = sum_m D(m, n) X(m, k) over this
-      // CTA's 128 rows as a register-tiled fp32 product.  Warp w sums rows 16w..16w+15; inside a warp
-      // each lane owns a 4 n x 8 k block (3 LDS.128 per 32 FFMA); the 8 per-warp partials are added
-      // through shared memory, the per-CTA result goes to global, the last M tile adds the tiles up.
-      if (prof && tid == 64) prof[13] = clock64();
-      float* sD = smem + 32 * kTTPitch;     // [128 m][36]: this tile's D, row-major
-      float* Xs = sD + kBM * 36;            // [128 m][36]: the X chunk, row-major
-      float* Ps = Xs + kBM * 36;            // [8 warps][32 n][36]: per-warp partial sums (k halves swizzled)
-      uint32_t* last_flag = reinterpret_cast<uint32_t*>(ctl + 896);
-      const int te = tid - 64, we = te >> 5;
-      const int nq = lane >> 2, ko = lane & 3;
-      const int kp = o.dw0_kp;
-      const int ones = o.dw0_ones;
-      const int nt = n0 >> 5;
-      float* part = o.dw0_part + (static_cast<size_t>(mt) * ntn + nt) * 32 * kp;
+      if (fl & F_COLSUM) {
 #pragma unroll
-      for (int j4 = 0; j4 < kEN / 4; ++j4)
-        *reinterpret_cast<float4*>(sD + row * 36 + cn0 + 4 * j4) =
-            make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-      for (int kc0 = 0; kc0 < (kp >> 5); ++kc0) {
-        if (kc0 > 0) {
-          const float4* xg = reinterpret_cast<const float4*>(
-              o.dw0_x + (static_cast<size_t>(kc0) * (o.M >> 3) + (m0 >> 3)) * 256);
-#pragma unroll
-          for (int i = 0; i < kAFloats / 4 / 256; ++i) xr[i] = __ldg(xg + te + i * 256);
-        }
-#pragma unroll
-        for (int i = 0; i < kAFloats / 4 / 256; ++i) {
-          const int f = te + i * 256;  // float4 index inside the CT32 chunk: [row group][k core][row]
-          const int m = (f >> 6) * 8 + (f & 7), kc = (f >> 3) & 7;
-          if (ones >= 0 && (ones >> 2) == kc0 * 8 + kc) {
-            xr[i].x = (ones & 3) == 0 ? 1.f : xr[i].x;
-            xr[i].y = (ones & 3) == 1 ? 1.f : xr[i].y;
-            xr[i].z = (ones & 3) == 2 ? 1.f : xr[i].z;
-            xr[i].w = (ones & 3) == 3 ? 1.f : xr[i].w;
-          }
-          *reinterpret_cast<float4*>(Xs + m * 36 + 4 * kc) = xr[i];
+        for (int j = 0; j < kEN; ++j) {
+          float s = v[j];
+          s += __shfl_xor_sync(0xffffffffu, s, 16);
+          s += __shfl_xor_sync(0xffffffffu, s, 8);
+          s += __shfl_xor_sync(0xffffffffu, s, 4);
+          s += __shfl_xor_sync(0xffffffffu, s, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 1);
+          if (lane == j) cs_smem[q * 32 + cn0 + j] = s;
         }
         asm volatile("bar.sync 2, 256;\n" ::: "memory");
-        float acc[4][8];
+        if (warp == 2) {
+          const float s = cs_smem[lane] + cs_smem[32 + lane] + cs_smem[64 + lane] + cs_smem[96 + lane];
+          o.colsum[static_cast<size_t>(mt) * o.colsum_ld + n0h + lane] = s;
+          if (o.colsum_out && !(fl & F_DW0)) {  // (with a fused dW_0 its arrival ticket serves both totals)
+            // deterministic cross-CTA total: the last M tile to arrive sums all partials in order
+            // (release/acquire ticket by lane 0; the warp barrier orders the other lanes' stores before it)
+            const int mtiles = o.M / kBM;
+            __syncwarp();
+            unsigned int ticket = 0;
+            if (lane == 0) ticket = ptx::atom_add_acq_rel_gpu(o.colsum_cnt + (n0h / kBN), 1u);
+            ticket = __shfl_sync(0xffffffffu, ticket, 0);
+            if (ticket == static_cast<unsigned int>(mtiles - 1)) {
+              float tot = 0.f;
+              for (int i0 = 0; i0 < mtiles; i0 += 8) {  // up to 8 tiles in flight
+                float ld8[8];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+                for (int i = 0; i < 8; ++i)
+                  ld8[i] = (i0 + i < mtiles) ? __ldcg(o.colsum + static_cast<size_t>(i0 + i) * o.colsum_ld + n0h + lane) : 0.f;
 #pragma unroll
-          for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
-#pragma unroll 4
-        for (int mm = 0; mm < 16; ++mm) {
-          const int ml = we * 16 + mm;
-          const float4 d4 = *reinterpret_cast<const float4*>(sD + ml * 36 + 4 * nq);
-          const float4 x0 = *reinterpret_cast<const float4*>(Xs + ml * 36 + 8 * ko);
-          const float4 x1 = *reinterpret_cast<const float4*>(Xs + ml * 36 + 8 * ko + 4);
-          const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
-          const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                for (int i = 0; i < 8; ++i) tot += ld8[i];
+              }
+              if (n0h + lane < o.colsum_n) o.colsum_out[n0h + lane] = tot;
+              if (lane == 0) o.colsum_cnt[n0h / kBN] = 0u;
+            }
+          }
+        }
+      }
+      if (fl & F_DW0) {
+        // ---- fused layer-0 weight gradient (see GemmOp::dw0_*): P[n][k] = sum_m D(m, n) X(m, k) over this
+        // CTA's 128 rows as a register-tiled fp32 product.  Warp w sums rows 16w..16w+15; inside a warp
+        // each lane owns a 4 n x 8 k block (3 LDS.128 per 32 FFMA); the 8 per-warp partials are added
+        // through shared memory, the per-CTA result goes to global, the last M tile adds the tiles up.
+        if (prof && tid == 64) prof[13] = clock64();
+        float* sD = smem + 32 * kTTPitch;     // [128 m][36]: this tile's D, row-major
+        float* Xs = sD + kBM * 36;            // [128 m][36]: the X chunk, row-major
+        float* Ps = Xs + kBM * 36;            // [8 warps][32 n][36]: per-warp partial sums (k halves swizzled)
+        uint32_t* last_flag = reinterpret_cast<uint32_t*>(ctl + 896);
+        const int te = tid - 64, we = te >> 5;
+        const int nq = lane >> 2, ko = lane & 3;
+        const int kp = o.dw0_kp;
+        const int ones = o.dw0_ones;
+        const int nt = n0h >> 5;
+        float* part = o.dw0_part + (static_cast<size_t>(mt) * ntn + nt) * 32 * kp;
+#pragma unroll
+        for (int j4 = 0; j4 < kEN / 4; ++j4)
+          *reinterpret_cast<float4*>(sD + row * 36 + cn0 + 4 * j4) =
+              make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        for (int kc0 = 0; kc0 < (kp >> 5); ++kc0) {
+          if (kc0 > 0) {
+            const float4* xg = reinterpret_cast<const float4*>(
+                o.dw0_x + (static_cast<size_t>(kc0) * (o.M >> 3) + (m0 >> 3)) * 256);
+#pragma unroll
+            for (int i = 0; i < kAFloats / 4 / 256; ++i) xr[i] = __ldg(xg + te + i * 256);
+          }
+#pragma unroll
+          for (int i = 0; i < kAFloats / 4 / 256; ++i) {
+            const int f = te + i * 256;  // float4 index inside the CT32 chunk: [row group][k core][row]
+            const int m = (f >> 6) * 8 + (f & 7), kc = (f >> 3) & 7;
+            if (ones >= 0 && (ones >> 2) == kc0 * 8 + kc) {
+              xr[i].x = (ones & 3) == 0 ? 1.f : xr[i].x;
+              xr[i].y = (ones & 3) == 1 ? 1.f : xr[i].y;
+              xr[i].z = (ones & 3) == 2 ? 1.f : xr[i].z;
+              xr[i].w = (ones & 3) == 3 ? 1.f : xr[i].w;
+            }
+            *reinterpret_cast<float4*>(Xs + m * 36 + 4 * kc) = xr[i];
+          }
+          asm volatile("bar.sync 2, 256;\n" ::: "memory");
+          float acc[4][8];
 #pragma unroll
           for (int a = 0; a < 4; ++a)
 #pragma unroll
-            for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+            for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+#pragma unroll 4
+          for (int mm = 0; mm < 16; ++mm) {
+            const int ml = we * 16 + mm;
+            const float4 d4 = *reinterpret_cast<const float4*>(sD + ml * 36 + 4 * nq);
+            const float4 x0 = *reinterpret_cast<const float4*>(Xs + ml * 36 + 8 * ko);
+            const float4 x1 = *reinterpret_cast<const float4*>(Xs + ml * 36 + 8 * ko + 4);
+            const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+            const float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(dv[a], xv[b], acc[a][b]);
+          }
+          // float4 stores; the two 4-k halves of odd n-quads are swapped so a quarter warp covers all banks
+#pragma unroll
+          for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              *reinterpret_cast<float4*>(Ps + we * (32 * 36) + (4 * nq + a) * 36 + 8 * ko + 4 * (h ^ (nq & 1))) =
+                  make_float4(acc[a][4 * h + 0], acc[a][4 * h + 1], acc[a][4 * h + 2], acc[a][4 * h + 3]);
+          asm volatile("bar.sync 2, 256;\n" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < (kBN * kBK) / 256; ++i) {
+            const int oo = te + i * 256;
+            const int n = oo >> 5, k = oo & 31;  // lanes = consecutive k
+            float tot = 0.f;
+            const int ks = k ^ (((n >> 2) & 1) << 2);
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) tot += Ps[w8 * (32 * 36) + n * 36 + ks];
+            part[static_cast<size_t>(n) * kp + kc0 * 32 + k] = tot;
+          }
+          // (the next chunk's Xs stores are ordered behind every warp's reads by the two barriers above)
         }
-        // float4 stores; the two 4-k halves of odd n-quads are swapped so a quarter warp covers all banks
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            *reinterpret_cast<float4*>(Ps + we * (32 * 36) + (4 * nq + a) * 36 + 8 * ko + 4 * (h ^ (nq & 1))) =
-                make_float4(acc[a][4 * h + 0], acc[a][4 * h + 1], acc[a][4 * h + 2], acc[a][4 * h + 3]);
+        // deterministic cross-CTA totals (dW_0 and, if present, the bias column sums): the last M tile
+        // to arrive adds the per-tile partials in tile order
+        const int mtiles = o.M / kBM;
+        if (prof && tid == 64) prof[14] = clock64();
         asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        if (te == 0)
+          *last_flag = (ptx::atom_add_acq_rel_gpu(o.dw0_cnt + nt, 1u) == static_cast<unsigned int>(mtiles - 1)) ? 1u : 0u;
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        if (prof && tid == 64) prof[15] = clock64();
+        if (*last_flag) {
+          const float* p0 = o.dw0_part + static_cast<size_t>(nt) * 32 * kp;
+          const size_t mt_stride = static_cast<size_t>(ntn) * 32 * kp;
+          const int ma = o.dw0_map_a, ma4 = o.dw0_map_a4, ms = o.dw0_map_s, cols = o.dw0_cols, nv = o.dw0_n - n0h;
+          float* outp = o.dw0_out + static_cast<size_t>(n0h) * o.dw0_ld;
+          float* bias_out = o.dw0_bias_out;
+          const int ld = o.dw0_ld;
+          // 32 x kp outputs, 4 per thread per round; every tile's partial of a round is in flight
+          // together (up to 8 M tiles; more are added in further passes of the same order)
+          for (int base = 0; base < 32 * kp; base += 1024) {
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int i0 = 0; i0 < mtiles; i0 += 8) {
+              float ld4[8][4];
 #pragma unroll
-        for (int i = 0; i < (kBN * kBK) / 256; ++i) {
-          const int oo = te + i * 256;
-          const int n = oo >> 5, k = oo & 31;  // lanes = consecutive k
-          float tot = 0.f;
-          const int ks = k ^ (((n >> 2) & 1) << 2);
+              for (int i = 0; i < 8; ++i)
 #pragma unroll
-          for (int w8 = 0; w8 < 8; ++w8) tot += Ps[w8 * (32 * 36) + n * 36 + ks];
-          part[static_cast<size_t>(n) * kp + kc0 * 32 + k] = tot;
-        }
-        // (the next chunk's Xs stores are ordered behind every warp's reads by the two barriers above)
-      }
-      // deterministic cross-CTA totals (dW_0 and, if present, the bias column sums): the last M tile
-      // to arrive adds the per-tile partials in tile order
-      const int mtiles = o.M / kBM;
-      if (prof && tid == 64) prof[14] = clock64();
-      asm volatile("bar.sync 2, 256;\n" ::: "memory");
-      if (te == 0)
-        *last_flag = (ptx::atom_add_acq_rel_gpu(o.dw0_cnt + nt, 1u) == static_cast<unsigned int>(mtiles - 1)) ? 1u : 0u;
-      asm volatile("bar.sync 2, 256;\n" ::: "memory");
-      if (prof && tid == 64) prof[15] = clock64();
-      if (*last_flag) {
-        const float* p0 = o.dw0_part + static_cast<size_t>(nt) * 32 * kp;
-        const size_t mt_stride = static_cast<size_t>(ntn) * 32 * kp;
-        const int ma = o.dw0_map_a, ma4 = o.dw0_map_a4, ms = o.dw0_map_s, cols = o.dw0_cols, nv = o.dw0_n - n0;
-        float* outp = o.dw0_out + static_cast<size_t>(n0) * o.dw0_ld;
-        float* bias_out = o.dw0_bias_out;
-        const int ld = o.dw0_ld;
-        // 32 x kp outputs, 4 per thread per round; every tile's partial of a round is in flight
-        // together (up to 8 M tiles; more are added in further passes of the same order)
-        for (int base = 0; base < 32 * kp; base += 1024) {
-          float tot[4] = {0.f, 0.f, 0.f, 0.f};
-          for (int i0 = 0; i0 < mtiles; i0 += 8) {
-            float ld4[8][4];
+                for (int j = 0; j < 4; ++j)
+                  ld4[i][j] = (i0 + i < mtiles) ? __ldcg(p0 + (i0 + i) * mt_stride + base + te + 256 * j) : 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+              for (int i = 0; i < 8; ++i)
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                ld4[i][j] = (i0 + i < mtiles) ? __ldcg(p0 + (i0 + i) * mt_stride + base + te + 256 * j) : 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-              for (int j = 0; j < 4; ++j) tot[j] += ld4[i][j];
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int oo = base + te + 256 * j;
-            const int n = oo / kp, kk = oo - n * kp;
-            int col = kk;
-            bool ok = kk < cols && n < nv;
-            if (ma4 > 0) {  // [action | pad4 | state] -> [state | action]
-              if (kk < ma) col = ms + kk;
-              else if (kk >= ma4) col = kk - ma4;
-              else ok = false;
-              ok = ok && (kk < ma4 + ms);
+                for (int j = 0; j < 4; ++j) tot[j] += ld4[i][j];
             }
-            if (ok) outp[static_cast<size_t>(n) * ld + col] = tot[j];
-            if (kk == ones && n < nv) bias_out[n0 + n] = tot[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int oo = base + te + 256 * j;
+              const int n = oo / kp, kk = oo - n * kp;
+              int col = kk;
+              bool ok = kk < cols && n < nv;
+              if (ma4 > 0) {  // [action | pad4 | state] -> [state | action]
+                if (kk < ma) col = ms + kk;
+                else if (kk >= ma4) col = kk - ma4;
+                else ok = false;
+                ok = ok && (kk < ma4 + ms);
+              }
+              if (ok) outp[static_cast<size_t>(n) * ld + col] = tot[j];
+              if (kk == ones && n < nv) bias_out[n0h + n] = tot[j];
+            }
           }
+          if ((fl & F_COLSUM) && o.colsum_out && we == 0) {
+            float tot = 0.f;
+            for (int i = 0; i < mtiles; ++i)
+              tot += __ldcg(o.colsum + static_cast<size_t>(i) * o.colsum_ld + n0h + lane);
+            if (n0h + lane < o.colsum_n) o.colsum_out[n0h + lane] = tot;
+          }
+          if (te == 0) o.dw0_cnt[nt] = 0u;
         }
-        if ((fl & F_COLSUM) && o.colsum_out && we == 0) {
-          float tot = 0.f;
-          for (int i = 0; i < mtiles; ++i)
-            tot += __ldcg(o.colsum + static_cast<size_t>(i) * o.colsum_ld + n0 + lane);
-          if (n0 + lane < o.colsum_n) o.colsum_out[n0 + lane] = tot;
-        }
-        if (te == 0) o.dw0_cnt[nt] = 0u;
       }
     }
   }
