@@ -128,6 +128,7 @@ struct Stage {
   bool bumps_tick = false;  // holds the loss kernel that advances DevState::tick
   std::vector<GemmLaunch> launches;  // prepare_stage_tables: one per <= kMaxOps ops, descriptors on the device
   std::vector<int> launch_tiles;
+  std::vector<int> launch_first;  // index of each launch's first op in `ops`
   void add_simt(std::function<void(cudaStream_t)> f, int n_launches = 1, bool is_chain = false) {
     simt.push_back(std::move(f));
     simt_launches.push_back(n_launches);
@@ -1558,42 +1559,114 @@ namespace oprl {
 // Once per program, before any capture: finalize every stage's ops, pick the split-K factor of each
 // launch and upload the op descriptors to device memory (the kernels get a pointer, not 4.4 KB of
 // by-value parameters per launch).
+// Tile shape and split-K factor of one launch over `ops`, and what it should cost (us).  The cost model is fitted to
+// the stage profiles and ncu launch lists of round 2: ~1.5 us per launch, and per wave of n_sm CTAs ~2.5 us of
+// prologue + epilogue (+3 us per 32 input columns of a fused layer-0 gradient, +3 us for a split-K exchange) plus
+// 0.40 us (128 x 32) or 0.55 us (128 x 64) per 32-wide K chunk of the longest tile.  It only has to rank the few
+// partitions tried below.
+struct LaunchPlan {
+  int nsub, ks, tiles;
+  double cost;
+};
+static LaunchPlan plan_launch(const oprl_engine* e, const GemmOp* ops, int n, bool wide_on, int ks_cap) {
+  LaunchPlan lp{1, 1, 0, 0.0};
+  int narrow_tiles = 0, max_chunks = 0;
+  bool wide = wide_on && e->cfg.gemm_mode != OPRL_GEMM_SIMT;
+  double dw0 = 0.0;
+  for (int i = 0; i < n; ++i) {
+    narrow_tiles += gemm_tiles(ops[i]);
+    wide = wide && gemm_wide_ok(ops[i]);
+    if (ops[i].dw0_out) dw0 = std::max(dw0, 3.0 * (ops[i].dw0_kp / 32));
+    max_chunks = std::max(max_chunks, ops[i].K / kBK);
+  }
+  // 128 x 64 tiles where the narrow tiling would not fit one wave of SMs and every op of the launch can take them
+  wide = wide && narrow_tiles > e->n_sm;
+  lp.nsub = wide ? 2 : 1;
+  int ks = wide ? 1 : gemm_choose_ksplit(ops, n, e->n_sm);
+  while (ks > 1 && ks > ks_cap) ks >>= 1;
+  lp.ks = ks;
+  for (int i = 0; i < n; ++i) lp.tiles += gemm_tiles(ops[i], lp.nsub);
+  const int waves = (lp.tiles * ks + e->n_sm - 1) / e->n_sm;
+  lp.cost = 1.5 + waves * (2.5 + dw0 + (ks > 1 ? 3.0 : 0.0) + ((max_chunks + ks - 1) / ks) * (wide ? 0.55 : 0.40));
+  return lp;
+}
+
+// Once per program, before any capture: finalize every stage's ops, pick tile shape and split-K factor of each
+// launch and upload the op descriptors to device memory (the kernels get a pointer, not 4.4 KB of by-value
+// parameters per launch).  The ops of a stage are independent, so a stage may be issued as two launches when the
+// model above says that is cheaper by a clear margin: long-K weight-gradient products apart from the short-K rest
+// (the former then get split-K clusters instead of stretching every wave), or wide-tile ops apart from ops that
+// cannot take wide tiles.
 static void prepare_stage_tables(oprl_engine* e, Program* p) {
   // split-K over clusters when the launch leaves most SMs idle (OPRL_B200_KSPLIT=1 turns it off, 2 / 4 cap it)
   static const int ks_cap = getenv("OPRL_B200_KSPLIT") ? atoi(getenv("OPRL_B200_KSPLIT")) : 4;
   static const int max_big = getenv("OPRL_B200_GEMM_MAXBIG") ? atoi(getenv("OPRL_B200_GEMM_MAXBIG")) : 7;
   static const bool wide_on = !(getenv("OPRL_B200_GEMM_WIDE") && atoi(getenv("OPRL_B200_GEMM_WIDE")) == 0);
+  static const bool part_on = !(getenv("OPRL_B200_GEMM_PARTITION") && atoi(getenv("OPRL_B200_GEMM_PARTITION")) == 0);
+  const double kMinGain = 2.0;  // us: do not split a stage for less
   for (auto& sg : p->stages) {
     sg.launches.clear();
     sg.launch_tiles.clear();
-    for (size_t i0 = 0; i0 < sg.ops.size(); i0 += kMaxOps) {
+    sg.launch_first.clear();
+    if (sg.ops.empty()) continue;
+    // candidate partitions of this stage's ops into <= 2 groups: by K (longest first), by wide-tile eligibility
+    std::vector<GemmOp> best = sg.ops;
+    size_t best_cut = sg.ops.size();
+    auto cost_of = [&](const std::vector<GemmOp>& ops, size_t cut) {
+      double c = 0.0;
+      for (size_t b0 = 0, b1 = cut; b0 < ops.size(); b0 = b1, b1 = ops.size())
+        for (size_t i0 = b0; i0 < b1; i0 += kMaxOps)
+          c += plan_launch(e, &ops[i0], static_cast<int>(std::min<size_t>(kMaxOps, b1 - i0)), wide_on, ks_cap).cost;
+      return c;
+    };
+    double best_cost = cost_of(best, best_cut);
+    if (part_on && sg.ops.size() > 1) {
+      const double single = best_cost;
+      std::vector<GemmOp> byk = sg.ops;
+      std::stable_sort(byk.begin(), byk.end(), [](const GemmOp& a, const GemmOp& b) { return a.K > b.K; });
+      for (size_t cut = 1; cut < byk.size(); ++cut) {
+        if (byk[cut].K == byk[cut - 1].K) continue;
+        const double c = cost_of(byk, cut);
+        if (c + kMinGain <= single && c < best_cost) { best = byk; best_cut = cut; best_cost = c; }
+      }
+      std::vector<GemmOp> bye = sg.ops;
+      std::stable_partition(bye.begin(), bye.end(), [](const GemmOp& a) { return gemm_wide_ok(a); });
+      size_t ne = 0;
+      while (ne < bye.size() && gemm_wide_ok(bye[ne])) ++ne;
+      if (ne > 0 && ne < bye.size()) {
+        const double c = cost_of(bye, ne);
+        if (c + kMinGain <= single && c < best_cost) { best = bye; best_cut = ne; best_cost = c; }
+      }
+    }
+    sg.ops = best;
+    // multi-wave launches: longest tiles first, so the second wave is made of the short ones (CTAs are handed to
+    // SMs in block order as SMs free up)
+    for (size_t b0 = 0, b1 = best_cut; b0 < sg.ops.size(); b0 = b1, b1 = sg.ops.size()) {
+      int narrow_tiles = 0;
+      for (size_t i = b0; i < b1; ++i) narrow_tiles += gemm_tiles(sg.ops[i]);
+      if (narrow_tiles > 2 * e->n_sm && b1 - b0 <= kMaxOps)
+        std::stable_sort(sg.ops.begin() + b0, sg.ops.begin() + b1, [](const GemmOp& a, const GemmOp& b) { return a.K > b.K; });
+    }
+    for (size_t b0 = 0, b1 = best_cut; b0 < sg.ops.size(); b0 = b1, b1 = sg.ops.size())
+    for (size_t i0 = b0; i0 < b1; i0 += kMaxOps) {
       GemmLaunch L;
       memset(&L, 0, sizeof(L));
-      L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, sg.ops.size() - i0));
-      // 128 x 64 tiles where the narrow tiling would not fit one wave of SMs and every op of the launch can take them
-      // (gemm.cuh gemm_wide_ok); OPRL_B200_GEMM_WIDE=0 keeps 128 x 32 everywhere
-      int narrow_tiles = 0;
-      bool wide = wide_on && e->cfg.gemm_mode != OPRL_GEMM_SIMT;
-      for (int i = 0; i < L.n_ops; ++i) {
-        narrow_tiles += gemm_tiles(sg.ops[i0 + i]);
-        wide = wide && gemm_wide_ok(sg.ops[i0 + i]);
-      }
-      wide = wide && narrow_tiles > e->n_sm;
-      L.nsub = wide ? 2 : 1;
+      L.n_ops = static_cast<int>(std::min<size_t>(kMaxOps, b1 - i0));
+      const LaunchPlan lp = plan_launch(e, &sg.ops[i0], L.n_ops, wide_on, ks_cap);
+      L.nsub = lp.nsub;
+      L.ksplit = lp.ks;
       int tiles = 0;
       for (int i = 0; i < L.n_ops; ++i) {
-        gemm_finalize(sg.ops[i0 + i], wide ? kWideMaxBig : max_big);
+        gemm_finalize(sg.ops[i0 + i], lp.nsub == 2 ? kWideMaxBig : max_big);
         tiles += gemm_tiles(sg.ops[i0 + i], L.nsub);
         L.tile_end[i] = tiles;
       }
-      int ks = wide ? 1 : gemm_choose_ksplit(&sg.ops[i0], L.n_ops, e->n_sm);
-      while (ks > 1 && ks > ks_cap) ks >>= 1;
-      L.ksplit = ks;
       GemmOp* d = reinterpret_cast<GemmOp*>(e->alloc_floats((sizeof(GemmOp) * L.n_ops + 3) / 4));
       CU(cudaMemcpyAsync(d, &sg.ops[i0], sizeof(GemmOp) * L.n_ops, cudaMemcpyHostToDevice, e->stream));
       L.ops = d;
       sg.launches.push_back(L);
       sg.launch_tiles.push_back(tiles);
+      sg.launch_first.push_back(static_cast<int>(i0));
     }
   }
   CU(cudaStreamSynchronize(e->stream));
@@ -1608,8 +1681,10 @@ static void prepare_stage_tables(oprl_engine* e, Program* p) {
       for (size_t li = 0; li < sg.launches.size(); ++li) {
         fprintf(stderr, "  stage %2d seg %d gemm launch: %d tiles (128 x %d) x ksplit %d :", k, sg.segment,
                 sg.launch_tiles[li], 32 * sg.launches[li].nsub, sg.launches[li].ksplit);
-        for (size_t i = li * kMaxOps; i < std::min(sg.ops.size(), (li + 1) * kMaxOps); ++i)
-          fprintf(stderr, " [%dx%dx%d]", sg.ops[i].M, sg.ops[i].N, sg.ops[i].K);
+        for (int i = 0; i < sg.launches[li].n_ops; ++i) {
+          const GemmOp& o = sg.ops[sg.launch_first[li] + i];
+          fprintf(stderr, " [%dx%dx%d]", o.M, o.N, o.K);
+        }
         fprintf(stderr, "\n");
       }
       for (size_t i = 0; i < sg.simt.size(); ++i)
@@ -1644,7 +1719,7 @@ static int run_stages(oprl_engine* e, Program* p, int segment, cudaStream_t st, 
     if (max_stages-- <= 0) break;
     if (!sg.ops.empty() && (what == 0 || what == 1)) {
       launch_gemm_ops(e, sg, st);
-      n += static_cast<int>((sg.ops.size() + kMaxOps - 1) / kMaxOps);
+      n += static_cast<int>(sg.launches.size());
     }
     if (what != 1)
       for (size_t i = 0; i < sg.simt.size(); ++i) {

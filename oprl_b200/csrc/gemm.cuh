@@ -167,14 +167,14 @@ __host__ __device__ __forceinline__ int gemm_tiles(const GemmOp& o, int nsub = 1
 // (TQC's 160- and 480-tile launches drop from 2 and 4 waves of 148 SMs to 1 and 2).  Shared memory: 5 ring stages of
 // 32 KB (A 16 KB, B raw/hi 8 KB, B lo 8 KB) + a 32 KB mask tile; tensor memory: <= 5 accumulators x 64 columns +
 // 3 A slots x 64 columns = 512.  The epilogue runs the narrow tile's code twice (columns 0-31, then 32-63).
-// Not available to ops that use the tanh' factors, the fused layer-0 gradient or the riding scalar head (their
-// per-tile state is sized for 32 columns), nor to split-K launches.
+// Not available to ops that use the tanh' factors or the riding scalar head (their per-tile state is sized for 32
+// columns), nor to split-K launches.
 constexpr int kWideStages = 5;
 constexpr int kWideASlots = 3;
 constexpr int kWideMaxBig = 4;
 constexpr int kGemmSmemBytesWide = kWideStages * (kAFloats + 4 * kBFloats) * 4 + 2 * kMaskBytes + 1280;
 inline bool gemm_wide_ok(const GemmOp& o) {
-  return o.N % (2 * kBN) == 0 && !o.rs && !o.aux_vec && !o.dw0_out;
+  return o.N % (2 * kBN) == 0 && !o.rs && !o.aux_vec;
 }
 // host: derived fields (TMEM accumulator plan) -- call once per op before launching
 inline void gemm_finalize(GemmOp& o, int max_big = 7) {
@@ -183,8 +183,7 @@ inline void gemm_finalize(GemmOp& o, int max_big = 7) {
   o.n_big = (nchunks + o.group - 1) / o.group;
 }
 // host: CTAs per tile for one launch -- the largest of {4, 2, 1} that keeps the whole launch in one
-// wave of `n_sm` single-CTA SMs, leaves rank 0 the ring stages the partial tiles land in, and is
-// worth the exchange (an op must have at least 2 chunks per CTA)
+// wave of `n_sm` single-CTA SMs and is worth the exchange (an op must have at least 2 chunks per CTA)
 inline int gemm_choose_ksplit(const GemmOp* ops, int n_ops, int n_sm) {
   int tiles = 0, max_chunks = 0;
   for (int i = 0; i < n_ops; ++i) {
@@ -194,7 +193,6 @@ inline int gemm_choose_ksplit(const GemmOp* ops, int n_ops, int n_sm) {
   for (int ks = 4; ks >= 2; ks >>= 1) {
     if (tiles * ks > n_sm) continue;
     if (max_chunks < 2 * ks) continue;
-    if ((max_chunks + ks - 1) / ks > kStages - (ks - 1)) continue;
     return ks;
   }
   return 1;
@@ -273,6 +271,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     return;
   }
   const int passes = o.passes;
+  // ring depth: a split-K CTA keeps the last two stages (48 KB) as landing slots for the partial tiles of ranks 1-3
+  const int nst = (kNSub == 1 && ks > 1) ? kStages - 2 : kNStages;
   long long* prof = (L.prof && blockIdx.x == 0) ? L.prof : nullptr;
   long long* prof1 = (L.prof && blockIdx.x == 1 && ks > 1) ? L.prof : nullptr;  // rank 1 of tile 0
   if (prof1 && tid == 0) prof1[16] = clock64();
@@ -317,10 +317,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     const int a_rb = o.a_rows >> 3;
     const int b_rb = o.b_rows >> 3;
     const uint32_t tx = (kAFloats + kBFl) * 4u;
+    int s = 0;
+    uint32_t ph = 0;
     for (int cl = 0; cl < nloc; ++cl) {
       const int c = kr + cl * ks;
-      const int s = cl % kNStages;
-      const uint32_t ph = (cl / kNStages) & 1;
       ptx::mbar_wait(&empty[s], ph ^ 1);
       if (ptx::elect_one()) {
         float* st = smem + s * kStageFl;
@@ -340,6 +340,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
       }
       __syncwarp();
+      if (++s == nst) {
+        s = 0;
+        ph ^= 1;
+      }
     }
     if (prof && lane == 0) prof[2] = clock64();
   } else {
@@ -369,10 +373,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       int in_group = 0;
       uint32_t big = tmem_d + static_cast<uint32_t>(kBNt);
       uint32_t ok = 0;
+      int s = 0, aslot = 0;
+      uint32_t par = 0;
       for (int c = 0; c < nloc; ++c) {  // c: local chunk index
-        const int s = c % kNStages;
         if (!ok) {
-          const uint32_t par = static_cast<uint32_t>((c / kNStages) & 1);
           uint32_t spins = 0;
           while (!ptx::mbar_test_wait_addr(conv0 + s * 8u, par)) {
             if (++spins > (1u << 26)) __trap();
@@ -380,10 +384,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         ptx::tc_fence_after();
         if (prof && c == 0) prof[3] = clock64();
-        ok = (c + 1 < nloc) ? ptx::mbar_test_wait_addr(conv0 + ((c + 1) % kNStages) * 8u, static_cast<uint32_t>(((c + 1) / kNStages) & 1)) : 0u;
+        int s1 = s + 1;
+        uint32_t par1 = par;
+        if (s1 == nst) {
+          s1 = 0;
+          par1 ^= 1u;
+        }
+        ok = (c + 1 < nloc) ? ptx::mbar_test_wait_addr(conv0 + static_cast<uint32_t>(s1) * 8u, par1) : 0u;
         const uint32_t dl_hi = (((sb0 + static_cast<uint32_t>(s) * kStageBy) >> 4) & 0x3FFFu) | lbo_bits;
         const uint32_t dl_lo = dl_hi + ((kBFl * 4u) >> 4);
-        const uint32_t ta_hi = tmem_d + a_col0 + static_cast<uint32_t>((c % kNASlots) * kATmemCols);
+        const uint32_t ta_hi = tmem_d + a_col0 + static_cast<uint32_t>(aslot * kATmemCols);
         const uint32_t ta_lo = ta_hi + kBK;
 #pragma unroll
         for (int j = 0; j < kBK / 8; ++j) {
@@ -399,6 +409,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           in_group = 0;
           big += static_cast<uint32_t>(kBNt);
         }
+        s = s1;
+        par = par1;
+        if (++aslot == kNASlots) aslot = 0;
       }
       ptx::mma_commit(accum);
       if (prof) prof[4] = clock64();
@@ -472,9 +485,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // (32 k) goes registers -> TMEM (the MMA reads A from tensor memory, so shared memory only
       // serves the narrow B operand); B: in place (hi) + a second 4 KB buffer (lo).
       const uint32_t ta_lane = *tmem_slot + (static_cast<uint32_t>(q * 32) << 16) + a_col0;
+      int s = half;  // ring stage / phase of chunk c, and of chunk c - kNASlots (the A slot's previous user)
+      uint32_t ph = 0;
+      int sp = (kNASlots & 1) == half ? 0 : 1;  // (first c >= kNASlots of this group's parity) - kNASlots
+      uint32_t php = 0;
       for (int c = half; c < nloc; c += 2) {  // c: local chunk index
-        const int s = c % kNStages;
-        const uint32_t ph = (c / kNStages) & 1;
         ptx::mbar_wait(&full[s], ph);
         const float* st = smem + s * kStageFl;
         float hi[kBK], lo[kBK];
@@ -489,9 +504,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (c >= kNASlots) {
           // the TMEM slot is free once the MMAs of chunk c - kNASlots retired (their commit
           // arrives on that chunk's `empty` barrier)
-          const int cp = c - kNASlots;
-          ptx::mbar_wait(&empty[cp % kNStages], (cp / kNStages) & 1);
+          ptx::mbar_wait(&empty[sp], php);
           ptx::tc_fence_after();
+          sp += 2;
+          if (sp >= nst) {
+            sp -= nst;
+            php ^= 1u;
+          }
         }
         const uint32_t ta = ta_lane + static_cast<uint32_t>((c % kNASlots) * kATmemCols);
         ptx::tmem_st32(ta, hi);
@@ -515,6 +534,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&conv[s]);
+        s += 2;
+        if (s >= nst) {
+          s -= nst;
+          ph ^= 1u;
+        }
       }
       ptx::mbar_wait(accum, 0);
       ptx::tc_fence_after();
@@ -525,9 +549,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // FFMA cross-check path: same smem contents, products on CUDA cores in plain fp32.
 #pragma unroll
       for (int j = 0; j < kEN; ++j) v[j] = 0.f;
+      int s = 0;
+      uint32_t ph = 0;
       for (int c = 0; c < nloc; ++c) {
-        const int s = c % kStages;
-        const uint32_t ph = (c / kStages) & 1;
         ptx::mbar_wait(&full[s], ph);
         const float* sa = smem + s * kStageFloats;
         const float* sb = sa + kAFloats;
@@ -541,6 +565,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         asm volatile("bar.sync 1, 256;\n" ::: "memory");
         if (tid == 64) ptx::mbar_arrive(&empty[s]);
+        if (++s == nst) {
+          s = 0;
+          ph ^= 1u;
+        }
       }
     }
     // every MMA (or FFMA pass) of this tile is done: the smem ring is free for epilogue staging
@@ -549,14 +577,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       // ---- split-K: partial tiles travel to rank 0 through distributed shared memory (plain
       // st.shared::cluster stores; a 16 KB cp.async.bulk shared::cta -> shared::cluster copy measured
       // slower, ~2 200 vs ~1 800 cycles: one SM pair moves only ~8 B/clk over DSMEM either way).
-      // Slot of rank r = the A part of ring stage kStages - r of rank 0 (the host only splits when
-      // rank 0's own chunks leave those stages unused); element (row, 4 columns j4) of a thread sits
-      // at float4 index (half * 4 + j4) * 128 + row in both CTAs.
+      // Slot of rank r = 16 KB number r - 1 behind the (shortened) ring of rank 0; element (row, 4 columns j4)
+      // of a thread sits at float4 index (half * 4 + j4) * 128 + row in both CTAs.
       if (kr > 0) {
         if (prof1 && tid == 64) prof1[17] = clock64();
         ptx::cluster_wait();  // rank 0 has initialised xbar (every thread of the cluster arrived at kernel start)
         if (prof1 && tid == 64) prof1[18] = clock64();
-        const uint32_t slot = ptx::mapa(ptx::smem_u32(smem + (kStages - kr) * kStageFloats), 0);
+        const uint32_t slot = ptx::mapa(ptx::smem_u32(smem + nst * kStageFloats + (kr - 1) * kAFloats), 0);
 #pragma unroll
         for (int j4 = 0; j4 < kEN / 4; ++j4)
           ptx::st_cluster_v4(slot + static_cast<uint32_t>(((half * 4 + j4) * 128 + row) * 16), v[4 * j4 + 0],
@@ -570,7 +597,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
       } else {
         ptx::mbar_wait_cluster(xbar, 0);
         for (int r = 1; r < active; ++r) {
-          const float4* slot = reinterpret_cast<const float4*>(smem + (kStages - r) * kStageFloats);
+          const float4* slot = reinterpret_cast<const float4*>(smem + nst * kStageFloats + (r - 1) * kAFloats);
 #pragma unroll
           for (int j4 = 0; j4 < kEN / 4; ++j4) {
             const float4 p4 = slot[(half * 4 + j4) * 128 + row];
@@ -690,7 +717,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           *reinterpret_cast<float4*>(out_tt + ct_index(tt_rows, n0h + n, m0 + mm)) = x;
         }
       }
-      if (fl & F_RM) {
+      if ((fl & F_RM) && !o.rm_trans && o.map_a4 <= 0) {
+        // plain row-major output (the weight gradients): staged through shared memory so that a warp stores
+        // 32 consecutive columns of one row (one 128-byte line) instead of one column of 32 rows (32 sectors)
+        float* sR = smem + 32 * kTTPitch + 2 * kBM * 36 + 8 * 32 * 36;  // [128][33], behind the dW_0 buffers
+#pragma unroll
+        for (int j = 0; j < kEN; ++j) sR[row * 33 + cn0 + j] = v[j];
+        asm volatile("bar.sync 2, 256;\n" ::: "memory");
+        const int we = (tid - 64) >> 5;
+        const int col = n0h + lane;
+        if (col < o.rm_n) {
+          float* dst = o.rm + col;
+          const int ld = o.rm_ld;
+#pragma unroll 4
+          for (int r = 0; r < 16; ++r) {
+            const int mr = we * 16 + r;
+            if (m0 + mr < o.rm_m) dst[static_cast<size_t>(m0 + mr) * ld] = sR[mr * 33 + lane];
+          }
+        }
+      } else if (fl & F_RM) {
         if (!o.rm_trans) {
           if (m < o.rm_m) {
 #pragma unroll
@@ -769,13 +814,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         const int kp = o.dw0_kp;
         const int ones = o.dw0_ones;
         const int nt = n0h >> 5;
-        float* part = o.dw0_part + (static_cast<size_t>(mt) * ntn + nt) * 32 * kp;
+        const int ntn32 = o.N / kBN;  // partial sums are kept per 32-column sub-tile
+        float* part = o.dw0_part + (static_cast<size_t>(mt) * ntn32 + nt) * 32 * kp;
 #pragma unroll
         for (int j4 = 0; j4 < kEN / 4; ++j4)
           *reinterpret_cast<float4*>(sD + row * 36 + cn0 + 4 * j4) =
               make_float4(v[4 * j4 + 0], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
         for (int kc0 = 0; kc0 < (kp >> 5); ++kc0) {
-          if (kc0 > 0) {
+          if (kc0 > 0 || (h > 0 && kp > 32)) {  // (xr still holds chunk 0 unless an earlier pass moved on)
             const float4* xg = reinterpret_cast<const float4*>(
                 o.dw0_x + (static_cast<size_t>(kc0) * (o.M >> 3) + (m0 >> 3)) * 256);
 #pragma unroll
@@ -843,7 +889,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         if (prof && tid == 64) prof[15] = clock64();
         if (*last_flag) {
           const float* p0 = o.dw0_part + static_cast<size_t>(nt) * 32 * kp;
-          const size_t mt_stride = static_cast<size_t>(ntn) * 32 * kp;
+          const size_t mt_stride = static_cast<size_t>(ntn32) * 32 * kp;
           const int ma = o.dw0_map_a, ma4 = o.dw0_map_a4, ms = o.dw0_map_s, cols = o.dw0_cols, nv = o.dw0_n - n0h;
           float* outp = o.dw0_out + static_cast<size_t>(n0h) * o.dw0_ld;
           float* bias_out = o.dw0_bias_out;

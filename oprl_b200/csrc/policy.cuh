@@ -192,21 +192,26 @@ __global__ void __launch_bounds__(kTdThreads) actor_seed_kernel(ActorSeedArgs a,
     lts += a.logp[m] + a.target_entropy;
   }
   if (a.tqc) {
-    // mean over the n_nets * n_quantiles atoms of a row: one warp per row, coalesced, four rows in flight (a thread
+    // mean over the n_nets * n_quantiles atoms of a row: one warp per row, coalesced, 32 loads per lane in flight (a thread
     // per row walked 125 strided loads one after the other: 13 us for a logging scalar on the critical path)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_nq = 1.f / static_cast<float>(a.nq);
-    for (int m0 = warp * 4; m0 < a.B; m0 += (kTdThreads / 32) * 4) {
-      float s[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int kRows = 8, kPer = 4;  // rows in flight per warp, atoms per lane and row (nq <= 128)
+    for (int m0 = warp * kRows; m0 < a.B; m0 += (kTdThreads / 32) * kRows) {
+      float x[kRows][kPer];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (m0 + u < a.B)
-          for (int k = lane; k < a.nq; k += 32) s[u] += a.q[static_cast<size_t>(m0 + u) * a.nq + k];
+      for (int u = 0; u < kRows; ++u)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+        for (int i = 0; i < kPer; ++i) {
+          const int k = lane + 32 * i;
+          x[u][i] = (m0 + u < a.B && k < a.nq) ? a.q[static_cast<size_t>(m0 + u) * a.nq + k] : 0.f;
+        }
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s[u] += __shfl_xor_sync(0xffffffffu, s[u], off);
-        if (lane == 0 && m0 + u < a.B) qs += s[u] * inv_nq;
+      for (int u = 0; u < kRows; ++u) {
+        float sum = (x[u][0] + x[u][1]) + (x[u][2] + x[u][3]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (lane == 0 && m0 + u < a.B) qs += sum * inv_nq;
       }
     }
   }
