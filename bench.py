@@ -423,7 +423,9 @@ def run_engine(args):
         roof_gemm = tensor_roofline("oprl::gemm_kernel<false> (grouped 128x32 tcgen05 3xTF32 tiles: the weight-gradient products)",
                                     "gemm_kernel", dw_mflop, gemm_ms, gemm_launches)
     else:
-        roof = tensor_roofline("oprl::gemm_kernel<false> (grouped 128x32 tcgen05 3xTF32 tiles)", "gemm_kernel", ALGO_MFLOP[args.algo], gemm_ms, gemm_launches)
+        tiles = "128x32 tiles" if args.algo in ("ddpg", "td3") else "128x32 tiles, 128x64 in launches that exceed one wave of SMs"
+        roof = tensor_roofline("oprl::gemm_kernel<false, 1|2> (grouped tcgen05 3xTF32 GEMM, %s)" % tiles, "gemm_kernel",
+                               ALGO_MFLOP[args.algo], gemm_ms, gemm_launches)
         roof_gemm = None
     roof["simt_us_per_update"] = simt_ms * 1e3
     roof["gemm_us_per_update"] = gemm_ms * 1e3

@@ -160,21 +160,23 @@ struct GemmLaunch {
 };
 
 __host__ __device__ __forceinline__ int gemm_tiles(const GemmOp& o, int nsub = 1) {
-  return (o.M / kBM) * (o.N / (kBN * nsub));
+  return (o.M / kBM) * ((o.N + kBN * nsub - 1) / (kBN * nsub));
 }
 // Wide-tile variant (`GemmLaunch::nsub` = 2, tile 128 x 64): the same K loop with N = 64 MMAs -- the split A operand
 // is produced once per 64 output columns instead of once per 32, and a launch of T narrow tiles becomes T / 2 CTAs
 // (TQC's 160- and 480-tile launches drop from 2 and 4 waves of 148 SMs to 1 and 2).  Shared memory: 5 ring stages of
 // 32 KB (A 16 KB, B raw/hi 8 KB, B lo 8 KB) + a 32 KB mask tile; tensor memory: <= 5 accumulators x 64 columns +
 // 3 A slots x 64 columns = 512.  The epilogue runs the narrow tile's code twice (columns 0-31, then 32-63).
-// Not available to ops that use the tanh' factors or the riding scalar head (their per-tile state is sized for 32
-// columns), nor to split-K launches.
+// An op whose N is an odd multiple of 32 ends in a ragged tile: only 32 rows of B are copied, the MMAs still run 64
+// wide over whatever the second half of the B buffer holds, and the second epilogue pass is skipped (those
+// accumulator columns are never read).  Not available to ops that use the tanh' factors or the riding scalar head
+// (their per-tile state is sized for 32 columns), nor to split-K launches.
 constexpr int kWideStages = 5;
 constexpr int kWideASlots = 3;
 constexpr int kWideMaxBig = 4;
 constexpr int kGemmSmemBytesWide = kWideStages * (kAFloats + 4 * kBFloats) * 4 + 2 * kMaskBytes + 1280;
 inline bool gemm_wide_ok(const GemmOp& o) {
-  return o.N % (2 * kBN) == 0 && !o.rs && !o.aux_vec;
+  return !o.rs && !o.aux_vec;
 }
 // host: derived fields (TMEM accumulator plan) -- call once per op before launching
 inline void gemm_finalize(GemmOp& o, int max_big = 7) {
@@ -258,10 +260,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     __syncthreads();
   }
   const GemmOp& o = so;
-  const int ntn = o.N / kBNt;
+  const int ntn = (o.N + kBNt - 1) / kBNt;
   const int mt = t / ntn;
   const int m0 = mt * kBM;
   const int n0 = (t % ntn) * kBNt;
+  const int nsub = (kNSub == 2 && n0 + kBN >= o.N) ? 1 : kNSub;  // 32-column sub-tiles this CTA owns (ragged last tile: 1)
   const int nchunks = o.K / kBK;
   // this CTA's share of the K chunks: global chunk kr + ks * cl for cl < nloc
   const int nloc = kr < nchunks ? (nchunks - kr + ks - 1) / ks : 0;
@@ -316,7 +319,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     ptx::pdl_wait();  // operands are the previous kernel's outputs
     const int a_rb = o.a_rows >> 3;
     const int b_rb = o.b_rows >> 3;
-    const uint32_t tx = (kAFloats + kBFl) * 4u;
+    const uint32_t b_bytes = static_cast<uint32_t>(kBFloats * nsub) * 4u;
+    const uint32_t tx = kAFloats * 4u + b_bytes;
     int s = 0;
     uint32_t ph = 0;
     for (int cl = 0; cl < nloc; ++cl) {
@@ -327,13 +331,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         ptx::mbar_expect_tx(&full[s], tx);
         ptx::bulk_g2s(st, o.a + (static_cast<size_t>(c) * a_rb + (m0 >> 3)) * 256, kAFloats * 4, &full[s]);
         // (the 32 * kNSub rows of B are kNSub * 4 consecutive 1 KB row-group blocks of this K chunk)
-        ptx::bulk_g2s(st + kAFloats, o.b + (static_cast<size_t>(c) * b_rb + (n0 >> 3)) * 256, kBFl * 4,
-                      &full[s]);
+        ptx::bulk_g2s(st + kAFloats, o.b + (static_cast<size_t>(c) * b_rb + (n0 >> 3)) * 256, b_bytes, &full[s]);
         if (c == 0 && o.mask) {  // (chunk 0 belongs to rank 0, the CTA that runs the epilogue)
           // epilogue ReLU mask: each [128 x 32] tile of the saved activation is one contiguous 16 KB
-          ptx::mbar_expect_tx(mask_bar, kMaskBy);
-#pragma unroll
-          for (int h = 0; h < kNSub; ++h)
+          ptx::mbar_expect_tx(mask_bar, static_cast<uint32_t>(kMaskBytes * nsub));
+          for (int h = 0; h < nsub; ++h)
             ptx::bulk_g2s(mask_smem + h * (kMaskBytes / 4),
                           o.mask + (static_cast<size_t>((n0 >> 5) + h) * (o.mask_rows >> 3) + (m0 >> 3)) * 256,
                           kMaskBytes, mask_bar);
@@ -615,7 +617,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     // The epilogue handles one 32-column sub-tile at a time (a wide tile has two; its second pass re-reads the
     // accumulators and reuses the staging buffers behind a barrier).
 #pragma unroll 1
-    for (int h = 0; h < kNSub; ++h) {
+    for (int h = 0; h < nsub; ++h) {
       if (h > 0) {
         asm volatile("bar.sync 2, 256;\n" ::: "memory");
         read_acc(h);

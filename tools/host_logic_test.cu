@@ -74,10 +74,9 @@ int main() {
     CHECK(gemm_choose_ksplit(&big, 1, 148) == 2);
     GemmOp five[5] = {big, big, big, big, big};  // 320 tiles: more than one wave already
     CHECK(gemm_choose_ksplit(five, 5, 148) == 1);
-    GemmOp deep = op(128, 32, 1024);  // 32 chunks: rank 0 would need the exchange stages for its own ring
-    const int ks = gemm_choose_ksplit(&deep, 1, 148);
-    CHECK(ks == 1 || (32 + ks - 1) / ks <= kStages - (ks - 1));
-    GemmOp k448 = op(128, 32, 448);  // 14 chunks: 2-way leaves 7 stages + 1 slot, 4-way 4 + 3
+    GemmOp deep = op(128, 32, 1024);  // 32 chunks: any depth splits (the partial tiles land behind a shortened ring)
+    CHECK(gemm_choose_ksplit(&deep, 1, 148) == 4);
+    GemmOp k448 = op(128, 32, 448);  // 14 chunks
     CHECK(gemm_choose_ksplit(&k448, 1, 148) == 4);
     GemmOp mixed[2] = {one, k32};  // the deepest op decides; the shallow one's extra ranks leave at once
     CHECK(gemm_choose_ksplit(mixed, 2, 148) == 4);
@@ -86,7 +85,27 @@ int main() {
   }
   // ---- shared-memory budget of one CTA (227 KB opt-in limit) and the exchange slots
   CHECK(kGemmSmemBytes + 2048 <= 227 * 1024);
+  CHECK(kGemmSmemBytesWide + 2048 <= 227 * 1024);
   CHECK(kStageFloats * 4 == kStageBytes && kAFloats * 4 <= kStageBytes);
+  CHECK(3 * kAFloats <= 2 * kStageFloats);  // three 16 KB partial-tile slots fit the two ring stages a split-K CTA gives up
+  // epilogue staging (transposed tile, dW_0 buffers, row-major tile) stays inside the shortest ring (split-K: 6 stages)
+  CHECK((32 * kTTPitch + 2 * kBM * 36 + 8 * 32 * 36 + kBM * 33) * 4 <= (kStages - 2) * kStageBytes);
+  CHECK((32 * kTTPitch + 2 * kBM * 36 + 8 * 32 * 36 + kBM * 33) * 4 <= kWideStages * (kAFloats + 4 * kBFloats) * 4);
+  // ---- wide tiles: tile counts (ragged last tile), accumulator plan within 512 tensor-memory columns
+  {
+    GemmOp w = op(256, 512, 512);
+    CHECK(gemm_tiles(w) == 32 && gemm_tiles(w, 2) == 16);
+    GemmOp r = op(256, 96, 256);  // 3 sub-tiles of 32 columns: two wide tiles, the second ragged
+    CHECK(gemm_tiles(r, 2) == 4);
+    GemmOp n32 = op(256, 32, 256);
+    CHECK(gemm_tiles(n32, 2) == 2 && gemm_wide_ok(n32));
+    for (int K = 32; K <= 4096; K += 32) {
+      GemmOp o = op(128, 64, K);
+      gemm_finalize(o, kWideMaxBig);
+      CHECK(o.n_big <= kWideMaxBig && o.n_big * o.group >= K / kBK);
+      CHECK(64 * (o.n_big + 1) + kWideASlots * kATmemCols <= 512);
+    }
+  }
   printf("host logic: %s (%d failures)\n", fails ? "FAIL" : "PASS", fails);
   return fails ? 1 : 0;
 }
