@@ -49,7 +49,7 @@ L_EP = 1000
 MIN_SETTLE_STEPS = 16  # untimed steps before the timed window whatever --warmup says (graph captures, lazy allocations)
 
 
-def ncu_traffic_per_launch(kernel_substr):
+def ncu_traffic_per_launch(kernel_substr, algo=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the newest committed
     `ncu --set full` raw-page CSV under profiles/ (cold L2: ncu flushes caches between replays).  None if absent.
     The raw page is: a header row, a units row, then one row per profiled launch."""
@@ -57,7 +57,11 @@ def ncu_traffic_per_launch(kernel_substr):
     import glob
 
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "": 1.0}
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*raw*.csv")), reverse=True):
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*raw*.csv")), reverse=True)
+    tag = lambda p_: next((a for a in WORKLOADS if f"_{a}_" in os.path.basename(p_)), None)
+    # a capture of this algorithm's own update first (file name carries _<algo>_), then the untagged ones (DDPG)
+    paths = [p_ for p_ in paths if algo and tag(p_) == algo] + [p_ for p_ in paths if tag(p_) is None]
+    for path in paths:
         try:
             rows = [r for r in csv.reader(open(path)) if r]
             hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
@@ -405,7 +409,7 @@ def run_engine(args):
 
     def tensor_roofline(kernel, substr, mflop, k_ms, k_launches):
         tf = mflop * 1e6 / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-        tr = ncu_traffic_per_launch(substr)
+        tr = ncu_traffic_per_launch(substr, args.algo)
         return {"bound": "tensor", "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
                 "traffic": tr["bytes_per_launch"] if tr else None, "traffic_source": tr["source"] if tr else None,
                 "kernel": kernel, "launches_per_update": k_launches, "us_per_update": k_ms * 1e3,

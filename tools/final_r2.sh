@@ -12,6 +12,17 @@ done
 OPRL_B200_CHAIN=1 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_ddpg_plan_full_chain.json 2>> gpurun_out/r2_bench.err
 OPRL_B200_CHAIN_ACTOR=1 python bench.py --no-cpu-baseline > gpurun_out/r2_bench_ddpg_plan_actor_chain.json 2>> gpurun_out/r2_bench.err
 bash tools/profile_r2.sh r2 > gpurun_out/r2_profile.log 2>&1
+# the wide configurations: launch plan + in-situ stage costs, warm launch list, one --set full pass over a TQC update
+for a in ddpg td3 sac tqc; do
+  OPRL_B200_DUMP_STAGES=1 timeout 300 python tools/stage_profile.py --algo $a > gpurun_out/r2_stage_costs_$a.txt 2> gpurun_out/r2_stage_plan_$a.txt
+done
+for a in sac tqc; do bash tools/gpu_ncu_list.sh $a r2 500 70 > /dev/null 2>&1; done
+ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|gemm_kernel|tqc_loss" -s 560 -c 30 \
+    -o gpurun_out/tqc_r2 -f python bench.py --algo tqc --steps 6 --warmup 4 --no-cpu-baseline > gpurun_out/ncu_tqc.log 2>&1
+M="gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,launch__shared_mem_per_block_dynamic,sm__cycles_active.max,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__throughput.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum"
+ncu -i gpurun_out/tqc_r2.ncu-rep --page raw --csv --metrics $M > gpurun_out/r2_ncu_tqc_update_raw.csv 2>> gpurun_out/ncu_export.log
+rm -f gpurun_out/tqc_r2.ncu-rep
+python tools/sass_summary.py > gpurun_out/r2_sass_kernels.txt 2>&1
 tail -3 gpurun_out/r2_bench.err
 python - <<'PY'
 import json, glob
