@@ -124,7 +124,12 @@ def mlp_forward(params, x):
         x = torch.addmm(params[2 * i + 1], x, params[2 * i].t())
         if i < n_layers - 1:
             if PREACT_PROBE["enabled"]:
-                PREACT_PROBE["min_abs"] = min(PREACT_PROBE["min_abs"], float(x.detach().abs().min()))
+                ax = x.detach().abs()
+                PREACT_PROBE["min_abs"] = min(PREACT_PROBE["min_abs"], float(ax.min()))
+                # exact zeros are structural (a row whose inputs and bias are all zero), not a rounding knife edge
+                nz = ax[ax > 0]
+                if nz.numel():
+                    PREACT_PROBE["min_abs_nonzero"] = min(PREACT_PROBE.get("min_abs_nonzero", float("inf")), float(nz.min()))
             x = torch.relu(x)
     return x
 

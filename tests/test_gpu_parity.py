@@ -173,17 +173,18 @@ def test_host_batch_and_int64_done_match_the_device_path():
         assert torch.equal(results[0][g], results[1][g]), g
 
 
-@pytest.mark.parametrize("name,B", [("ddpg", 1), ("ddpg", 100), ("td3", 257), ("sac", 33)])
+@pytest.mark.parametrize("name,B", [("ddpg", 1), ("ddpg", 100), ("td3", 257), ("sac", 33), ("sac", 1000), ("tqc", 300)])
 def test_odd_batch_sizes_against_the_oracle(name, B):
     """Batch sizes that are not multiples of the 128-row MMA tile (or of anything): fresh seeded
     inputs, the CPU oracle as the checker.  The data seed is advanced until the update is well
-    conditioned (no ReLU pre-activation within 5e-7 of zero, see oracle/gen_golden.py)."""
+    conditioned (no ReLU pre-activation within 5e-7 of zero, see oracle/gen_golden.py).  (sac, 1000) and (tqc, 300)
+    run through the 128 x 64 tiles with ragged rows (launches above one wave of SMs, batch not a multiple of 128)."""
     from oracle import oprl_oracle as O
 
-    fx = load_case({"ddpg": "ddpg_b8", "td3": "td3", "sac": "sac_fixed"}[name])
+    fx = load_case({"ddpg": "ddpg_b8", "td3": "td3", "sac": "sac_fixed", "tqc": "tqc"}[name])
     spec = spec_from_fixture(fx)
     S, A = spec.state_dim, spec.action_dim
-    n_noise = {"ddpg": 0, "td3": 1, "sac": 2}[name]
+    n_noise = {"ddpg": 0, "td3": 1, "sac": 2, "tqc": 2}[name]
     for seed in range(100, 160):
         rng = np.random.default_rng(seed)
         batch = [torch.from_numpy(x) for x in (
@@ -193,13 +194,14 @@ def test_odd_batch_sizes_against_the_oracle(name, B):
         g = torch.Generator().manual_seed(seed)
         noise = [torch.randn(B, A, generator=g) for _ in range(n_noise)]
         orc = oracle_from_fixture(fx)
-        O.PREACT_PROBE.update(enabled=True, min_abs=float("inf"))
+        O.PREACT_PROBE.update(enabled=True, min_abs=float("inf"), min_abs_nonzero=float("inf"))
         ref = orc.update(*batch, noise=noise)
         O.PREACT_PROBE["enabled"] = False
-        if O.PREACT_PROBE["min_abs"] >= 5e-7:
-            break
+        if O.PREACT_PROBE["min_abs_nonzero"] >= 5e-7 or name == "tqc":
+            break  # (TQC: ~3 M hidden pre-activations per update, no seed clears 5e-7 -- element-wise bar below)
     else:
         pytest.skip("no well-conditioned seed found")
+    conditioned = O.PREACT_PROBE["min_abs_nonzero"] >= 5e-7
     algo = make_algo(fx)
     load_initial(algo, oracle_from_fixture(fx))
     for i, nz in enumerate(noise):
@@ -208,10 +210,20 @@ def test_odd_batch_sizes_against_the_oracle(name, B):
     sc = algo.engine.scalars()
     for key in ("critic_loss", "actor_loss"):
         assert abs(sc[key] - ref[key]) <= LOSS_TOL, (key, sc[key], ref[key])
-    sq = 0.0
+    diffs = []
     for key in ("actor", "critic", "critic_target", "actor_target"):
         got = engine_flat(algo, key)
         if got is not None:
-            sq += float(((got.astype(np.float64) - orc.flat(key)) ** 2).sum())
-    print(f"{name} B={B}: param L2 after 1 update vs oracle = {np.sqrt(sq):.3e}")
-    assert np.sqrt(sq) <= PARAM_L2_TOL
+            diffs.append(np.abs(got.astype(np.float64) - orc.flat(key)))
+    d = np.concatenate(diffs)
+    l2 = float(np.sqrt((d ** 2).sum()))
+    print(f"{name} B={B}: param L2 after 1 update vs oracle = {l2:.3e} (max element {d.max():.2e}, conditioned: {conditioned})")
+    if conditioned:
+        assert l2 <= PARAM_L2_TOL
+    else:
+        # a ReLU within rounding noise of zero may flip: at most a handful of elements move by up to 2 * lr, the rest
+        # holds the bar (same criterion as the multi-update fixture check above)
+        outlier = d > 1e-5
+        assert int(outlier.sum()) <= max(8, d.size // 20000), int(outlier.sum())
+        assert d.max() <= 2.5 * 3e-4
+        assert float(np.sqrt((d[~outlier] ** 2).sum())) <= PARAM_L2_TOL
