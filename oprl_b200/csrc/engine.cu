@@ -184,7 +184,7 @@ struct oprl_engine {
   // itself (kernels.cuh publish_state); scalars_enqueue then costs no GPU work.  OPRL_B200_HOST_SCALARS=0:
   // always the D2H copy + event.
   bool host_scalars = true;
-  DevState* h_pub = nullptr;  // pinned [kHostRing]
+  PubSlot* h_pub = nullptr;  // pinned [kHostRing]
   // single-learner engines only: the data-parallel programs keep the validated D2H read-back
   bool publishes() const { return host_scalars && h_pub && cfg.world_size == 1; }
   // Publishing costs the update's last kernel a system-scope fence (~3 us on the chain), so it is a
@@ -1932,9 +1932,9 @@ int oprl_engine_create(const oprl_cfg* cfg, oprl_engine** out) {
   if (const char* v = getenv("OPRL_B200_HOST_SCALARS")) e->host_scalars = atoi(v) != 0;
   if (e->host_scalars) {
     void* hp;
-    CU(cudaHostAlloc(&hp, sizeof(DevState) * kHostRing, cudaHostAllocMapped | cudaHostAllocPortable));
-    memset(hp, 0, sizeof(DevState) * kHostRing);
-    e->h_pub = static_cast<DevState*>(hp);
+    CU(cudaHostAlloc(&hp, sizeof(PubSlot) * kHostRing, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(hp, 0, sizeof(PubSlot) * kHostRing);
+    e->h_pub = static_cast<PubSlot*>(hp);
   }
   if (e->cfg.world_size < 1) e->cfg.world_size = 1;
   CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
@@ -2408,10 +2408,19 @@ int oprl_scalars_wait(oprl_engine* e, int ticket, float* out_host, int n) {
     if (age >= static_cast<unsigned long long>(kHostRing))
       return fail(-1, "scalar ticket expired (%d updates later; ring of %d)", static_cast<int>(age), kHostRing);
     const unsigned long long idx = newest - age;  // index of the update whose scalars are wanted
-    const volatile DevState* slot = e->h_pub + (idx % kHostRing);
+    // sequence-locked record (kernels.cuh publish_state): every 16-byte unit carries the low word of the tick
+    const volatile PubSlot* slot = e->h_pub + (idx % kHostRing);
+    const unsigned int want = static_cast<unsigned int>(idx + 1);
     unsigned long long spins = 0;
     const auto t0 = std::chrono::steady_clock::now();
-    while (slot->tick < idx + 1) {
+    for (;;) {
+      bool ready = true;
+      for (int u = 0; u < kPubUnits; ++u) {
+        const unsigned int got = slot->w[4 * u + 3];
+        if (static_cast<int>(got - want) > 0) return fail(-1, "scalar ticket overwritten by a later update");
+        ready = ready && got == want;
+      }
+      if (ready) break;
       if ((++spins & 4095) == 0) {
         const cudaError_t q = cudaStreamQuery(e->stream);
         if (q != cudaSuccess && q != cudaErrorNotReady) return fail(-2, "CUDA error %s while waiting for scalars", cudaGetErrorString(q));
@@ -2419,11 +2428,17 @@ int oprl_scalars_wait(oprl_engine* e, int ticket, float* out_host, int n) {
           return fail(-1, "timed out waiting for update %llu to publish its scalars", idx);
       }
     }
-    if (slot->tick != idx + 1) return fail(-1, "scalar ticket overwritten by a later update");
     std::atomic_thread_fence(std::memory_order_acquire);
-    float tmp[32];
-    for (int i = 0; i < 32; ++i) tmp[i] = slot->scalars[i];
-    tmp[SC_ALPHA] = slot->alpha;
+    float tmp[36];
+    for (int u = 0; u < kPubUnits; ++u)
+      for (int k = 0; k < 3; ++k) {
+        const unsigned int bits = slot->w[4 * u + k];
+        memcpy(&tmp[3 * u + k], &bits, 4);
+      }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    for (int u = 0; u < kPubUnits; ++u)
+      if (slot->w[4 * u + 3] != want) return fail(-1, "scalar ticket overwritten by a later update");
+    tmp[SC_ALPHA] = tmp[32];
     memcpy(out_host, tmp, sizeof(float) * n);
     return 0;
   }

@@ -33,22 +33,36 @@ struct DevState {
 
 constexpr double kBeta1 = 0.9, kBeta2 = 0.999;
 
-// Host-visible copy of the state block: the last kernel of an update writes DevState into slot
-// (tick - 1) % kHostRing of a pinned, device-mapped ring -- every word but the tick first, a system
-// fence, then the tick as the sequence number the host polls.  Replaces a D2H copy + event per step
-// in loops that read the losses of every update (OPRL_B200_HOST_SCALARS=1).
+// Host-visible copy of the update's scalars: the last kernel of an update writes them into slot (tick - 1) % kHostRing
+// of a pinned, device-mapped ring which the host polls -- no D2H copy, no event, in loops that read the losses of
+// every update (OPRL_B200_HOST_SCALARS=1).  The slot is a sequence-locked record: twelve 16-byte units, each three
+// payload words + the low word of the tick, each written by ONE aligned 16-byte store, so no system-scope fence has
+// to order "payload, then sequence number" (that fence held the update's last kernel ~1.5 us: PCIe round trip); the
+// host accepts the record when every unit carries the tick it waits for and still does after the payload was read.
+// Payload word p: scalars[p] for p < 32, alpha for p = 32, zero above.
 // Call with all threads of one block, after a barrier that orders the block's own writes to *st.
 constexpr int kHostRing = 8;
-__device__ __forceinline__ void publish_state(const DevState* st, DevState* ring, int tid, int nthreads) {
-  if (!ring) return;
+constexpr int kPubUnits = 12;
+struct alignas(256) PubSlot {
+  unsigned int w[64];  // kPubUnits x {payload, payload, payload, tick}
+};
+__device__ __forceinline__ void publish_state(const DevState* st, PubSlot* ring, int tid, int nthreads) {
+  (void)nthreads;
+  if (!ring || tid >= kPubUnits) return;
   const unsigned long long tick = *reinterpret_cast<const volatile unsigned long long*>(&st->tick);
-  DevState* slot = ring + ((tick - 1ull) % kHostRing);
-  const volatile unsigned int* src = reinterpret_cast<const volatile unsigned int*>(st);
-  volatile unsigned int* dst = reinterpret_cast<volatile unsigned int*>(slot);
-  for (int i = 2 + tid; i < static_cast<int>(sizeof(DevState) / 4); i += nthreads) dst[i] = src[i];
-  __threadfence_system();
-  __syncthreads();
-  if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(slot) = tick;
+  PubSlot* slot = ring + ((tick - 1ull) % kHostRing);
+  unsigned int v[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int p = 3 * tid + k;
+    float f = 0.f;
+    if (p < 32) f = *reinterpret_cast<const volatile float*>(&st->scalars[p]);
+    else if (p == 32) f = *reinterpret_cast<const volatile float*>(&st->alpha);
+    v[k] = __float_as_uint(f);
+  }
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"l"(slot->w + 4 * tid), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(static_cast<unsigned int>(tick))
+               : "memory");
 }
 
 // Advance the per-update counters (one thread, at the end of the loss kernel): everything that
@@ -518,7 +532,7 @@ constexpr int kAdamPatchSmem = 2 * 32 * 33 * 4;  // dynamic shared memory of a l
 // from the per-tile partial head dot products the critic forward GEMM left behind (GemmOp::tail_out).
 // A logging scalar only -- nothing on the gradient path waits for it.
 struct LossTail {
-  DevState* pub;      // non-null: this launch is the update's last kernel -- publish_state() to this ring
+  PubSlot* pub;       // non-null: this launch is the update's last kernel -- publish_state() to this ring
   const float* part;  // nullptr = no duty
   const float* b3;
   float* out;

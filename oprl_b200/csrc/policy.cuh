@@ -238,7 +238,7 @@ struct AlphaStep {
   float add;  // SAC: target_entropy ; TQC: 0
   int world;  // data-parallel learners: sum the per-rank shares (runs after the actor Adam's handshake)
   const float* peer_x[kMaxRanks];
-  DevState* pub;  // non-null: publish_state() to this host ring (this is the update's last kernel)
+  PubSlot* pub;  // non-null: publish_state() to this host ring (this is the update's last kernel)
 };
 __device__ __forceinline__ void alpha_step(DevState* st, const AlphaStep& as) {
   float share = 0.f;
