@@ -674,7 +674,8 @@ static void add_critic_head(oprl_engine* e, Builder& b, int stage, int mode, int
   a.counter = reinterpret_cast<unsigned int*>(e->alloc_floats(1 + (blocks + 15) / 16));
   a.alpha_x = alpha_x;
   a.bump_actor = bump_actor ? 1 : 0;
-  const int threads = pad32(H);
+  const int threads = pad32(H) * nq;  // one thread per (critic, hidden unit)
+  if (threads > 512) throw std::runtime_error("critic_hidden too wide for the fused scalar-head kernel");
   const size_t smem = std::max<size_t>(static_cast<size_t>(threads / 32) * 32 + 32, static_cast<size_t>(blocks) * 8) * sizeof(float);
   DevState* st = e->d_state;
   b.stage(stage).add_simt([a, st, blocks, threads, smem](cudaStream_t sm) {

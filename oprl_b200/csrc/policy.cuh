@@ -426,7 +426,7 @@ namespace oprl {
 // dot product per row: running it -- and the first backward step it seeds -- as padded tensor-core
 // GEMM stages costs three launches of the dependency chain for ~0.1 % of the FLOPs.  This kernel
 // does the whole neighbourhood of the loss in one launch, one block per 8 batch rows, one thread
-// per hidden unit:
+// per (critic, hidden unit):
 //   mode 0 (critic step; ddpg.py:94-98, td3.py:95-112, sac.py:96-105)
 //     q_i = h2_i . w3_i + b3_i ; qn_i likewise from the target nets ; y = r + (1-d) gamma (min_i qn_i - alpha logp')
 //     L = sum_i mean (q_i - y)^2 ; dq_i = (2/count)(q_i - y)
@@ -461,17 +461,23 @@ struct CriticHeadArgs {
   int bump_actor;
 };
 constexpr int kHeadRows = 8;
-__global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant__ CriticHeadArgs a, DevState* st) {
+// One thread per (critic, hidden unit): blockDim.x = pad32(H) * nq.  With both critics in one thread (round 1) TD3's
+// head stage cost 14.3 us against 7.4 us for DDPG's single critic: twice the loads, shuffles and reduction round
+// trips in series.  The critics meet only in the 32-entry result block in shared memory (min over the targets).
+__global__ void __launch_bounds__(512) critic_head_kernel(const __grid_constant__ CriticHeadArgs a, DevState* st) {
   ptx::pdl_trigger();
   ptx::pdl_wait();
-  extern __shared__ float sh[];  // [warps][32] dot partials, then [8][4] results
-  const int n = threadIdx.x;     // hidden unit
-  const int lane = n & 31, warp = n >> 5, nwarps = blockDim.x >> 5;
+  extern __shared__ float sh[];  // [warps][16] dot partials, then [4][8] results
+  const int tid = threadIdx.x;
+  const int Hp = blockDim.x / a.nq;  // threads per critic (a multiple of 32)
+  const int ci = tid / Hp;           // this thread's critic
+  const int n = tid - ci * Hp;       // hidden unit
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, wpc = Hp >> 5;
   const int m0 = blockIdx.x * kHeadRows;
   const bool live = n < a.H;
   // Nothing in this kernel reads the step counters / tick, and everything that consumed the old
   // values ran in earlier launches: advance them first, off the critical tail.
-  if (a.mode == 0 && blockIdx.x == 0 && n == 0) bump_counters(st, a.bump_actor);
+  if (a.mode == 0 && blockIdx.x == 0 && tid == 0) bump_counters(st, a.bump_actor);
   // per-row inputs of the loss, fetched now so that their latency overlaps the dot products
   float rr[kHeadRows], dd[kHeadRows], lp[kHeadRows];
 #pragma unroll
@@ -488,30 +494,25 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
     b3v[i] = a.b3[i][0];
     if (a.mode == 0) b3tv[i] = a.b3t[i][0];
   }
-  // ---- phase 1: the dot products of this block's 8 rows
-  float hv[2][kHeadRows];  // online hidden activations of this thread's unit (kept for phase 2)
-  float w3v[2] = {0.f, 0.f};
-  float prod[4][kHeadRows];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    if (i >= a.nq) break;
-    w3v[i] = live ? a.w3[i][n] : 0.f;
-    const float w3t = (a.mode == 0 && live) ? a.w3t[i][n] : 0.f;
+  // ---- phase 1: the dot products of this block's 8 rows, this thread's critic (online, and target in the critic step)
+  float hv[kHeadRows];  // online hidden activations of this thread's unit (kept for phase 2)
+  float prod[2][kHeadRows];
+  const float w3v = live ? a.w3[ci][n] : 0.f;
+  {
+    const float w3t = (a.mode == 0 && live) ? a.w3t[ci][n] : 0.f;
 #pragma unroll
     for (int r = 0; r < kHeadRows; ++r) {
       const size_t off = ct_index(a.h_rows, m0 + r, n);
-      const float h = live ? a.h2[i][off] : 0.f;
-      hv[i][r] = h;
-      prod[i][r] = h * w3v[i];
-      if (a.mode == 0) prod[2 + i][r] = live ? a.h2t[i][off] * w3t : 0.f;
+      const float h = live ? a.h2[ci][off] : 0.f;
+      hv[r] = h;
+      prod[0][r] = h * w3v;
+      prod[1][r] = (a.mode == 0 && live) ? a.h2t[ci][off] * w3t : 0.f;
     }
   }
-  float* red = sh;  // [nwarps][32]
+  float* red = sh;  // [nwarps][16]: [online | target][row]
 #pragma unroll
-  for (int s = 0; s < 4; ++s) {
-    // streams 0-1: online critics, 2-3: target critics (critic step only)
-    const bool valid = (s < 2) ? (s < a.nq) : (a.mode == 0 && s - 2 < a.nq);
-    if (!valid) continue;
+  for (int s = 0; s < 2; ++s) {
+    if (s == 1 && a.mode != 0) continue;
 #pragma unroll
     for (int r = 0; r < kHeadRows; ++r) {
       float x = prod[s][r];
@@ -520,15 +521,19 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
       x += __shfl_xor_sync(0xffffffffu, x, 4);
       x += __shfl_xor_sync(0xffffffffu, x, 2);
       x += __shfl_xor_sync(0xffffffffu, x, 1);
-      if (lane == 0) red[warp * 32 + s * kHeadRows + r] = x;
+      if (lane == 0) red[warp * 16 + s * kHeadRows + r] = x;
     }
   }
   __syncthreads();
-  float* res = sh + nwarps * 32;  // [4][8] dot products, then dq[2][8]
-  if (n < 32) {
+  // res[(2 * target + critic) * 8 + row]: streams 0-1 online critics, 2-3 target critics (critic step only)
+  float* res = sh + nwarps * 16;
+  if (tid < 32) {
+    const int strm = tid >> 3, r = tid & 7;
+    const int c = strm & 1, tg = strm >> 1;
     float x = 0.f;
-    for (int wv = 0; wv < nwarps; ++wv) x += red[wv * 32 + n];
-    res[n] = x;
+    if (c < a.nq && (tg == 0 || a.mode == 0))
+      for (int wv = c * wpc; wv < (c + 1) * wpc; ++wv) x += red[wv * 16 + tg * kHeadRows + r];
+    res[tid] = x;
   }
   __syncthreads();
   // ---- per-row loss terms and seeds (every thread computes them redundantly: no extra barrier)
@@ -572,33 +577,32 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
       if (a.logp) lpsum += lp[r];
     }
   }
-  // ---- phase 2: dz2 = dq w3^T (.) relu'(h2), column sums
+  // ---- phase 2: dz2 = dq w3^T (.) relu'(h2), column sums -- this thread's critic
   const int W = a.nq * 2 * a.H + 8;
   float* mypart = a.part + static_cast<size_t>(blockIdx.x) * W;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    if (i >= a.nq) break;
+  {
     float gw = 0.f, gb = 0.f;
     float dzv[kHeadRows];
 #pragma unroll
     for (int r = 0; r < kHeadRows; ++r) {
-      const float dz = hv[i][r] > 0.f ? dq[i][r] * w3v[i] : 0.f;
+      const float dqr = ci == 0 ? dq[0][r] : dq[1][r];
+      const float dz = hv[r] > 0.f ? dqr * w3v : 0.f;
       dzv[r] = dz;
-      gw = fmaf(dq[i][r], hv[i][r], gw);
+      gw = fmaf(dqr, hv[r], gw);
       gb += dz;
-      if (live) a.dz2[i][ct_index(a.h_rows, m0 + r, n)] = dz;
+      if (live) a.dz2[ci][ct_index(a.h_rows, m0 + r, n)] = dz;
     }
-    if (live && a.dz2T[i]) {
-      float* dst = a.dz2T[i] + ct_index(a.dzT_rows, n, m0);
+    if (live && a.dz2T[ci]) {
+      float* dst = a.dz2T[ci] + ct_index(a.dzT_rows, n, m0);
       *reinterpret_cast<float4*>(dst) = make_float4(dzv[0], dzv[1], dzv[2], dzv[3]);
       *reinterpret_cast<float4*>(dst + 32) = make_float4(dzv[4], dzv[5], dzv[6], dzv[7]);
     }
     if (live && a.mode == 0) {
-      mypart[i * 2 * a.H + n] = gw;
-      mypart[i * 2 * a.H + a.H + n] = gb;
+      mypart[ci * 2 * a.H + n] = gw;
+      mypart[ci * 2 * a.H + a.H + n] = gb;
     }
   }
-  if (n == 0) {
+  if (tid == 0) {
     float* tail = mypart + a.nq * 2 * a.H;
     tail[0] = loss; tail[1] = qsum; tail[2] = ysum; tail[3] = esum;
     tail[4] = dsum[0]; tail[5] = dsum[1]; tail[6] = lpsum;
@@ -616,12 +620,12 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
     // block pulling all of [gridDim.x][W] through its SM (528 KB at batch 1024) was 15 us of this kernel.
     const unsigned int grp = blockIdx.x >> 4, ngrp = (gridDim.x + 15u) >> 4;
     const unsigned int gsize = min(16u, gridDim.x - grp * 16u);
-    if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter + 1 + grp, 1u);
+    if (tid == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter + 1 + grp, 1u);
     __syncthreads();
     if (ticket != gsize - 1) return;
     const float* gp = a.part + static_cast<size_t>(grp) * 16 * W;
     float* dst = a.part2 + static_cast<size_t>(grp) * W;
-    for (int c = n; c < W; c += blockDim.x) {
+    for (int c = tid; c < W; c += blockDim.x) {
       float tv[16];
 #pragma unroll
       for (int k = 0; k < 16; ++k) tv[k] = static_cast<unsigned int>(k) < gsize ? __ldcg(gp + static_cast<size_t>(k) * W + c) : 0.f;
@@ -630,21 +634,21 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
       for (int k = 0; k < 16; ++k) sum += tv[k];
       dst[c] = sum;
     }
-    if (n == 0) a.counter[1 + grp] = 0u;
+    if (tid == 0) a.counter[1 + grp] = 0u;
     __syncthreads();
-    if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
+    if (tid == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
     __syncthreads();
     if (ticket != ngrp - 1) return;
     part = a.part2;
     nparts = ngrp;
   } else {
-    if (n == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
+    if (tid == 0) ticket = ptx::atom_add_acq_rel_gpu(a.counter, 1u);
     __syncthreads();
     if (ticket != gridDim.x - 1) return;
   }
   // every load of the reduction is issued before the first add: the per-block scalar tails (warp 0:
   // lane = block, 7 values each) and, in the critic step, the head-weight / bias-gradient partials
-  // of this thread's hidden unit (batches of sixteen blocks, two critics)
+  // of this thread's (critic, hidden unit) (batches of sixteen blocks)
   float tl[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const unsigned int nb32 = (nparts + 31) / 32;
   if (warp == 0 && nb32 == 1) {
@@ -655,27 +659,25 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
     }
   }
   if (a.mode == 0 && live) {
-    for (int i = 0; i < a.nq; ++i) {
-      // loads batched sixteen blocks at a time (independent L2 round trips), adds in block order
-      float gw = 0.f, gb = 0.f;
-      for (unsigned int b0 = 0; b0 < nparts; b0 += 16) {
-        float tw[16], tb[16];
+    // loads batched sixteen blocks at a time (independent L2 round trips), adds in block order
+    float gw = 0.f, gb = 0.f;
+    for (unsigned int b0 = 0; b0 < nparts; b0 += 16) {
+      float tw[16], tb[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const bool ok = b0 + k < nparts;
-          const float* p = part + static_cast<size_t>(ok ? b0 + k : 0) * W + i * 2 * a.H;
-          tw[k] = ok ? __ldcg(p + n) : 0.f;
-          tb[k] = ok ? __ldcg(p + a.H + n) : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          gw += tw[k];
-          gb += tb[k];
-        }
+      for (int k = 0; k < 16; ++k) {
+        const bool ok = b0 + k < nparts;
+        const float* p = part + static_cast<size_t>(ok ? b0 + k : 0) * W + ci * 2 * a.H;
+        tw[k] = ok ? __ldcg(p + n) : 0.f;
+        tb[k] = ok ? __ldcg(p + a.H + n) : 0.f;
       }
-      a.gw3[i][n] = gw;
-      a.gb2[i][n] = gb;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        gw += tw[k];
+        gb += tb[k];
+      }
     }
+    a.gw3[ci][n] = gw;
+    a.gb2[ci][n] = gb;
   }
   float t[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (nb32 == 1) {
@@ -690,16 +692,16 @@ __global__ void __launch_bounds__(256) critic_head_kernel(const __grid_constant_
       }
     }
   } else {
-    // more blocks (batch > 256): gathered by (block, k) threads in parallel, summed in block order
+    // more parts: gathered by (block, k) threads in parallel, summed in block order
     __syncthreads();
-    for (unsigned int idx = n; idx < nparts * 8; idx += blockDim.x)
+    for (unsigned int idx = tid; idx < nparts * 8; idx += blockDim.x)
       sh[idx] = __ldcg(part + static_cast<size_t>(idx >> 3) * W + a.nq * 2 * a.H + (idx & 7));
     __syncthreads();
-    if (n == 0)
+    if (tid == 0)
       for (unsigned int b = 0; b < nparts; ++b)
         for (int k = 0; k < 7; ++k) t[k] += sh[b * 8 + k];
   }
-  if (n == 0) {
+  if (tid == 0) {
     if (a.mode == 0) {
       st->scalars[SC_CRITIC_LOSS] = t[0] * a.inv_count;
       st->scalars[SC_Q_MEAN] = t[1] * a.inv_count;
