@@ -96,6 +96,8 @@ struct Layer {
   size_t w_off, b_off;  // float offsets inside the group's flat arena
   int split, off_lo, off_hi;  // reference input column j -> tiled column (layer 0 only)
   TM W, WT, TW;    // tiled operand copies: W [Np x Kp], WT [Kp x Np], target W [Np x Kp]
+  float* dw0_part = nullptr;  // layer 0: [kDeferMaxMt][Np][Kp] per-M-tile partials of the fused dW_0 (shared by all programs)
+  int dw0_ones = -1;          // tiled pad column that carries the bias gradient in those partials (-1: none, no deferral)
 };
 struct Net {
   std::vector<Layer> L;
@@ -304,6 +306,10 @@ static void build_group(oprl_engine* e, Group& g, int n_nets, const std::vector<
         ly.split = S;
         ly.off_lo = A4;
         ly.off_hi = 0;  // critic: reference column S + j -> tiled column j
+        // deferred fused dW_0 (GemmOp::dw0_defer): the partials live here, whatever program produced them
+        const int A = e->cfg.action_dim;
+        ly.dw0_ones = (A4 > A) ? A : (ly.Kp > A4 + S ? A4 + S : -1);
+        if (ly.dw0_ones >= 0) ly.dw0_part = e->alloc_floats(static_cast<size_t>(kDeferMaxMt) * ly.Np * ly.Kp);
       } else {
         ly.Kp = pad32(ly.in);
         ly.split = ly.in;
@@ -331,11 +337,6 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
     for (auto& ly : net.L) {
       AdamSeg w;
       memset(&w, 0, sizeof(w));
-      w.theta = g.theta + ly.w_off;
-      w.grad = g.grad + ly.w_off;
-      w.m = g.m + ly.w_off;
-      w.v = g.v + ly.w_off;
-      w.target = g.target ? g.target + ly.w_off : nullptr;
       w.w = ly.W.p;
       w.wt = ly.WT.p;
       w.tw = g.target ? ly.TW.p : nullptr;
@@ -347,19 +348,20 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
       w.split = ly.split; w.off_lo = ly.off_lo; w.off_hi = ly.off_hi;
       w.opt = opt;
       w.goff = static_cast<int>(ly.w_off);
+      w.gpart = ly.dw0_part;
+      w.gp_ones = -1;
       segs.push_back(w);
       AdamSeg b;
       memset(&b, 0, sizeof(b));
-      b.theta = g.theta + ly.b_off;
-      b.grad = g.grad + ly.b_off;
-      b.m = g.m + ly.b_off;
-      b.v = g.v + ly.b_off;
-      b.target = g.target ? g.target + ly.b_off : nullptr;
       b.n = ly.out;
       b.rows = 1;
       b.cols = ly.out;
       b.opt = opt;
       b.goff = static_cast<int>(ly.b_off);
+      b.gpart = ly.dw0_part;
+      b.gp_ones = ly.dw0_ones;
+      b.w_rows = ly.Np;   // (no tiled copies of a bias: only the deferred-gradient path reads these two)
+      b.wt_rows = ly.Kp;
       segs.push_back(b);
       g.max_seg = std::max(g.max_seg, static_cast<size_t>(w.n));
     }
@@ -431,19 +433,20 @@ static CommArgs make_comm(oprl_engine* e, int group, bool exit_barrier) {
 }
 
 static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, bool exit_barrier = false,
-                        LossTail lt = LossTail{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f}) {
+                        LossTail lt = LossTail{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f}, int gp_mt = 0) {
   // one element per thread: a single load -> compute -> store round trip (which matters most when
   // the gradient loads cross NVLink)
   dim3 grid(g.n_blocks);
   const int group = (&g == &e->grp[OPRL_NET_ACTOR]) ? 0 : 1;
+  const AdamArenas ar{g.theta, g.grad, g.m, g.v, g.target};
   if (g.adam_smem)
     launch_k(adam_kernel<true>, grid, dim3(kAdamThreads), static_cast<size_t>(g.adam_smem), st,
-             static_cast<const AdamSeg*>(g.d_segs), static_cast<const int2*>(g.d_blocks), make_hyper(e->cfg),
-             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt);
+             static_cast<const AdamSeg*>(g.d_segs), static_cast<const int2*>(g.d_blocks), ar, make_hyper(e->cfg),
+             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt, gp_mt);
   else
     launch_k(adam_kernel<false>, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs),
-             static_cast<const int2*>(g.d_blocks), make_hyper(e->cfg),
-             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt);
+             static_cast<const int2*>(g.d_blocks), ar, make_hyper(e->cfg),
+             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt, gp_mt);
 }
 
 // --------------------------------------------------------------- program builder
@@ -453,6 +456,7 @@ struct Builder {
   Program* p;
   int passes;
   int seg = 0;
+  int defer_mt[2] = {0, 0};  // M tiles of the deferred layer-0 gradients of this program (0 actor, 1 critic; 0 = not deferred)
 
   Stage& stage(int i) {
     while (static_cast<int>(p->stages.size()) <= i) {
@@ -603,6 +607,17 @@ struct Builder {
             o.colsum = nullptr;
             o.colsum_out = nullptr;
             o.colsum_cnt = nullptr;
+          }
+          // single learner: leave the sum over M tiles to the Adam kernel (no arrival ticket, no last-CTA pass on
+          // the chain); data-parallel peers read the gradient ARENA, so there the epilogue finishes the job
+          static const bool defer_on = !(getenv("OPRL_B200_DW0_DEFER") && atoi(getenv("OPRL_B200_DW0_DEFER")) == 0);
+          if (defer_on && e->cfg.world_size == 1 && !e->comm.connected && lp.dw0_part && o.dw0_ones == lp.dw0_ones &&
+              Bp / kBM <= kDeferMaxMt) {
+            o.dw0_part = lp.dw0_part;
+            o.dw0_defer = 1;
+            defer_mt[is_actor ? 0 : 1] = Bp / kBM;
+          } else {
+            defer_mt[is_actor ? 0 : 1] = 0;
           }
           dw0_fused = true;
         }
@@ -1092,7 +1107,7 @@ static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* 
     const bool exit_barrier = !do_actor;
     LossTail ltc{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
     if (!do_actor && (p->flags & kFlagPublish)) ltc.pub = e->h_pub;
-    b.stage(2).add_simt([e, &gc, mode, exit_barrier, ltc](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc); });
+    b.stage(2).add_simt([e, &gc, mode, exit_barrier, ltc, gmt = b.defer_mt[1]](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc, gmt); });
   }
   if (!do_actor) return;
   add_chain_actor_step(e, b, w, p, 3, a_rm, a_h0T, a_h1T);
@@ -1100,7 +1115,7 @@ static void build_chain_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* 
   {
     LossTail lt{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
     lt.pub = (p->flags & kFlagPublish) ? e->h_pub : nullptr;
-    b.stage(5).add_simt([e, &ga, lt](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt); });
+    b.stage(5).add_simt([e, &ga, lt, gmt = b.defer_mt[0]](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt, gmt); });
   }
 }
 
@@ -1220,7 +1235,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     const bool exit_barrier = !do_actor;  // no actor handshake follows to fence the critic gradients
     LossTail ltc{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
     if (!do_actor && (p->flags & kFlagPublish)) ltc.pub = e->h_pub;  // TD3 critic-only update: this is its last kernel
-    b.stage(s).add_simt([e, &gc, mode, exit_barrier, ltc](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc); });
+    b.stage(s).add_simt([e, &gc, mode, exit_barrier, ltc, gmt = b.defer_mt[1]](cudaStream_t sm) { launch_adam(e, gc, mode, sm, exit_barrier, ltc, gmt); });
     ++s;
   }
   if (do_actor && use_chain_actor(e)) {
@@ -1232,7 +1247,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     b.seg = 2;
     LossTail lt{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f};
     lt.pub = (p->flags & kFlagPublish) ? e->h_pub : nullptr;
-    b.stage(s).add_simt([e, &ga, lt](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt); });
+    b.stage(s).add_simt([e, &ga, lt, gmt = b.defer_mt[0]](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt, gmt); });
     return;
   }
   if (do_actor) {
@@ -1314,7 +1329,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     s = b.backward(s, ga.nets[0], ga.grad, p_a, dza, dzaT, w->XT, true, true, nullptr);
     // actor Adam + Polyak + re-tiling   (ddpg.py:107,79-84 ; td3.py:141,83-84)
     b.seg = 2;
-    b.stage(s).add_simt([e, &ga, lt](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt); });
+    b.stage(s).add_simt([e, &ga, lt, gmt = b.defer_mt[0]](cudaStream_t sm) { launch_adam(e, ga, 1 | 2 | 4 | 8, sm, false, lt, gmt); });
     ++s;
   }
 }
@@ -1459,7 +1474,9 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   b.seg = 1;
   // critic Adam + Polyak (sac.py:85 soft_update at the end of update() touches nothing the actor
   // step reads; tqc.py:154-159 does it right here) + re-tiling
-  b.stage(s).add_simt([e, &gc](cudaStream_t sm) { launch_adam(e, gc, 1 | 2 | 4 | 8, sm); });
+  b.stage(s).add_simt([e, &gc, gmt = b.defer_mt[1]](cudaStream_t sm) {
+    launch_adam(e, gc, 1 | 2 | 4 | 8, sm, false, LossTail{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f}, gmt);
+  });
   ++s;
   // ---- actor step (its forward + sampling head already ran beside the critic step) ------
   // critics at (s, pi(s)) with the just-updated weights
@@ -1545,8 +1562,8 @@ static void build_sac_tqc(oprl_engine* e, oprl_engine::Work* w, Program* p) {
   al.world = e->comm.connected ? e->comm.world : 1;
   for (int r = 0; r < al.world && e->comm.connected; ++r) al.peer_x[r] = e->comm.peer_grad[0][r] + ga.floats;
   al.pub = (p->flags & kFlagPublish) ? e->h_pub : nullptr;  // alpha_step_kernel is the last kernel of a SAC / TQC update
-  b.stage(s).add_simt([e, &ga, al, st](cudaStream_t sm) {
-    launch_adam(e, ga, 1 | 4, sm);
+  b.stage(s).add_simt([e, &ga, al, st, gmt = b.defer_mt[0]](cudaStream_t sm) {
+    launch_adam(e, ga, 1 | 4, sm, false, LossTail{nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0.f}, gmt);
     launch_k(alpha_step_kernel, dim3(1), dim3(32), 0, sm, st, al);
   }, 2);
   ++s;

@@ -132,6 +132,10 @@ struct GemmOp {
   // read as 1.0, so P[n][dw0_ones] = sum_m D(m, n) = db_0[n]; it is stored to dw0_bias_out[n].
   int dw0_ones;
   float* dw0_bias_out;
+  // dw0_defer: stop after the per-M-tile partials are stored -- the Adam kernel adds them (same order) when it
+  // fetches the gradient, so the arrival ticket and the last CTA's reduction leave the update's critical path
+  // (requires dw0_ones >= 0: the bias gradient rides in the same partials)
+  int dw0_defer;
   int passes;   // 3 = 3xTF32 (fp32-accurate), 1 = single tf32 pass
   int group;    // K chunks per hi*hi accumulator (gemm_finalize)
   int n_big;    // number of hi*hi accumulators, <= 7
@@ -881,9 +885,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
           // (the next chunk's Xs stores are ordered behind every warp's reads by the two barriers above)
         }
         // deterministic cross-CTA totals (dW_0 and, if present, the bias column sums): the last M tile
-        // to arrive adds the per-tile partials in tile order
+        // to arrive adds the per-tile partials in tile order -- unless the consumer does (dw0_defer)
         const int mtiles = o.M / kBM;
         if (prof && tid == 64) prof[14] = clock64();
+        if (o.dw0_defer) continue;
         asm volatile("bar.sync 2, 256;\n" ::: "memory");
         if (te == 0)
           *last_flag = (ptx::atom_add_acq_rel_gpu(o.dw0_cnt + nt, 1u) == static_cast<unsigned int>(mtiles - 1)) ? 1u : 0u;

@@ -460,21 +460,33 @@ __global__ void __launch_bounds__(kTdThreads) td_kernel(TdArgs a, DevState* st) 
 // Polyak loops (ddpg.py:72-84, nn_functions.py:5-10).  One pass over
 // [theta, g, m, v, theta_target]; also refreshes the CT32 hi/lo operand copies
 // (W and W^T, target W) that the GEMM kernel consumes (plain fp32; the GEMM splits to tf32).
+// One tensor of a parameter group.  The five arenas of a group (theta, grad, m, v, target) share one layout, so a
+// segment carries its element offset (`goff`) and the kernel gets the arena bases as a parameter (AdamArenas, constant
+// bank): five pointers fewer in the registers of every thread than one pointer per array.
 struct AdamSeg {
-  float* theta;
-  const float* grad;
-  float* m;
-  float* v;
-  float* target;  // nullable
   float* w;   // tiled [rows_pad x cols_pad] (nullable for biases)
   float* wt;  // tiled transposed (nullable)
   float* tw;  // tiled target weights (nullable)
-  int w_rows, wt_rows;   // padded row counts of the tiled copies
+  // Deferred layer-0 gradient (GemmOp::dw0_defer): when the launch says so (gp_mt > 0) the gradient of element
+  // (r, c) of this tensor is the sum over M tiles mt < gp_mt of gpart[mt * w_rows * wt_rows + r * wt_rows + c], c = the
+  // tiled column of the element (weights) or gp_ones (the bias, whose gradient rides in a pad column of the same
+  // product).  nullptr: always read the gradient arena.
+  const float* gpart;
+  int gp_ones;
+  int w_rows, wt_rows;   // padded row counts of the tiled copies W [w_rows x wt_rows], W^T [wt_rows x w_rows]
   int n, rows, cols;     // row-major [rows x cols]
   int split, off_lo, off_hi;  // tiled col = j < split ? j + off_lo : j - split + off_hi
   int opt;                    // 0 actor, 1 critic
-  int goff;                   // element offset of this tensor inside the group's gradient arena
+  int goff;                   // element offset of this tensor inside the group's arenas
 };
+struct AdamArenas {
+  float* theta;
+  float* grad;
+  float* m;
+  float* v;
+  float* target;  // nullable
+};
+constexpr int kDeferMaxMt = 8;  // M tiles (of 128 batch rows) a deferred layer-0 gradient may have
 
 // ---- fused gradient all-reduce (data-parallel learners on one NVLink domain) ----------------
 // Every rank maps every other rank's gradient arena and flag block (CUDA IPC).  The Adam kernel
@@ -545,8 +557,8 @@ struct LossTail {
 // update there (measured A/B on one box), so it is kept out of their kernel.
 template <bool kPatch>
 __global__ void __launch_bounds__(kAdamThreads)
-    adam_kernel(const AdamSeg* segs, const int2* blocks, AdamHyper hp, const DevState* st, int mode,
-                const __grid_constant__ CommArgs cm, const LossTail lt) {
+    adam_kernel(const AdamSeg* segs, const int2* blocks, const __grid_constant__ AdamArenas ar, AdamHyper hp,
+                const DevState* st, int mode, const __grid_constant__ CommArgs cm, const LossTail lt, int gp_mt) {
   ptx::pdl_trigger();
   // block -> (tensor, first element): one block per 256 consecutive elements of one tensor, so the
   // grid holds no idle blocks (a [6] bias does not get the grid width of a [256 x 256] weight)
@@ -568,7 +580,7 @@ __global__ void __launch_bounds__(kAdamThreads)
   const float s_bc2_sqrt = st->bc2_sqrt[sg.opt];
   // one element: all-reduce (rank order) -> Adam -> Polyak; returns the new online / target values
   auto element = [&](int i, float& p, float& tp) {
-    p = sg.theta[i];
+    p = ar.theta[sg.goff + i];
     if (mode & 1) {
       float g;
       if (reduce) {
@@ -581,25 +593,48 @@ __global__ void __launch_bounds__(kAdamThreads)
 #pragma unroll
         for (int r = 0; r < kMaxRanks; ++r)
           if (r < cm.world) g += gr[r];
+      } else if (gp_mt > 0 && sg.gpart) {
+        // layer-0 gradient left as per-M-tile partials by the fused GEMM epilogue: add them here, in tile order
+        // (what the epilogue's last CTA did behind an arrival ticket), and keep the arena complete
+        int r = i, c = sg.gp_ones;
+        if (c < 0) {
+          r = i / sg.cols;
+          const int j = i - r * sg.cols;
+          c = j < sg.split ? j + sg.off_lo : j - sg.split + sg.off_hi;
+        }
+        const float* pp = sg.gpart + static_cast<size_t>(r) * sg.wt_rows + c;
+        const size_t stride = static_cast<size_t>(sg.w_rows) * sg.wt_rows;
+        g = 0.f;
+        for (int t = 0; t < gp_mt; t += 4) {  // four tiles in flight (a 256-row batch has two, 1024 rows eight)
+          const float p0 = __ldcg(pp + t * stride);
+          const float p1 = t + 1 < gp_mt ? __ldcg(pp + (t + 1) * stride) : 0.f;
+          const float p2 = t + 2 < gp_mt ? __ldcg(pp + (t + 2) * stride) : 0.f;
+          const float p3 = t + 3 < gp_mt ? __ldcg(pp + (t + 3) * stride) : 0.f;
+          g += p0;
+          g += p1;
+          g += p2;
+          g += p3;
+        }
+        ar.grad[sg.goff + i] = g;
       } else {
-        g = sg.grad[i];
+        g = ar.grad[sg.goff + i];
       }
-      float m = sg.m[i];
-      float v = sg.v[i];
+      float m = ar.m[sg.goff + i];
+      float v = ar.v[sg.goff + i];
       m = fmaf(hp.w1, g - m, m);                              // exp_avg.lerp_(grad, 1 - beta1)
       v = __fadd_rn(__fmul_rn(v, hp.beta2f), __fmul_rn(__fmul_rn(hp.w2, g), g));  // mul_().addcmul_()
       const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s_bc2_sqrt), hp.eps);
       p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-s_step_size, m), denom));  // addcdiv_: p + (value*m)/denom
-      sg.m[i] = m;
-      sg.v[i] = v;
-      sg.theta[i] = p;
+      ar.m[sg.goff + i] = m;
+      ar.v[sg.goff + i] = v;
+      ar.theta[sg.goff + i] = p;
     }
     tp = 0.f;
-    if (sg.target) {
-      tp = sg.target[i];
+    if (ar.target) {
+      tp = ar.target[sg.goff + i];
       if (mode & 2) {
         tp = __fadd_rn(__fmul_rn(hp.tau, p), __fmul_rn(hp.one_minus_tau, tp));
-        sg.target[i] = tp;
+        ar.target[sg.goff + i] = tp;
       }
     }
   };
@@ -640,11 +675,11 @@ __global__ void __launch_bounds__(kAdamThreads)
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int i = (r0 + wrp + 8 * q) * sg.cols + c0 + lane;
-      ep[q] = sg.theta[i];
-      et[q] = sg.target ? sg.target[i] : 0.f;
+      ep[q] = ar.theta[sg.goff + i];
+      et[q] = ar.target ? ar.target[sg.goff + i] : 0.f;
       if (mode & 1) {
-        em[q] = sg.m[i];
-        ev[q] = sg.v[i];
+        em[q] = ar.m[sg.goff + i];
+        ev[q] = ar.v[sg.goff + i];
         if (reduce) {
           float gr[kMaxRanks];
 #pragma unroll
@@ -655,7 +690,7 @@ __global__ void __launch_bounds__(kAdamThreads)
             if (r < cm.world) g += gr[r];
           eg[q] = g;
         } else {
-          eg[q] = sg.grad[i];
+          eg[q] = ar.grad[sg.goff + i];
         }
       }
     }
@@ -670,13 +705,13 @@ __global__ void __launch_bounds__(kAdamThreads)
         const float v = __fadd_rn(__fmul_rn(ev[q], hp.beta2f), __fmul_rn(__fmul_rn(hp.w2, g), g));
         const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(v), s_bc2_sqrt), hp.eps);
         p = __fadd_rn(p, __fdiv_rn(__fmul_rn(-s_step_size, m), denom));
-        sg.m[i] = m;
-        sg.v[i] = v;
-        sg.theta[i] = p;
+        ar.m[sg.goff + i] = m;
+        ar.v[sg.goff + i] = v;
+        ar.theta[sg.goff + i] = p;
       }
-      if (sg.target && (mode & 2)) {
+      if (ar.target && (mode & 2)) {
         tp = __fadd_rn(__fmul_rn(hp.tau, p), __fmul_rn(hp.one_minus_tau, tp));
-        sg.target[i] = tp;
+        ar.target[sg.goff + i] = tp;
       }
       pp[rr][lane] = p;
       pt[rr][lane] = tp;
