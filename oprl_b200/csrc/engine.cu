@@ -97,6 +97,8 @@ struct Layer {
   int split, off_lo, off_hi;  // reference input column j -> tiled column (layer 0 only)
   TM W, WT, TW;    // tiled operand copies: W [Np x Kp], WT [Kp x Np], target W [Np x Kp]
   float* dw0_part = nullptr;  // layer 0: [kDeferMaxMt][Np][Kp] per-M-tile partials of the fused dW_0 (shared by all programs)
+  float* dw0_part_own = nullptr;  // ... the engine's own buffer; under the fused data-parallel path dw0_part points
+  size_t dw0_part_off = 0;        // dw0_part_off floats into the exported gradient arena instead (peers read it)
   int dw0_ones = -1;          // tiled pad column that carries the bias gradient in those partials (-1: none, no deferral)
 };
 struct Net {
@@ -105,6 +107,7 @@ struct Net {
 struct Group {  // actor (1 net) or critic (n_critics nets) -- one flat arena, one Adam
   std::vector<Net> nets;
   size_t floats = 0;
+  size_t part_floats = 0;  // deferred layer-0 gradient partials of all nets (appended to the EXPORTED gradient arena)
   float *theta = nullptr, *grad = nullptr, *m = nullptr, *v = nullptr, *target = nullptr;
   bool want_target = false;
   AdamSeg* d_segs = nullptr;
@@ -309,7 +312,11 @@ static void build_group(oprl_engine* e, Group& g, int n_nets, const std::vector<
         // deferred fused dW_0 (GemmOp::dw0_defer): the partials live here, whatever program produced them
         const int A = e->cfg.action_dim;
         ly.dw0_ones = (A4 > A) ? A : (ly.Kp > A4 + S ? A4 + S : -1);
-        if (ly.dw0_ones >= 0) ly.dw0_part = e->alloc_floats(static_cast<size_t>(kDeferMaxMt) * ly.Np * ly.Kp);
+        if (ly.dw0_ones >= 0) {
+          ly.dw0_part = ly.dw0_part_own = e->alloc_floats(static_cast<size_t>(kDeferMaxMt) * ly.Np * ly.Kp);
+          ly.dw0_part_off = g.part_floats;  // (relative to the end of the arena proper + its tail)
+          g.part_floats += static_cast<size_t>(kDeferMaxMt) * ly.Np * ly.Kp;
+        }
       } else {
         ly.Kp = pad32(ly.in);
         ly.split = ly.in;
@@ -349,6 +356,7 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
       w.opt = opt;
       w.goff = static_cast<int>(ly.w_off);
       w.gpart = ly.dw0_part;
+      w.gp_off = static_cast<int>(g.floats + OPRL_GRAD_TAIL + ly.dw0_part_off);
       w.gp_ones = -1;
       segs.push_back(w);
       AdamSeg b;
@@ -359,6 +367,7 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
       b.opt = opt;
       b.goff = static_cast<int>(ly.b_off);
       b.gpart = ly.dw0_part;
+      b.gp_off = static_cast<int>(g.floats + OPRL_GRAD_TAIL + ly.dw0_part_off);
       b.gp_ones = ly.dw0_ones;
       b.w_rows = ly.Np;   // (no tiled copies of a bias: only the deferred-gradient path reads these two)
       b.wt_rows = ly.Kp;
@@ -439,14 +448,17 @@ static void launch_adam(oprl_engine* e, Group& g, int mode, cudaStream_t st, boo
   dim3 grid(g.n_blocks);
   const int group = (&g == &e->grp[OPRL_NET_ACTOR]) ? 0 : 1;
   const AdamArenas ar{g.theta, g.grad, g.m, g.v, g.target};
-  if (g.adam_smem)
-    launch_k(adam_kernel<true>, grid, dim3(kAdamThreads), static_cast<size_t>(g.adam_smem), st,
-             static_cast<const AdamSeg*>(g.d_segs), static_cast<const int2*>(g.d_blocks), ar, make_hyper(e->cfg),
-             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt, gp_mt);
-  else
-    launch_k(adam_kernel<false>, grid, dim3(kAdamThreads), 0, st, static_cast<const AdamSeg*>(g.d_segs),
-             static_cast<const int2*>(g.d_blocks), ar, make_hyper(e->cfg),
-             static_cast<const DevState*>(e->d_state), mode, make_comm(e, group, exit_barrier), lt, gp_mt);
+  const CommArgs cm = make_comm(e, group, exit_barrier);
+  const AdamSeg* segs = g.d_segs;
+  const int2* blocks = g.d_blocks;
+  const DevState* ds = e->d_state;
+  const AdamHyper hp = make_hyper(e->cfg);
+  const size_t smem = static_cast<size_t>(g.adam_smem);
+  // four instantiations: {element-wise, 32 x 32 patches} x {single learner, in-kernel all-reduce}
+  if (g.adam_smem && cm.world > 1) launch_k(adam_kernel<true, true>, grid, dim3(kAdamThreads), smem, st, segs, blocks, ar, hp, ds, mode, cm, lt, gp_mt);
+  else if (g.adam_smem) launch_k(adam_kernel<true, false>, grid, dim3(kAdamThreads), smem, st, segs, blocks, ar, hp, ds, mode, cm, lt, gp_mt);
+  else if (cm.world > 1) launch_k(adam_kernel<false, true>, grid, dim3(kAdamThreads), smem, st, segs, blocks, ar, hp, ds, mode, cm, lt, gp_mt);
+  else launch_k(adam_kernel<false, false>, grid, dim3(kAdamThreads), smem, st, segs, blocks, ar, hp, ds, mode, cm, lt, gp_mt);
 }
 
 // --------------------------------------------------------------- program builder
@@ -611,7 +623,10 @@ struct Builder {
           // single learner: leave the sum over M tiles to the Adam kernel (no arrival ticket, no last-CTA pass on
           // the chain); data-parallel peers read the gradient ARENA, so there the epilogue finishes the job
           static const bool defer_on = !(getenv("OPRL_B200_DW0_DEFER") && atoi(getenv("OPRL_B200_DW0_DEFER")) == 0);
-          if (defer_on && e->cfg.world_size == 1 && !e->comm.connected && lp.dw0_part && o.dw0_ones == lp.dw0_ones &&
+          // (fused data-parallel path: the partials live behind the exported gradient arena and every rank adds
+          // every rank's; the NCCL baseline all-reduces the arena tensor, so there the epilogue finishes the job)
+          const bool single = e->cfg.world_size == 1 && !e->comm.connected;
+          if (defer_on && (single || e->comm.connected) && lp.dw0_part && o.dw0_ones == lp.dw0_ones &&
               Bp / kBM <= kDeferMaxMt) {
             o.dw0_part = lp.dw0_part;
             o.dw0_defer = 1;
@@ -2551,7 +2566,7 @@ int oprl_comm_init(oprl_engine* e, int rank, int world, void* handles_out) {
   cm.rank = rank;
   cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(handles_out);
   for (int k = 0; k < 2; ++k) {
-    if (!cm.grad[k]) cm.grad[k] = e->alloc_floats(e->grp[k].floats + OPRL_GRAD_TAIL);
+    if (!cm.grad[k]) cm.grad[k] = e->alloc_floats(e->grp[k].floats + OPRL_GRAD_TAIL + e->grp[k].part_floats);
     CU(cudaIpcGetMemHandle(&h[k], cm.grad[k]));
   }
   if (!cm.flags) {
@@ -2593,8 +2608,11 @@ int oprl_comm_connect(oprl_engine* e, const void* all_handles, const int* device
   }
   // gradients are produced straight into the exported arenas from now on
   for (int k = 0; k < 2; ++k) {
-    e->grp[k].grad = cm.grad[k];
-    upload_segs(e, e->grp[k], k);
+    Group& g = e->grp[k];
+    g.grad = cm.grad[k];
+    for (auto& net : g.nets)  // deferred layer-0 partials move behind the exported arena (peers add them too)
+      if (net.L[0].dw0_part_own) net.L[0].dw0_part = cm.grad[k] + g.floats + OPRL_GRAD_TAIL + net.L[0].dw0_part_off;
+    upload_segs(e, g, k);
   }
   cm.connected = true;
   e->cfg.world_size = cm.world;

@@ -472,6 +472,7 @@ struct AdamSeg {
   // tiled column of the element (weights) or gp_ones (the bias, whose gradient rides in a pad column of the same
   // product).  nullptr: always read the gradient arena.
   const float* gpart;
+  int gp_off;  // the same partials as an offset into the (exported) gradient arena: where a data-parallel peer's copy is
   int gp_ones;
   int w_rows, wt_rows;   // padded row counts of the tiled copies W [w_rows x wt_rows], W^T [wt_rows x w_rows]
   int n, rows, cols;     // row-major [rows x cols]
@@ -555,7 +556,9 @@ struct LossTail {
 // kPatch: compiled with the 32 x 32 patch path (groups of large matrices, TQC).  The plain instantiation is what the
 // latency-bound DDPG / TD3 / SAC launches run: the patch path's extra registers (48 -> 64) alone cost 1-2 us per
 // update there (measured A/B on one box), so it is kept out of their kernel.
-template <bool kPatch>
+// kDP: compiled with the in-kernel gradient all-reduce (data-parallel learners); the single-learner instantiation
+// carries none of its registers.
+template <bool kPatch, bool kDP>
 __global__ void __launch_bounds__(kAdamThreads)
     adam_kernel(const AdamSeg* segs, const int2* blocks, const __grid_constant__ AdamArenas ar, AdamHyper hp,
                 const DevState* st, int mode, const __grid_constant__ CommArgs cm, const LossTail lt, int gp_mt) {
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(kAdamThreads)
   const int2 bt = blocks[blockIdx.x];
   const AdamSeg sg = segs[bt.x];
   ptx::pdl_wait();
-  const bool reduce = cm.world > 1 && (mode & 1);
+  const bool reduce = kDP && cm.world > 1 && (mode & 1);
   const unsigned int epoch = static_cast<unsigned int>(st->step[sg.opt]);
   if (reduce) {
     if (static_cast<int>(threadIdx.x) < cm.world) {
@@ -583,7 +586,34 @@ __global__ void __launch_bounds__(kAdamThreads)
     p = ar.theta[sg.goff + i];
     if (mode & 1) {
       float g;
-      if (reduce) {
+      if (reduce && gp_mt > 0 && sg.gpart) {
+        // deferred layer-0 gradient under data parallelism: every rank's per-M-tile partials (behind its exported
+        // arena), all requested before the first add; per rank in tile order, then the ranks in rank order --
+        // the association the non-deferred path has (epilogue: tiles, Adam: ranks)
+        int r = i, c = sg.gp_ones;
+        if (c < 0) {
+          r = i / sg.cols;
+          const int j = i - r * sg.cols;
+          c = j < sg.split ? j + sg.off_lo : j - sg.split + sg.off_hi;
+        }
+        const size_t off = static_cast<size_t>(sg.gp_off) + static_cast<size_t>(r) * sg.wt_rows + c;
+        const size_t stride = static_cast<size_t>(sg.w_rows) * sg.wt_rows;
+        g = 0.f;
+        for (int t0 = 0; t0 < gp_mt; t0 += 2) {
+          float pv[kMaxRanks][2];
+#pragma unroll
+          for (int q = 0; q < kMaxRanks; ++q)
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+              pv[q][u] = (q < cm.world && t0 + u < gp_mt) ? cm.peer_grad[q][off + (t0 + u) * stride] : 0.f;
+          // (more than two tiles per rank, batch > 256: the rank sums are continued tile pair by tile pair, which
+          // changes the association against the single-learner order by rounding only)
+#pragma unroll
+          for (int q = 0; q < kMaxRanks; ++q)
+            if (q < cm.world) g += pv[q][0] + pv[q][1];
+        }
+        ar.grad[sg.goff + i] = g;
+      } else if (reduce) {
         // every rank's copy of this element is requested before the first add: one NVLink round
         // trip instead of world - 1 dependent ones; the sum itself stays in rank order
         float gr[kMaxRanks];
