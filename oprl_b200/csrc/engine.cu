@@ -625,8 +625,11 @@ struct Builder {
           static const bool defer_on = !(getenv("OPRL_B200_DW0_DEFER") && atoi(getenv("OPRL_B200_DW0_DEFER")) == 0);
           // (fused data-parallel path: the partials live behind the exported gradient arena and every rank adds
           // every rank's; the NCCL baseline all-reduces the arena tensor, so there the epilogue finishes the job)
+          // Measured A/B, one box each: 2 GPUs 108.4 -> 104.1 us/step, 4 GPUs 112.4 -> 108.4, but 8 GPUs 122.9 -> 124.1
+          // (the layer-0 blocks of the Adam launch then pull 8 x 2 remote values per element): up to 4 ranks only.
           const bool single = e->cfg.world_size == 1 && !e->comm.connected;
-          if (defer_on && (single || e->comm.connected) && lp.dw0_part && o.dw0_ones == lp.dw0_ones &&
+          const bool dp_ok = e->comm.connected && e->comm.world <= 4;
+          if (defer_on && (single || dp_ok) && lp.dw0_part && o.dw0_ones == lp.dw0_ones &&
               Bp / kBM <= kDeferMaxMt) {
             o.dw0_part = lp.dw0_part;
             o.dw0_defer = 1;
