@@ -1,8 +1,8 @@
 """GPU: the launch-plan choices of the grouped GEMM path keep the parity bar whichever way they fall.
 
 By default `prepare_stage_tables` (csrc/engine.cu) gives launches that exceed one wave of SMs 128 x 64 tiles, may issue
-a stage as two launches when its cost model says so, and re-tiles large weight matrices in 32 x 32 patches inside the
-Adam kernel (TQC).  The SAC (batch 1024) and TQC fixtures run through those paths in tests/test_gpu_parity.py; here
+a stage as two launches when its cost model says so, re-tiles large weight matrices in 32 x 32 patches inside the
+Adam kernel (TQC), and leaves the sum over M tiles of the fused layer-0 gradient to the Adam kernel.  The SAC (batch 1024) and TQC fixtures run through those paths in tests/test_gpu_parity.py; here
 the same fixtures run with each choice switched off in a child interpreter (the switches are read once per process),
 and the plans are checked to differ the way the switches say.
 """
@@ -40,8 +40,10 @@ def test_wide_tiles_are_used_where_a_launch_exceeds_one_wave():
 
 
 @pytest.mark.parametrize("env", [{"OPRL_B200_GEMM_WIDE": "0"}, {"OPRL_B200_GEMM_PARTITION": "0"},
-                                 {"OPRL_B200_ADAM_PATCH": "0"}, {"OPRL_B200_ADAM_PATCH": "1"}],
-                         ids=["narrow-tiles", "no-partition", "adam-elementwise", "adam-patches-everywhere"])
+                                 {"OPRL_B200_ADAM_PATCH": "0"}, {"OPRL_B200_ADAM_PATCH": "1"},
+                                 {"OPRL_B200_DW0_DEFER": "0"}],
+                         ids=["narrow-tiles", "no-partition", "adam-elementwise", "adam-patches-everywhere",
+                              "dw0-sum-in-the-epilogue"])
 def test_plan_switches_hold_the_parity_bar(env):
     child_env = dict(os.environ, **env)
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-x", "-q", "-s",
