@@ -1618,7 +1618,8 @@ static LaunchPlan plan_launch(const oprl_engine* e, const GemmOp* ops, int n, bo
   // 128 x 64 tiles where the narrow tiling would not fit one wave of SMs and every op of the launch can take them
   wide = wide && narrow_tiles > e->n_sm;
   lp.nsub = wide ? 2 : 1;
-  int ks = wide ? 1 : gemm_choose_ksplit(ops, n, e->n_sm);
+  static const int max4 = getenv("OPRL_B200_KSPLIT4_MAX_CTAS") ? atoi(getenv("OPRL_B200_KSPLIT4_MAX_CTAS")) : kSplit4MaxCtas;
+  int ks = wide ? 1 : gemm_choose_ksplit(ops, n, e->n_sm, max4);
   while (ks > 1 && ks > ks_cap) ks >>= 1;
   lp.ks = ks;
   for (int i = 0; i < n; ++i) lp.tiles += gemm_tiles(ops[i], lp.nsub);

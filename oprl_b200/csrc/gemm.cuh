@@ -190,7 +190,12 @@ inline void gemm_finalize(GemmOp& o, int max_big = 7) {
 }
 // host: CTAs per tile for one launch -- the largest of {4, 2, 1} that keeps the whole launch in one
 // wave of `n_sm` single-CTA SMs and is worth the exchange (an op must have at least 2 chunks per CTA)
-inline int gemm_choose_ksplit(const GemmOp* ops, int n_ops, int n_sm) {
+// `max4`: the most CTAs a launch of 4-CTA clusters may have.  A cluster needs its 4 SMs free in ONE GPC at the same
+// time; at 32 clusters (128 CTAs on 148 SMs) some wait for a second round behind the previous kernel's last CTAs.
+// Measured (B200, one box): cap 148 -> 112: DDPG 88.2 -> 87.5, TD3 76.0 -> 72.0 us per update.  Long K loops (more
+// than 16 chunks: SAC's batch-1024 weight gradients) keep the 4-way split, there the shorter loop is worth more.
+constexpr int kSplit4MaxCtas = 112;
+inline int gemm_choose_ksplit(const GemmOp* ops, int n_ops, int n_sm, int max4 = kSplit4MaxCtas) {
   int tiles = 0, max_chunks = 0;
   for (int i = 0; i < n_ops; ++i) {
     tiles += gemm_tiles(ops[i]);
@@ -198,6 +203,7 @@ inline int gemm_choose_ksplit(const GemmOp* ops, int n_ops, int n_sm) {
   }
   for (int ks = 4; ks >= 2; ks >>= 1) {
     if (tiles * ks > n_sm) continue;
+    if (ks == 4 && tiles * ks > max4 && max_chunks <= 16) continue;
     if (max_chunks < 2 * ks) continue;
     return ks;
   }

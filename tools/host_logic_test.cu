@@ -78,8 +78,14 @@ int main() {
     CHECK(gemm_choose_ksplit(&deep, 1, 148) == 4);
     GemmOp k448 = op(128, 32, 448);  // 14 chunks
     CHECK(gemm_choose_ksplit(&k448, 1, 148) == 4);
-    GemmOp mixed[2] = {one, k32};  // the deepest op decides; the shallow one's extra ranks leave at once
+    GemmOp k32s = op(128, 256, 32);  // 8 tiles
+    GemmOp mixed[2] = {one, k32s};  // the deepest op decides; the shallow one's extra ranks leave at once (24 tiles x 4 = 96 CTAs)
     CHECK(gemm_choose_ksplit(mixed, 2, 148) == 4);
+    GemmOp two[2] = {one, one};  // 32 tiles: 4-way would be 128 CTAs = 32 clusters, above the placement cap of 112
+    CHECK(gemm_choose_ksplit(two, 2, 148) == 2);
+    GemmOp longk = op(256, 256, 1024);  // ... but a 32-chunk K loop keeps the 4-way split
+    GemmOp twolong[2] = {longk, longk};
+    CHECK(gemm_choose_ksplit(twolong, 2, 148) == 4);
     CHECK(gemm_choose_ksplit(&one, 1, 32) == 2);  // a small part: SM budget caps the split
     CHECK(gemm_choose_ksplit(&one, 1, 16) == 1);
   }
