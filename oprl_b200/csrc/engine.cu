@@ -100,6 +100,12 @@ struct Layer {
   float* dw0_part_own = nullptr;  // ... the engine's own buffer; under the fused data-parallel path dw0_part points
   size_t dw0_part_off = 0;        // dw0_part_off floats into the exported gradient arena instead (peers read it)
   int dw0_ones = -1;          // tiled pad column that carries the bias gradient in those partials (-1: none, no deferral)
+  // layers >= 1: [kDeferMaxMt][Np] per-M-tile column sums (= bias gradient partials) of the GEMM that produces dz of
+  // this layer, when that GEMM leaves the sum over M tiles to the Adam kernel too (same mechanism, same placement)
+  float* cs_part = nullptr;
+  float* cs_part_own = nullptr;
+  size_t cs_part_off = 0;
+  mutable bool cs_defer = false;  // some program of this engine produces this bias gradient that way (sticky)
 };
 struct Net {
   std::vector<Layer> L;
@@ -189,6 +195,7 @@ struct oprl_engine {
   // itself (kernels.cuh publish_state); scalars_enqueue then costs no GPU work.  OPRL_B200_HOST_SCALARS=0:
   // always the D2H copy + event.
   bool host_scalars = true;
+  bool segs_dirty = false;  // a program build marked more bias gradients as deferred: re-upload the Adam segment tables
   PubSlot* h_pub = nullptr;  // pinned [kHostRing]
   // single-learner engines only: the data-parallel programs keep the validated D2H read-back
   bool publishes() const { return host_scalars && h_pub && cfg.world_size == 1; }
@@ -322,6 +329,9 @@ static void build_group(oprl_engine* e, Group& g, int n_nets, const std::vector<
         ly.split = ly.in;
         ly.off_lo = 0;
         ly.off_hi = 0;
+        ly.cs_part = ly.cs_part_own = e->alloc_floats(static_cast<size_t>(kDeferMaxMt) * ly.Np);
+        ly.cs_part_off = g.part_floats;
+        g.part_floats += static_cast<size_t>(kDeferMaxMt) * ly.Np;
       }
       ly.w_off = off;
       off += static_cast<size_t>(ly.out) * ly.in;
@@ -371,6 +381,14 @@ static void upload_segs(oprl_engine* e, Group& g, int opt) {
       b.gp_ones = ly.dw0_ones;
       b.w_rows = ly.Np;   // (no tiled copies of a bias: only the deferred-gradient path reads these two)
       b.wt_rows = ly.Kp;
+      // (single learner only: under data parallelism the hidden-layer bias sums stay in the producing epilogues --
+      // the layer-0 deferral is the one measured there)
+      if (ly.cs_defer && !e->comm.connected) {  // bias gradient = column sums left as [M tile][Np] partials: element r of tile t at t * Np + r
+        b.gpart = ly.cs_part;
+        b.gp_off = static_cast<int>(g.floats + OPRL_GRAD_TAIL + ly.cs_part_off);
+        b.gp_ones = 0;
+        b.wt_rows = 1;
+      }
       segs.push_back(b);
       g.max_seg = std::max(g.max_seg, static_cast<size_t>(w.n));
     }
@@ -489,6 +507,37 @@ struct Builder {
   }
   float* counters(int n) { return e->alloc_floats(n); }
   // OPRL_B200_DW0_GEMM=1 keeps the layer-0 weight gradient as its own GEMM stage (cross-check / A-B)
+  // Whether this program leaves the cross-M-tile sums of `net`'s group (fused dW_0 + db_0, column sums = hidden bias
+  // gradients) to the Adam kernel.  One predicate for all of them: the Adam launch gets ONE tile count per group.
+  // Single learner, or the fused data-parallel path up to 4 ranks (measured A/B, one box each: 2 GPUs 108.4 -> 104.1
+  // us/step, 4 GPUs 112.4 -> 108.4, but 8 GPUs 122.9 -> 124.1: the layer-0 blocks of the Adam launch then pull 8 x 2
+  // remote values per element); the NCCL baseline all-reduces the arena tensor, so there the epilogues finish the job.
+  bool defers(const Net& net) const {
+    static const bool defer_on = !(getenv("OPRL_B200_DW0_DEFER") && atoi(getenv("OPRL_B200_DW0_DEFER")) == 0);
+    const bool single = e->cfg.world_size == 1 && !e->comm.connected;
+    const bool dp_ok = e->comm.connected && e->comm.world <= 4;
+    const Layer& l0 = net.L[0];
+    return defer_on && (single || dp_ok) && fuse_dw0() && l0.dw0_part && l0.dw0_ones >= 0 && w->Bp / kBM <= kDeferMaxMt;
+  }
+  // column sums of `o` = the bias gradient of layer `lp`: final sum by the op's last CTA, or left to the Adam kernel
+  void bias_colsum(GemmOp& o, const Layer& lp, float* grad, bool defer) {
+    const int Bp = w->Bp;
+    o.colsum_ld = lp.Np;
+    o.colsum_n = lp.out;
+    if (defer && lp.cs_part) {
+      o.colsum = lp.cs_part;
+      o.colsum_out = nullptr;
+      o.colsum_cnt = nullptr;
+      if (!lp.cs_defer) {
+        lp.cs_defer = true;
+        e->segs_dirty = true;
+      }
+    } else {
+      o.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * lp.Np);
+      o.colsum_out = grad + lp.b_off;
+      o.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(lp.Np / kBN));
+    }
+  }
   static bool fuse_dw0() {
     static const bool off = getenv("OPRL_B200_DW0_GEMM") && atoi(getenv("OPRL_B200_DW0_GEMM")) != 0;
     return !off;
@@ -593,18 +642,18 @@ struct Builder {
       if (want_dw) {
         ndzT = e->alloc_tm(pad128(lp.out), Bp);
         o.tt = ndzT.p; o.tt_rows = pad128(lp.out);
-        o.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * lp.Np);
-        o.colsum_ld = lp.Np;
-        o.colsum_n = lp.out;
-        o.colsum_out = grad + lp.b_off;
-        o.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(lp.Np / kBN));
-        if (l == 1 && fuse_dw0()) {
+        const bool defer = defers(net);
+        defer_mt[is_actor ? 0 : 1] = defer ? Bp / kBM : 0;
+        // db_{l-1} = column sums of this op -- except for layer 0 under a fused dW_0 with a pad column to spare: there
+        // db_0 rides in the same product (a pad column of X read as 1.0)
+        const bool fuse = l == 1 && fuse_dw0();
+        const int ones = (A4 > A) ? A : (lp.Kp > A4 + S ? A4 + S : -1);
+        if (!(fuse && ones >= 0)) bias_colsum(o, lp, grad, defer && l > 1 && !e->comm.connected);
+        if (fuse) {
           // layer-0 weight gradient dz_0^T . X in this op's epilogue instead of a 2-CTA GEMM stage
           o.dw0_x = w->X.p;
           o.dw0_kp = lp.Kp;
-          o.dw0_part = e->alloc_floats(static_cast<size_t>(Bp / kBM) * lp.Np * lp.Kp);
           o.dw0_out = grad + lp.w_off;
-          o.dw0_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(lp.Np / kBN));
           o.dw0_ld = lp.in;
           o.dw0_n = lp.out;
           o.dw0_cols = lp.Kp;
@@ -612,30 +661,15 @@ struct Builder {
           o.dw0_map_a = is_actor ? 0 : A;
           o.dw0_map_a4 = A4;
           o.dw0_map_s = S;
-          // the bias gradient db_0 rides in the same product through a pad column of X read as 1.0
-          o.dw0_ones = (A4 > A) ? A : (lp.Kp > A4 + S ? A4 + S : -1);
-          if (o.dw0_ones >= 0) {
-            o.dw0_bias_out = o.colsum_out;
-            o.colsum = nullptr;
-            o.colsum_out = nullptr;
-            o.colsum_cnt = nullptr;
-          }
-          // single learner: leave the sum over M tiles to the Adam kernel (no arrival ticket, no last-CTA pass on
-          // the chain); data-parallel peers read the gradient ARENA, so there the epilogue finishes the job
-          static const bool defer_on = !(getenv("OPRL_B200_DW0_DEFER") && atoi(getenv("OPRL_B200_DW0_DEFER")) == 0);
-          // (fused data-parallel path: the partials live behind the exported gradient arena and every rank adds
-          // every rank's; the NCCL baseline all-reduces the arena tensor, so there the epilogue finishes the job)
-          // Measured A/B, one box each: 2 GPUs 108.4 -> 104.1 us/step, 4 GPUs 112.4 -> 108.4, but 8 GPUs 122.9 -> 124.1
-          // (the layer-0 blocks of the Adam launch then pull 8 x 2 remote values per element): up to 4 ranks only.
-          const bool single = e->cfg.world_size == 1 && !e->comm.connected;
-          const bool dp_ok = e->comm.connected && e->comm.world <= 4;
-          if (defer_on && (single || dp_ok) && lp.dw0_part && o.dw0_ones == lp.dw0_ones &&
-              Bp / kBM <= kDeferMaxMt) {
+          o.dw0_ones = ones;
+          if (ones >= 0) o.dw0_bias_out = grad + lp.b_off;
+          if (defer) {
+            // the sum over M tiles is left to the Adam kernel (no arrival ticket, no last-CTA pass on the chain)
             o.dw0_part = lp.dw0_part;
             o.dw0_defer = 1;
-            defer_mt[is_actor ? 0 : 1] = Bp / kBM;
           } else {
-            defer_mt[is_actor ? 0 : 1] = 0;
+            o.dw0_part = e->alloc_floats(static_cast<size_t>(Bp / kBM) * lp.Np * lp.Kp);
+            o.dw0_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(lp.Np / kBN));
           }
           dw0_fused = true;
         }
@@ -1337,11 +1371,7 @@ static void build_ddpg_td3(oprl_engine* e, oprl_engine::Work* w, Program* p) {
     dx.t = dza.p; dx.t_rows = Bp; dx.t_c0 = 0; dx.t_n = A;
     dx.tt = dzaT.p; dx.tt_rows = dzaT.rows;
     dx.n_valid = A;  // columns >= A of this tile are pad / state gradients: drop them
-    dx.colsum = e->alloc_floats(static_cast<size_t>(Bp / kBM) * a_last.Np);
-    dx.colsum_ld = a_last.Np;
-    dx.colsum_n = a_last.out;
-    dx.colsum_out = ga.grad + a_last.b_off;
-    dx.colsum_cnt = reinterpret_cast<unsigned int*>(e->alloc_floats(a_last.Np / kBN));
+    b.bias_colsum(dx, a_last, ga.grad, b.defers(ga.nets[0]) && !e->comm.connected);  // db of the actor's last layer
     s = b.backward(s, gc.nets[0], nullptr, p_cq, Dm, TM{nullptr, 0, 0}, w->XT, false, false, &dx, l_start);
     // actor backward
     s = b.backward(s, ga.nets[0], ga.grad, p_a, dza, dzaT, w->XT, true, true, nullptr);
@@ -1786,6 +1816,10 @@ static Program* get_program(oprl_engine* e, oprl_engine::Work* w, int flags) {
   try {
     if (e->cfg.algo == OPRL_ALGO_DDPG || e->cfg.algo == OPRL_ALGO_TD3) build_ddpg_td3(e, w, p.get());
     else build_sac_tqc(e, w, p.get());
+    if (e->segs_dirty) {
+      for (int k = 0; k < 2; ++k) upload_segs(e, e->grp[k], k);
+      e->segs_dirty = false;
+    }
     prepare_stage_tables(e, p.get());
   } catch (...) {
     e->alloc_scope = nullptr;
@@ -2611,14 +2645,18 @@ int oprl_comm_connect(oprl_engine* e, const void* all_handles, const int* device
     cm.peer_flags[r] = static_cast<unsigned int*>(p[2]);
   }
   // gradients are produced straight into the exported arenas from now on
+  cm.connected = true;  // (before the segment tables are rebuilt: they depend on it)
   for (int k = 0; k < 2; ++k) {
     Group& g = e->grp[k];
     g.grad = cm.grad[k];
     for (auto& net : g.nets)  // deferred layer-0 partials move behind the exported arena (peers add them too)
+    {
       if (net.L[0].dw0_part_own) net.L[0].dw0_part = cm.grad[k] + g.floats + OPRL_GRAD_TAIL + net.L[0].dw0_part_off;
+      for (auto& ly : net.L)
+        if (ly.cs_part_own) ly.cs_part = cm.grad[k] + g.floats + OPRL_GRAD_TAIL + ly.cs_part_off;
+    }
     upload_segs(e, g, k);
   }
-  cm.connected = true;
   e->cfg.world_size = cm.world;
   for (auto& kv : e->work) kv.second->prog.clear();
   return 0;
