@@ -2649,8 +2649,9 @@ int oprl_comm_connect(oprl_engine* e, const void* all_handles, const int* device
   for (int k = 0; k < 2; ++k) {
     Group& g = e->grp[k];
     g.grad = cm.grad[k];
-    for (auto& net : g.nets)  // deferred layer-0 partials move behind the exported arena (peers add them too)
-    {
+    // deferred-gradient partials move behind the exported arena (peers add the layer-0 ones too; the column-sum
+    // partials are not used under data parallelism, they just keep one placement rule)
+    for (auto& net : g.nets) {
       if (net.L[0].dw0_part_own) net.L[0].dw0_part = cm.grad[k] + g.floats + OPRL_GRAD_TAIL + net.L[0].dw0_part_off;
       for (auto& ly : net.L)
         if (ly.cs_part_own) ly.cs_part = cm.grad[k] + g.floats + OPRL_GRAD_TAIL + ly.cs_part_off;
